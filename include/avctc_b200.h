@@ -1,0 +1,109 @@
+/*
+ * avctc_b200.h — C ABI of libavctc_b200.so: the B200 (sm_100a) implementation of the AV-CTC hot path
+ * of limeorange1102/multimodal-av-model.
+ *
+ * The reference has no FFI/operator interface of its own (it is pure Python over PyTorch, SURVEY.md
+ * §8b); each entry point below replaces the PyTorch op (or Python loop) the reference reaches at the
+ * cited call site.  Conventions (SURVEY.md §8b "C-ABI underneath"):
+ *   - plain pointers + sizes only, no torch types; every pointer is DEVICE memory unless it says host
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library never allocates device
+ *     memory, never frees, never retains pointers, and never synchronises the host
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*)
+ *   - return 0 on success, a negative avctc_status on bad arguments, or a positive cudaError_t passed
+ *     through; nothing throws across the boundary (the Python host raises RuntimeError)
+ *   - dtype enums: AVCTC_F32 = 0, AVCTC_BF16 = 1
+ */
+#ifndef AVCTC_B200_H_
+#define AVCTC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define AVCTC_API __attribute__((visibility("default")))
+#else
+#define AVCTC_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    AVCTC_OK = 0,
+    AVCTC_ERR_BAD_ARG = -1,       /* null pointer, negative size, bad enum */
+    AVCTC_ERR_UNSUPPORTED = -2,   /* shape outside what the kernels are built for */
+    AVCTC_ERR_WORKSPACE = -3,     /* workspace_bytes too small */
+    AVCTC_ERR_ALIGNMENT = -4      /* pointer/stride alignment requirement violated */
+} avctc_status;
+
+enum { AVCTC_F32 = 0, AVCTC_BF16 = 1 };
+enum { AVCTC_REDUCE_NONE = 0, AVCTC_REDUCE_MEAN = 1, AVCTC_REDUCE_SUM = 2 };
+
+/* Library identification / build check. Returns e.g. "avctc_b200 0.1 sm_100a". Host pointer. */
+AVCTC_API const char* avctc_version(void);
+/* Human-readable text for a status returned by any entry point (host pointer, static storage). */
+AVCTC_API const char* avctc_status_string(int status);
+/* Tuning knobs for benchmarking (host-side process-global ints; not needed for correctness).
+ * key: "ctc_k" (states per lane: 0 = auto, 2/4/8/16), "beam_fast" (1 = threshold top-k fast path). */
+AVCTC_API int avctc_set_tuning(const char* key, int value);
+
+/* ------------------------------------------------------------------------------------------------
+ * CTC loss — replaces nn.CTCLoss(blank, zero_infinity=True) = ATen _ctc_loss/_ctc_loss_backward
+ *   constructed /root/reference/model/trainer.py:25 (also model/decoder.py:12)
+ *   called      /root/reference/model/trainer.py:116-117, 224-225; model/decoder.py:28-33
+ * log_probs is the [T,B,V] VIEW the reference passes (a transpose of [B,T,V]): element (t,b,c) at
+ * log_probs[t*stride_t + b*stride_b + c] (strides in elements, class stride must be 1).
+ * targets: int64, sample b's labels start at targets[b*target_stride] (2-D padded) or at
+ * targets[target_offsets[b]] when target_offsets != NULL (1-D concatenated).  Lengths are int64 DEVICE
+ * tensors and are read on the device (no host sync; values are clamped to [0,T] / [0,max_target_len]).
+ * ---------------------------------------------------------------------------------------------- */
+AVCTC_API size_t avctc_ctc_workspace_bytes(int T, int B, int max_target_len);
+
+/* alpha (and, when need_grad != 0, beta) lattice scan.  Writes nll[b] (fp32, +inf when infeasible)
+ * and fills `workspace` for avctc_ctc_backward. */
+AVCTC_API int avctc_ctc_forward(const void* log_probs, int dtype, int64_t stride_t, int64_t stride_b,
+                      int T, int B, int V,
+                      const int64_t* targets, int64_t target_stride, const int64_t* target_offsets,
+                      const int64_t* input_lengths, const int64_t* target_lengths,
+                      int max_target_len, int blank, int need_grad,
+                      float* nll, void* workspace, size_t workspace_bytes, void* stream);
+
+/* loss[0] = reduction over nll (mean: mean_b(nll_b / max(L_b,1)); sum), with inf -> 0 first when
+ * zero_infinity.  For AVCTC_REDUCE_NONE writes loss[b] (B floats). */
+AVCTC_API int avctc_ctc_reduce(const float* nll, const int64_t* target_lengths, int B, int reduction,
+                     int zero_infinity, float* loss, void* stream);
+
+/* grad[T,B,V] (contiguous, dtype = log_probs dtype) = d loss / d log_probs in ATen's softmax-folded
+ * convention: (exp(lp) - posterior) * g_b for t < input_length, 0 elsewhere and 0 for infeasible
+ * samples when zero_infinity.  g_b = grad_out[b*grad_out_stride] * (mean: 1/(B*max(L_b,1)); else 1);
+ * grad_out is a DEVICE fp32 scalar (stride 0) or [B] vector. */
+AVCTC_API int avctc_ctc_backward(const void* log_probs, int dtype, int64_t stride_t, int64_t stride_b,
+                       int T, int B, int V,
+                       const int64_t* targets, int64_t target_stride, const int64_t* target_offsets,
+                       const int64_t* input_lengths, const int64_t* target_lengths,
+                       int max_target_len, int blank, int reduction, int zero_infinity,
+                       const float* nll, const float* grad_out, int64_t grad_out_stride,
+                       void* grad, const void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Beam-search decode — replaces simple_beam_search(log_probs[T,V], beam_width, blank)
+ *   /root/reference/beam_search.py:2-42, called per utterance at model/trainer.py:230,237
+ * Batched: one CTA per utterance.  log_probs fp32, utterance n frame t class c at
+ * log_probs[n*stride_n + t*stride_t + c].  lengths (int64 device, may be NULL = all T frames, which is
+ * what the reference does) gives the number of frames to decode per utterance.
+ * out_ids[n*T .. ] int32 receives the collapsed token ids, out_len[n] their count.
+ * Token lists are bit-exact with the reference on CPU, including torch.topk's tie order.
+ * Optional debug export (may be NULL): final beam scores dbg_scores[n*beam + i] (double) and raw
+ * (uncollapsed) best-beam-first paths dbg_paths[(n*beam + i)*T + t] (int32).
+ * ---------------------------------------------------------------------------------------------- */
+AVCTC_API size_t avctc_beam_workspace_bytes(int N, int T, int V, int beam);
+AVCTC_API int avctc_beam_search(const float* log_probs, int64_t stride_n, int64_t stride_t, int N, int T, int V,
+                      const int64_t* lengths, int beam, int blank,
+                      int32_t* out_ids, int32_t* out_len, double* dbg_scores, int32_t* dbg_paths,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVCTC_B200_H_ */

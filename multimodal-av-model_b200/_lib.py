@@ -1,0 +1,80 @@
+"""ctypes binding of libavctc_b200.so (the C ABI declared in include/avctc_b200.h).
+
+There is NO CPU fallback: if the shared library is missing or a call fails, a RuntimeError is raised
+(the reference trainer's `except Exception: continue`, /root/reference/model/trainer.py:162-164, then
+behaves as it does for a failing PyTorch op).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libavctc_b200.so")
+_lib = None
+
+F32, BF16 = 0, 1
+REDUCTION = {"none": 0, "mean": 1, "sum": 2}
+
+_vp, _i, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/avctc_b200.h declares
+SIGNATURES = {
+    "avctc_version": (ctypes.c_char_p, []),
+    "avctc_status_string": (ctypes.c_char_p, [_i]),
+    "avctc_set_tuning": (_i, [ctypes.c_char_p, _i]),
+    "avctc_ctc_workspace_bytes": (_sz, [_i, _i, _i]),
+    "avctc_ctc_forward": (_i, [_vp, _i, _i64, _i64, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _i, _i, _i,
+                               _vp, _vp, _sz, _vp]),
+    "avctc_ctc_reduce": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "avctc_ctc_backward": (_i, [_vp, _i, _i64, _i64, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i,
+                                _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "avctc_beam_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "avctc_beam_search": (_i, [_vp, _i64, _i64, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+}
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback for the AV-CTC hot path.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = lib().avctc_status_string(int(status)).decode()
+        raise RuntimeError(f"{what} failed: {msg} (status {status})")
+
+
+def dtype_enum(t) -> int:
+    import torch
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise RuntimeError(f"unsupported dtype {t.dtype}: the sm_100a kernels take float32 or bfloat16")
+
+
+def stream_ptr(device) -> int:
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the AV-CTC hot path has no CPU implementation "
+                           "(the CPU restatement under oracle/ is test infrastructure only)")
+
+
+def set_tuning(key: str, value: int) -> None:
+    check(lib().avctc_set_tuning(key.encode(), int(value)), f"avctc_set_tuning({key})")

@@ -1,0 +1,365 @@
+// beam_search.cu — batched beam-search decode for sm_100a, one CTA (one warp) per utterance.
+//
+// Replaces simple_beam_search(log_probs[T,V], beam_width, blank) (/root/reference/beam_search.py:2-42),
+// which the reference calls once per utterance from a Python loop (model/trainer.py:229-242) at a cost
+// of one torch.topk launch and 2*k*n_beams .item() host syncs per frame.
+//
+// Exact semantics kept:
+//   * per frame: torch.topk(row, k) INCLUDING the CPU kernel's tie order (libstdc++ std::partial_sort
+//     with the comparator of ATen/native/TopKImpl.h:56-58, used when k*64 <= V)
+//   * every beam extended by the k tokens in order; scores are fp64 = score + double(log_p)
+//   * prune = stable sort by score descending (ties keep insertion order: beam-major, k-minor)
+//   * result = CTC collapse of beams[0] where `prev` is updated on every frame, blank included
+//
+// Per frame the warp (1) finds the top-(k+1) with a threshold pass (lane maxima -> (k+1)-th largest ->
+// compaction -> rank); when those k+1 values are pairwise distinct and NaN-free the top-k is unique and
+// any algorithm agrees with torch.  Otherwise (2) it runs the literal libstdc++ heap-select/sort-heap on
+// the shared-memory row (one lane owns the heap, the warp scans ahead with ballots).  (3) Only the
+// (b+1)(j+1) <= beam candidates can survive the prune (every (b',j') <= (b,j) sorts first), so <= ~beam*ln
+// candidates are ranked by counting, scores in fp64, back-pointers kept per frame.  Rows are staged
+// through a 3-deep cp.async ring so the T-step recurrence never waits on HBM.
+#include "common.cuh"
+
+namespace avctc {
+
+constexpr int kBeamMax = 32;       // beam widths supported by the kernel
+constexpr int kCandMax = 64;       // fast-path candidate list
+constexpr int kRowBufs = 3;
+constexpr int kBpSmemBytes = 24 * 1024;
+
+struct BeamParams {
+    const float* lp; int64_t stride_n, stride_t;
+    int N, T, V;
+    const int64_t* lengths;
+    int beam, blank, fast;
+    int32_t* out_ids; int32_t* out_len; double* dbg_scores; int32_t* dbg_paths;
+    uint32_t* bp_global;   // [N][T][beam] when back-pointers do not fit shared memory, else nullptr
+    int32_t* path_ws;      // [N][T]
+    int* status;           // device int, set to 1 on an unsupported tie (k*64 > V path)
+    int row_floats;        // smem floats per staged row
+    int n_enum;            // number of (b,j) candidate pairs
+};
+
+__device__ __forceinline__ bool ranks_before(float x, float y) {  // TopKImpl.h:56-58
+    return ((x != x) && !(y != y)) || (x > y);
+}
+
+// libstdc++ std::__adjust_heap + std::__push_heap on (value,index) pairs with comp = ranks_before.
+__device__ void adjust_heap(volatile float* hv, volatile int* hi, int hole, int len, float val, int vidx) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (ranks_before(hv[child], hv[child - 1])) child--;
+        hv[hole] = hv[child]; hi[hole] = hi[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        hv[hole] = hv[child - 1]; hi[hole] = hi[child - 1];
+        hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;
+    while (hole > top && ranks_before(hv[parent], val)) {
+        hv[hole] = hv[parent]; hi[hole] = hi[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    hv[hole] = val; hi[hole] = vidx;
+}
+
+// exact std::partial_sort(queue, queue+k, queue+V, ranks_before) -> (tv,ti)[0..k)
+__device__ void topk_exact(const float* row, int V, int k, volatile float* tv, volatile int* ti, int lane) {
+    if (lane == 0) {
+        for (int j = 0; j < k; ++j) { tv[j] = row[j]; ti[j] = j; }
+        if (k >= 2) {  // std::__make_heap
+            int parent = (k - 2) / 2;
+            while (true) {
+                const float v = tv[parent]; const int vi = ti[parent];
+                adjust_heap(tv, ti, parent, k, v, vi);
+                if (parent == 0) break;
+                parent--;
+            }
+        }
+    }
+    __syncwarp();
+    for (int i0 = k; i0 < V; i0 += 32) {  // std::__heap_select, warp looks 32 elements ahead
+        const int i = i0 + lane;
+        const float v = (i < V) ? row[i] : 0.f;
+        float top = tv[0];
+        unsigned m = __ballot_sync(kFullMask, i < V && ranks_before(v, top));
+        while (m) {
+            const int l = __ffs(m) - 1;
+            const float pv = __shfl_sync(kFullMask, v, l);
+            if (lane == 0) adjust_heap(tv, ti, 0, k, pv, i0 + l);   // std::__pop_heap(first, middle, i)
+            __syncwarp();
+            top = tv[0];
+            m = __ballot_sync(kFullMask, i < V && lane > l && ranks_before(v, top));
+        }
+    }
+    if (lane == 0) {  // std::__sort_heap
+        int last = k;
+        while (last > 1) {
+            --last;
+            const float v = tv[last]; const int vi = ti[last];
+            tv[last] = tv[0]; ti[last] = ti[0];
+            adjust_heap(tv, ti, 0, last, v, vi);
+        }
+    }
+    __syncwarp();
+}
+
+// threshold top-k; returns false when the result is not provably tie-free (caller runs topk_exact)
+__device__ bool topk_fast(const float* row, int V, int k, float* cv, int* ci, volatile float* tv,
+                          volatile int* ti, int lane) {
+    if (k + 1 > 32 || V < k + 1) return false;
+    float ml = AVCTC_NEG_INF;
+    bool bad = false;
+    for (int c = lane; c < V; c += 32) {
+        const float v = row[c];
+        bad |= (v != v);
+        ml = fmaxf(ml, v);
+    }
+    if (__any_sync(kFullMask, bad)) return false;
+    // (k+1)-th largest lane maximum: a lower bound of the (k+1)-th largest element
+    int rank = 0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+        const float o = __shfl_sync(kFullMask, ml, j);
+        rank += (o > ml) || (o == ml && j < lane);
+    }
+    const unsigned who = __ballot_sync(kFullMask, rank == k);
+    const float tau = __shfl_sync(kFullMask, ml, __ffs(who) - 1);
+    // compaction of everything >= tau
+    int count = 0;
+    for (int c0 = 0; c0 < V; c0 += 32) {
+        const int c = c0 + lane;
+        const float v = (c < V) ? row[c] : AVCTC_NEG_INF;
+        const bool take = (c < V) && (v >= tau);
+        const unsigned m = __ballot_sync(kFullMask, take);
+        const int pos = count + __popc(m & ((1u << lane) - 1));
+        if (take && pos < kCandMax) { cv[pos] = v; ci[pos] = c; }
+        count += __popc(m);
+    }
+    if (count > kCandMax || count < k + 1) return false;
+    __syncwarp();
+    // rank the candidates (value desc, index asc); keep ranks 0..k
+    for (int i = lane; i < count; i += 32) {
+        const float v = cv[i]; const int idx = ci[i];
+        int r = 0;
+        for (int j = 0; j < count; ++j) {
+            const float o = cv[j];
+            r += (o > v) || (o == v && ci[j] < idx);
+        }
+        if (r <= k) { tv[r] = v; ti[r] = idx; }
+    }
+    __syncwarp();
+    const bool tie = (lane < k) && (tv[lane] == tv[lane + 1]);
+    if (__any_sync(kFullMask, tie)) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(32) beam_search_kernel(const BeamParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = blockIdx.x, lane = threadIdx.x;
+    const int k = p.beam;
+    // ---- shared memory carve-up
+    float* rows = reinterpret_cast<float*>(smem_raw);                       // kRowBufs * row_floats
+    double* score = reinterpret_cast<double*>(rows + kRowBufs * p.row_floats);  // 2 * kBeamMax
+    double* cand_s = score + 2 * kBeamMax;                                  // n_enum
+    float* cv = reinterpret_cast<float*>(cand_s + p.n_enum);               // kCandMax
+    int* ci = reinterpret_cast<int*>(cv + kCandMax);                        // kCandMax
+    float* tv = reinterpret_cast<float*>(ci + kCandMax);                    // kBeamMax + 1
+    int* ti = reinterpret_cast<int*>(tv + kBeamMax + 1);                    // kBeamMax + 1
+    unsigned char* en_b = reinterpret_cast<unsigned char*>(ti + kBeamMax + 1);  // n_enum
+    unsigned char* en_j = en_b + p.n_enum;                                  // n_enum
+    uint32_t* bp_s = reinterpret_cast<uint32_t*>(
+        (reinterpret_cast<uintptr_t>(en_j + p.n_enum) + 15) & ~(uintptr_t)15);
+
+    long long fl = p.lengths ? p.lengths[n] : p.T;
+    const int frames = (int)(fl < 0 ? 0 : (fl > p.T ? p.T : fl));
+    uint32_t* bp = p.bp_global ? p.bp_global + (size_t)n * p.T * k : bp_s;
+    int32_t* path = p.path_ws + (size_t)n * p.T;
+    const float* base = p.lp + (int64_t)n * p.stride_n;
+
+    // candidate enumeration in insertion order (beam-major, k-minor); (b+1)(j+1) <= beam
+    if (lane == 0) {
+        int m = 0;
+        for (int b = 0; b < k; ++b)
+            for (int j = 0; j < k; ++j)
+                if ((b + 1) * (j + 1) <= k) { en_b[m] = (unsigned char)b; en_j[m] = (unsigned char)j; ++m; }
+        score[0] = 0.0;
+    }
+    int nb = 1, cur = 0;
+    int o_in[kRowBufs];
+#pragma unroll
+    for (int i = 0; i < kRowBufs; ++i) o_in[i] = 0;
+#pragma unroll
+    for (int i = 0; i < kRowBufs - 1; ++i) {
+        if (i < frames) o_in[i] = stage_row(base + (int64_t)i * p.stride_t, p.V, rows + i * p.row_floats, lane);
+        else cp_async_commit();
+    }
+    __syncwarp();
+
+    for (int t = 0; t < frames; ++t) {
+        // prefetch frame t + kRowBufs - 1 into the buffer frame t-1 just vacated
+        {
+            const int tn = t + kRowBufs - 1;
+            const int bi = tn % kRowBufs;
+            int o = 0;
+            if (tn < frames) o = stage_row(base + (int64_t)tn * p.stride_t, p.V, rows + bi * p.row_floats, lane);
+            else cp_async_commit();
+#pragma unroll
+            for (int i = 0; i < kRowBufs; ++i) if (i == bi) o_in[i] = o;
+        }
+        cp_async_wait<kRowBufs - 1>();
+        __syncwarp();
+        int ob = 0;
+#pragma unroll
+        for (int i = 0; i < kRowBufs; ++i) if (i == t % kRowBufs) ob = o_in[i];
+        const float* row = rows + (t % kRowBufs) * p.row_floats + ob;
+
+        bool ok = false;
+        if (p.fast) ok = topk_fast(row, p.V, k, cv, ci, tv, ti, lane);
+        if (!ok) {
+            if ((long long)k * 64 > p.V) { if (lane == 0) *p.status = 1; }
+            topk_exact(row, p.V, k, tv, ti, lane);
+        }
+        // ---- expand + prune
+        int M = 0;  // candidates: prefix of the enumeration with b < nb
+        for (int m0 = 0; m0 < p.n_enum; m0 += 32) {
+            const int m = m0 + lane;
+            const bool in = (m < p.n_enum) && (en_b[m] < nb);
+            M += __popc(__ballot_sync(kFullMask, in));
+        }
+        // enumeration is beam-major, so the b < nb entries are exactly the first M
+        const double* sc = score + cur * kBeamMax;
+        double* sn = score + (cur ^ 1) * kBeamMax;
+        for (int m = lane; m < M; m += 32) cand_s[m] = sc[en_b[m]] + (double)tv[en_j[m]];
+        __syncwarp();
+        const int keep = min(k, M);
+        for (int m = lane; m < M; m += 32) {
+            const double s = cand_s[m];
+            int r = 0;
+            for (int q = 0; q < M; ++q) {
+                const double o = cand_s[q];
+                r += (o > s) || (o == s && q < m);
+            }
+            if (r < keep) {
+                sn[r] = s;
+                bp[(size_t)t * k + r] = ((uint32_t)en_b[m] << 24) | (uint32_t)ti[en_j[m]];
+            }
+        }
+        __syncwarp();
+        cur ^= 1;
+        nb = keep;
+    }
+    cp_async_wait<0>();
+
+    // ---- back-track (lane i walks beam i; only beam 0 is the result) and CTC-collapse
+    if (frames > 0) {
+        const bool dbg = (p.dbg_paths != nullptr);
+        if (lane == 0 || (dbg && lane < nb)) {
+            int32_t* dst = dbg ? p.dbg_paths + ((size_t)n * k + lane) * p.T : path;
+            int idx = lane;
+            for (int t = frames - 1; t >= 0; --t) {
+                const uint32_t e = bp[(size_t)t * k + idx];
+                dst[t] = (int32_t)(e & 0xffffffu);
+                idx = (int)(e >> 24);
+            }
+            if (dbg && lane == 0)
+                for (int t = 0; t < frames; ++t) path[t] = dst[t];
+        }
+        if (p.dbg_scores && lane < nb) p.dbg_scores[(size_t)n * k + lane] = score[cur * kBeamMax + lane];
+    }
+    __syncwarp();
+    __threadfence_block();
+    int count = 0;
+    int32_t* out = p.out_ids + (size_t)n * p.T;
+    for (int t0 = 0; t0 < frames; t0 += 32) {
+        const int t = t0 + lane;
+        bool keepit = false;
+        int c = 0;
+        if (t < frames) {
+            c = path[t];
+            keepit = (c != p.blank) && (t == 0 || path[t - 1] != c);
+        }
+        const unsigned m = __ballot_sync(kFullMask, keepit);
+        if (keepit) out[count + __popc(m & ((1u << lane) - 1))] = c;
+        count += __popc(m);
+    }
+    if (lane == 0) p.out_len[n] = count;
+}
+
+static int enum_count(int k) {
+    int m = 0;
+    for (int b = 0; b < k; ++b)
+        for (int j = 0; j < k; ++j)
+            if ((b + 1) * (j + 1) <= k) ++m;
+    return m;
+}
+
+struct BeamPlan { size_t off_bp, off_path, off_status, total; bool bp_in_smem; size_t smem; int row_floats, n_enum; };
+
+static bool beam_plan(int N, int T, int V, int beam, BeamPlan* pl) {
+    if (beam < 1 || beam > kBeamMax || beam > V) return false;
+    pl->row_floats = (V + 8 + 3) & ~3;
+    pl->n_enum = enum_count(beam);
+    size_t fixed = (size_t)kRowBufs * pl->row_floats * 4 + 2 * kBeamMax * 8 + (size_t)pl->n_enum * 8 +
+                   kCandMax * 8 + (kBeamMax + 1) * 8 + 2 * (size_t)pl->n_enum + 16;
+    const size_t bp_bytes = (size_t)(T > 0 ? T : 1) * beam * 4;
+    pl->bp_in_smem = bp_bytes <= (size_t)kBpSmemBytes;
+    pl->smem = fixed + (pl->bp_in_smem ? bp_bytes : 0);
+    if (pl->smem > 200 * 1024) return false;
+    size_t o = 0;
+    pl->off_status = o; o += 256;
+    pl->off_path = o; o = (o + (size_t)N * (T > 0 ? T : 1) * 4 + 255) / 256 * 256;
+    pl->off_bp = o; if (!pl->bp_in_smem) o = (o + (size_t)N * bp_bytes + 255) / 256 * 256;
+    pl->total = o;
+    return true;
+}
+
+}  // namespace avctc
+
+using namespace avctc;
+
+extern "C" size_t avctc_beam_workspace_bytes(int N, int T, int V, int beam) {
+    BeamPlan pl;
+    if (N < 0 || T < 0 || V <= 0) return 0;
+    if (!beam_plan(N, T, V, beam, &pl)) return 0;
+    return pl.total;
+}
+
+extern "C" int avctc_beam_search(const float* log_probs, int64_t stride_n, int64_t stride_t, int N, int T, int V,
+                                 const int64_t* lengths, int beam, int blank, int32_t* out_ids,
+                                 int32_t* out_len, double* dbg_scores, int32_t* dbg_paths, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    if (N < 0 || T < 0 || V <= 0 || beam < 1) return AVCTC_ERR_BAD_ARG;
+    if (beam > V) return AVCTC_ERR_BAD_ARG;   // torch.topk raises "selected index k out of range"
+    if (N == 0) return AVCTC_OK;
+    if (!out_ids || !out_len || !workspace || (T > 0 && !log_probs)) return AVCTC_ERR_BAD_ARG;
+    BeamPlan pl;
+    if (!beam_plan(N, T, V, beam, &pl)) return AVCTC_ERR_UNSUPPORTED;
+    if (workspace_bytes < pl.total) return AVCTC_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 255) return AVCTC_ERR_ALIGNMENT;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    char* w = reinterpret_cast<char*>(workspace);
+    BeamParams bp;
+    bp.lp = log_probs; bp.stride_n = stride_n; bp.stride_t = stride_t;
+    bp.N = N; bp.T = T; bp.V = V; bp.lengths = lengths; bp.beam = beam; bp.blank = blank;
+    bp.fast = avctc_tuning_get("beam_fast", 1);
+    bp.out_ids = out_ids; bp.out_len = out_len; bp.dbg_scores = dbg_scores; bp.dbg_paths = dbg_paths;
+    bp.bp_global = pl.bp_in_smem ? nullptr : reinterpret_cast<uint32_t*>(w + pl.off_bp);
+    bp.path_ws = reinterpret_cast<int32_t*>(w + pl.off_path);
+    bp.status = reinterpret_cast<int*>(w + pl.off_status);
+    bp.row_floats = pl.row_floats; bp.n_enum = pl.n_enum;
+    AVCTC_CUDA_RETURN(cudaMemsetAsync(bp.status, 0, sizeof(int), st));
+    static size_t configured = 0;
+    if (pl.smem > 48 * 1024 && pl.smem > configured) {
+        AVCTC_CUDA_RETURN(cudaFuncSetAttribute(beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               200 * 1024));
+        configured = 200 * 1024;
+    }
+    beam_search_kernel<<<N, 32, pl.smem, st>>>(bp);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,665 @@
+// ctc_loss.cu — CTC loss forward/backward for sm_100a.
+//
+// Replaces nn.CTCLoss(blank, zero_infinity=True) as the reference calls it
+// (/root/reference/model/trainer.py:25,116-117,224-225; model/decoder.py:12,28-33), i.e. ATen's
+// _ctc_loss / _ctc_loss_backward, with two kernels:
+//
+//  ctc_scan_kernel  one CTA per (sample, direction).  The label-extended lattice (S = 2L+1 states) is
+//                   held in REGISTERS, K consecutive states per lane; the alpha recurrence and the beta
+//                   recurrence (run as the same recurrence on the time- and label-mirrored problem) are
+//                   two CTAs that run concurrently.  Neighbour states come from __shfl_up; when the
+//                   lattice needs more than one warp the warps form a systolic chain through a
+//                   shared-memory ring (warp w works on frame t while warp w-1 is already ahead), so the
+//                   t-loop has no __syncthreads.  Emissions are gathered D frames ahead into a register
+//                   ring.  Arithmetic is log2-domain fp32 with MUFU ex2/lg2, and every warp keeps its
+//                   lattice slice relative to a running fp64 offset (renormalised every D frames) so
+//                   |alpha| stays O(100) instead of O(T*10): that is what lets fp32 meet 1e-4 against
+//                   the fp64 reference at T=1000.
+//  ctc_grad_kernel  one WARP per (t,b) row, all SMs: streams the log-prob row in (cp.async), combines
+//                   alpha/beta into per-class posteriors (deterministic chains for repeated labels),
+//                   writes (exp(lp) - posterior) * g as aligned 16-byte stores.  HBM-bound:
+//                   algorithmic bytes = one read of log_probs + one write of grad.
+#include "common.cuh"
+
+namespace avctc {
+
+constexpr int kScanPrefetch = 8;   // D: emission prefetch depth == renormalisation period
+constexpr int kRing = 32;          // handoff ring slots between neighbouring warps
+constexpr int kMaxWarps = 16;
+constexpr int kChainNone = 0x3fffffff;
+constexpr int kChainFirst = 0x40000000;
+
+struct CtcPlan {
+    int K, W, S_pad, Lpad;
+    size_t off_alpha, off_beta, off_coff_a, off_coff_b, off_nll2, off_chain, total;
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static bool make_plan(int T, int B, int Lmax, CtcPlan* pl) {
+    const int S = 2 * Lmax + 1;
+    int K = 0, W = 0;
+    const int forced = avctc_tuning_get("ctc_k", 0);
+    if (forced == 2 || forced == 4 || forced == 8 || forced == 16) {
+        int w = (S + 32 * forced - 1) / (32 * forced);
+        if (w <= kMaxWarps) { K = forced; W = w; }
+    }
+    if (K == 0) {
+        if (S <= 64) { K = 2; W = 1; }
+        else if (S <= 128) { K = 4; W = 1; }
+        else if (S <= 512) { K = 2; W = (S + 63) / 64; }
+        else if (S <= 2048) { K = 4; W = (S + 127) / 128; }
+        else if (S <= 4096) { K = 8; W = (S + 255) / 256; }
+        else if (S <= 8192) { K = 16; W = (S + 511) / 512; }
+        else return false;
+    }
+    pl->K = K; pl->W = W; pl->S_pad = W * 32 * K; pl->Lpad = Lmax > 0 ? Lmax : 1;
+    const size_t TB = (size_t)(T > 0 ? T : 1) * (size_t)B;
+    size_t o = 0;
+    pl->off_alpha = o; o = align_up(o + TB * pl->S_pad * sizeof(float), 256);
+    pl->off_beta = o; o = align_up(o + TB * pl->S_pad * sizeof(float), 256);
+    pl->off_coff_a = o; o = align_up(o + TB * W * sizeof(double), 256);
+    pl->off_coff_b = o; o = align_up(o + TB * W * sizeof(double), 256);
+    pl->off_nll2 = o; o = align_up(o + (size_t)B * sizeof(double), 256);
+    pl->off_chain = o; o = align_up(o + (size_t)B * pl->Lpad * sizeof(int), 256);
+    pl->total = o;
+    return true;
+}
+
+struct ScanParams {
+    const void* lp; int64_t stride_t, stride_b;
+    int T, B, V;
+    const int64_t* targets; int64_t target_stride; const int64_t* target_offsets;
+    const int64_t* input_lengths; const int64_t* target_lengths;
+    int Lmax, blank, store;
+    float* nll;
+    float* alpha; float* beta; double* coff_a; double* coff_b; double* nll2; int* chain;
+    int W, S_pad, Lpad;
+};
+
+template <int K>
+__device__ __forceinline__ void store_states(float* dst, const float (&a)[K]) {
+    if constexpr (K == 2) {
+        *reinterpret_cast<float2*>(dst) = make_float2(a[0], a[1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < K / 4; ++i)
+            reinterpret_cast<float4*>(dst)[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+    }
+}
+
+template <int K, typename TIn>
+__global__ void __launch_bounds__(32 * kMaxWarps) ctc_scan_kernel(const ScanParams p) {
+    constexpr int KL = K / 2;
+    constexpr int D = (K >= 8) ? kScanPrefetch / 2 : kScanPrefetch;
+    const int b = blockIdx.x;
+    const int dir = blockIdx.y;  // 0: alpha (forward in time), 1: beta (mirrored problem)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    __shared__ float ring_v[kMaxWarps][kRing];
+    __shared__ double ring_c[kMaxWarps][kRing];
+    __shared__ int progress[kMaxWarps];
+    __shared__ double fin[2];
+
+    long long tbl = p.input_lengths[b];
+    long long tll = p.target_lengths[b];
+    const int Tb = (int)(tbl < 0 ? 0 : (tbl > p.T ? p.T : tbl));
+    const int L = (int)(tll < 0 ? 0 : (tll > p.Lmax ? p.Lmax : tll));
+    const int S = 2 * L + 1;
+    const int64_t* tgt = p.targets + (p.target_offsets ? p.target_offsets[b] : (int64_t)b * p.target_stride);
+
+    if (Tb == 0) {  // ATen: input_length 0 -> nll = 0 if L == 0 else inf
+        if (dir == 0 && tid == 0) {
+            p.nll[b] = (L == 0) ? 0.f : CUDART_INF_F;
+            if (p.nll2) p.nll2[b] = (L == 0) ? 0.0 : (double)CUDART_INF_F;
+        }
+        if (dir == 0 && p.chain)
+            for (int j = tid; j < L; j += blockDim.x) p.chain[(size_t)b * p.Lpad + j] = kChainFirst | kChainNone;
+        return;
+    }
+    if (tid < kMaxWarps) progress[tid] = 0;
+    if (tid < 2) fin[tid] = -(double)CUDART_INF_F;
+    __syncthreads();
+
+    const int Wact = (S + 32 * K - 1) / (32 * K);  // warps that own at least one real state
+    const TIn* lp = reinterpret_cast<const TIn*>(p.lp) + (int64_t)b * p.stride_b;
+    float* ws = dir ? p.beta : p.alpha;
+    double* coff = dir ? p.coff_b : p.coff_a;
+
+    if (warp < Wact) {
+        const int g = tid;             // global lane: owns (mirrored) states g*K .. g*K+K-1
+        const int nvalid = min(max(S - g * K, 0), K);
+        int lab[KL];
+        bool skip[KL];
+#pragma unroll
+        for (int i = 0; i < KL; ++i) {
+            const int j = g * KL + i;  // label position in (mirrored) order
+            lab[i] = p.blank; skip[i] = false;
+            if (j < L) {
+                long long c = tgt[dir ? (L - 1 - j) : j];
+                c = c < 0 ? 0 : (c >= p.V ? p.V - 1 : c);
+                lab[i] = (int)c;
+                if (j >= 1) {
+                    long long cp = tgt[dir ? (L - j) : (j - 1)];
+                    cp = cp < 0 ? 0 : (cp >= p.V ? p.V - 1 : cp);
+                    skip[i] = (cp != c);
+                }
+            }
+        }
+        auto row_of = [&](int tau) -> const TIn* {
+            const int t = dir ? (Tb - 1 - tau) : tau;
+            return lp + (int64_t)t * p.stride_t;
+        };
+        auto gather = [&](int tau, float& vb, float (&vl)[KL]) {
+            const TIn* row = row_of(tau);
+            vb = to_float(__ldg(row + p.blank)) * AVCTC_LOG2E;
+#pragma unroll
+            for (int i = 0; i < KL; ++i) vl[i] = to_float(__ldg(row + lab[i])) * AVCTC_LOG2E;
+        };
+
+        // ---- frame 0
+        float a[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) a[j] = AVCTC_NEG_INF;
+        {
+            float vb, vl[KL];
+            gather(0, vb, vl);
+            if (g == 0) {
+                a[0] = vb;
+                if (L > 0) a[1] = vl[0];
+            }
+        }
+        double C = 0.0;              // running offset of this warp's slice (log2 units), warp-uniform
+        bool empty = (warp > 0);     // no finite mass has entered this warp's slice yet
+        float mred = AVCTC_NEG_INF;
+        int avail = 0, cons = 0;
+
+        auto publish = [&](int tau) {
+            if (p.store) {
+                const int t = dir ? (Tb - 1 - tau) : tau;
+                const size_t rowi = (size_t)b * p.T + t;
+                store_states<K>(ws + rowi * p.S_pad + (size_t)g * K, a);
+                if (lane == 0) coff[rowi * p.W + warp] = C;
+            }
+            if (warp < Wact - 1) {
+                if (lane == 31) {
+                    const int need = tau - kRing + 2;
+                    while (cons < need) cons = ld_volatile_shared_s32(&progress[warp + 1]);
+                    const int slot = tau & (kRing - 1);
+                    *(volatile float*)&ring_v[warp][slot] = a[K - 1];
+                    *(volatile double*)&ring_c[warp][slot] = C;
+                    __threadfence_block();
+                    st_volatile_shared_s32(&progress[warp], tau + 1);
+                }
+                __syncwarp();
+            } else if (warp > 0 && lane == 0) {
+                // the last active warp still reports progress so its producer can recycle ring slots
+                st_volatile_shared_s32(&progress[warp], tau + 1);
+            }
+        };
+        publish(0);
+
+        // ---- emission prefetch ring
+        float pre_b[D], pre_l[D][KL];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            pre_b[d] = 0.f;
+#pragma unroll
+            for (int i = 0; i < KL; ++i) pre_l[d][i] = 0.f;
+            if (1 + d < Tb) gather(1 + d, pre_b[d], pre_l[d]);
+        }
+
+        for (int tau0 = 1; tau0 < Tb; tau0 += D) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const int tau = tau0 + d;
+                if (tau < Tb) {
+                    const float vb = pre_b[d];
+                    float vl[KL];
+#pragma unroll
+                    for (int i = 0; i < KL; ++i) vl[i] = pre_l[d][i];
+                    if (tau + D < Tb) gather(tau + D, pre_b[d], pre_l[d]);
+
+                    float prev_in = AVCTC_NEG_INF;
+                    if (warp > 0) {
+                        while (avail < tau) avail = ld_volatile_shared_s32(&progress[warp - 1]);
+                        __threadfence_block();
+                        const int slot = (tau - 1) & (kRing - 1);
+                        const float pv = *(volatile float*)&ring_v[warp - 1][slot];
+                        const double pc = *(volatile double*)&ring_c[warp - 1][slot];
+                        if (empty) {
+                            C = pc;  // adopt the producer's frame while this slice holds no mass
+                            if (pv > AVCTC_NEG_INF) empty = false;
+                        }
+                        prev_in = pv + (float)(pc - C);
+                    }
+                    if (d == 0) {
+                        float ml = a[0];
+#pragma unroll
+                        for (int j = 1; j < K; ++j) ml = fmaxf(ml, a[j]);
+                        mred = warp_max(ml);
+                    }
+                    const float up = __shfl_up_sync(kFullMask, a[K - 1], 1);
+                    const float prev = (lane == 0) ? prev_in : up;
+                    float nw[K];
+#pragma unroll
+                    for (int i = 0; i < KL; ++i) {
+                        const float below = (i == 0) ? prev : a[2 * i - 1];
+                        nw[2 * i] = lse2_log2(a[2 * i], below) + vb;
+                        nw[2 * i + 1] = lse3_log2(a[2 * i + 1], a[2 * i], skip[i] ? below : AVCTC_NEG_INF) + vl[i];
+                    }
+#pragma unroll
+                    for (int j = 0; j < K; ++j) a[j] = (j < nvalid) ? nw[j] : AVCTC_NEG_INF;
+                    if (d == D / 2) {
+                        if (mred > AVCTC_NEG_INF && mred < CUDART_INF_F) {
+#pragma unroll
+                            for (int j = 0; j < K; ++j) a[j] -= mred;
+                            C += (double)mred;
+                        }
+                    }
+                    publish(tau);
+                }
+            }
+        }
+        // ---- the two terminal states (mirrored index S-1 / S-2 are terminal for alpha)
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int s = g * K + j;
+            if (s == S - 1) fin[0] = (double)a[j] + C;
+            if (s == S - 2) fin[1] = (double)a[j] + C;
+        }
+    }
+    __syncthreads();
+    if (dir == 0) {
+        if (tid == 0) {
+            const double x = fin[0], y = fin[1];
+            const double m = fmax(x, y), n = fmin(x, y);
+            double ll2;
+            if (m == -(double)CUDART_INF_F) ll2 = m;
+            else ll2 = m + log2(1.0 + exp2(n - m));
+            p.nll[b] = (float)(-ll2 * AVCTC_LN2_D);
+            if (p.nll2) p.nll2[b] = -ll2;
+        }
+        if (p.chain) {
+            // repeated-label chains for the deterministic per-class posterior sum in ctc_grad_kernel
+            for (int j = tid; j < L; j += blockDim.x) {
+                const long long c = tgt[j];
+                bool first = true;
+                for (int k = 0; k < j; ++k) if (tgt[k] == c) { first = false; break; }
+                int nxt = kChainNone;
+                for (int k = j + 1; k < L; ++k) if (tgt[k] == c) { nxt = k; break; }
+                p.chain[(size_t)b * p.Lpad + j] = nxt | (first ? kChainFirst : 0);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct GradParams {
+    const void* lp; int64_t stride_t, stride_b;
+    int T, B, V;
+    const int64_t* targets; int64_t target_stride; const int64_t* target_offsets;
+    const int64_t* input_lengths; const int64_t* target_lengths;
+    int Lmax, blank, reduction, zero_infinity;
+    const float* nll; const float* grad_out; int64_t grad_out_stride;
+    void* grad;
+    const float* alpha; const float* beta; const double* coff_a; const double* coff_b;
+    const double* nll2; const int* chain;
+    int K, W, S_pad, Lpad;
+    int row_floats;   // per-warp smem floats for one staged row (>= V + 8, multiple of 4)
+    int w_floats;     // per-warp smem floats for state weights (>= 2*Lmax+1, multiple of 4)
+};
+
+template <typename T>
+struct VecTraits;
+template <>
+struct VecTraits<float> { static constexpr int kVec = 4; };
+template <>
+struct VecTraits<__nv_bfloat16> { static constexpr int kVec = 8; };
+
+__device__ __forceinline__ int stage_row(const __nv_bfloat16* grow, int V, float* buf, int lane) {
+    const int o = (int)((reinterpret_cast<uintptr_t>(grow) >> 1) & 7);
+    const int vstart = (o + 7) & ~7, vend = (o + V) & ~7;
+    auto scalar = [&](int lo, int hi) {
+        for (int pidx = lo + lane; pidx < hi; pidx += 32) buf[pidx] = __bfloat162float(grow[pidx - o]);
+    };
+    if (vstart < vend) {
+        scalar(o, vstart);
+        for (int q = vstart + 8 * lane; q < vend; q += 256) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(grow + (q - o)));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+            const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+            const float2 f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+            *reinterpret_cast<float4*>(buf + q) = make_float4(f0.x, f0.y, f1.x, f1.y);
+            *reinterpret_cast<float4*>(buf + q + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
+        }
+        scalar(vend, o + V);
+    } else {
+        scalar(o, o + V);
+    }
+    return o;
+}
+
+// write one output row from fp32 shared memory (buf[o + c], o = misalignment of the global row) or
+// zeros (buf == nullptr) with aligned 16-byte stores plus scalar head/tail.
+__device__ __forceinline__ void write_row(float* grow, int V, const float* buf, int o, int lane) {
+    const int vstart = (o + 3) & ~3, vend = (o + V) & ~3;
+    auto scalar = [&](int lo, int hi) {
+        for (int pidx = lo + lane; pidx < hi; pidx += 32) grow[pidx - o] = buf ? buf[pidx] : 0.f;
+    };
+    if (vstart < vend) {
+        scalar(o, vstart);
+        for (int q = vstart + 4 * lane; q < vend; q += 128) {
+            const float4 v = buf ? *reinterpret_cast<const float4*>(buf + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            __stcs(reinterpret_cast<float4*>(grow + (q - o)), v);
+        }
+        scalar(vend, o + V);
+    } else {
+        scalar(o, o + V);
+    }
+}
+__device__ __forceinline__ void write_row(__nv_bfloat16* grow, int V, const float* buf, int o, int lane) {
+    const int vstart = (o + 7) & ~7, vend = (o + V) & ~7;
+    auto scalar = [&](int lo, int hi) {
+        for (int pidx = lo + lane; pidx < hi; pidx += 32) grow[pidx - o] = __float2bfloat16(buf ? buf[pidx] : 0.f);
+    };
+    if (vstart < vend) {
+        scalar(o, vstart);
+        for (int q = vstart + 8 * lane; q < vend; q += 256) {
+            uint4 raw = make_uint4(0, 0, 0, 0);
+            if (buf) {
+                const float4 x = *reinterpret_cast<const float4*>(buf + q);
+                const float4 y = *reinterpret_cast<const float4*>(buf + q + 4);
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+                h[0] = __floats2bfloat162_rn(x.x, x.y); h[1] = __floats2bfloat162_rn(x.z, x.w);
+                h[2] = __floats2bfloat162_rn(y.x, y.y); h[3] = __floats2bfloat162_rn(y.z, y.w);
+            }
+            __stcs(reinterpret_cast<uint4*>(grow + (q - o)), raw);
+        }
+        scalar(vend, o + V);
+    } else {
+        scalar(o, o + V);
+    }
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) ctc_grad_kernel(const GradParams p) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int kVec = VecTraits<TIn>::kVec;
+    constexpr int NS = 6;   // states per lane whose alpha/beta loads are issued before the row lands
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    float* rowbuf = smem + (size_t)warp * (2 * p.row_floats + p.w_floats);
+    float* outbuf = rowbuf + p.row_floats;
+    float* wbuf = outbuf + p.row_floats;
+    const long long rows = (long long)p.T * p.B;
+    TIn* grad = reinterpret_cast<TIn*>(p.grad);
+    const TIn* lpbase = reinterpret_cast<const TIn*>(p.lp);
+
+    for (long long row = (long long)blockIdx.x * nwarp + warp; row < rows; row += (long long)gridDim.x * nwarp) {
+        const int t = (int)(row / p.B), b = (int)(row % p.B);
+        TIn* grow = grad + (size_t)row * p.V;
+        const int o_out = (int)((reinterpret_cast<uintptr_t>(grow) / sizeof(TIn)) & (kVec - 1));
+        long long tbl = p.input_lengths[b], tll = p.target_lengths[b];
+        const int Tb = (int)(tbl < 0 ? 0 : (tbl > p.T ? p.T : tbl));
+        const int L = (int)(tll < 0 ? 0 : (tll > p.Lmax ? p.Lmax : tll));
+        const int S = 2 * L + 1;
+        const float nllb = p.nll[b];
+        if (t >= Tb || (p.zero_infinity && nllb == CUDART_INF_F)) {
+            write_row(grow, p.V, nullptr, o_out, lane);
+            continue;
+        }
+        const TIn* lrow = lpbase + (int64_t)t * p.stride_t + (int64_t)b * p.stride_b;
+        const int o_in = stage_row(lrow, p.V, rowbuf, lane);
+
+        const int64_t* tgt = p.targets + (p.target_offsets ? p.target_offsets[b] : (int64_t)b * p.target_stride);
+        float scale = p.grad_out[(int64_t)b * p.grad_out_stride];
+        if (p.reduction == AVCTC_REDUCE_MEAN) scale /= ((float)p.B * (float)(L > 1 ? L : 1));
+        const size_t rowi = (size_t)b * p.T + t;
+        const float* arow = p.alpha + rowi * p.S_pad;
+        const float* brow = p.beta + rowi * p.S_pad;
+        const double* ca = p.coff_a + rowi * p.W;
+        const double* cb = p.coff_b + rowi * p.W;
+        const double nll2 = p.nll2[b];
+        const int perw = 32 * p.K;
+
+        // log2 of alpha_t(s)*beta_t(s)/P, offsets folded in fp64; loads issued before the row is waited on
+        double e0[NS];
+        int cls[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const int s = lane + 32 * i;
+            e0[i] = 0.0; cls[i] = p.blank;
+            if (s < S) {
+                const int sm = S - 1 - s;
+                e0[i] = (double)arow[s] + (double)brow[sm] + ca[s / perw] + cb[sm / perw] + nll2;
+                if (s & 1) {
+                    long long c = tgt[s >> 1];
+                    cls[i] = (int)(c < 0 ? 0 : (c >= p.V ? p.V - 1 : c));
+                }
+            }
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const int s = lane + 32 * i;
+            if (s < S) wbuf[s] = ex2_approx((float)(e0[i] - (double)(rowbuf[o_in + cls[i]] * AVCTC_LOG2E)));
+        }
+        for (int s = lane + 32 * NS; s < S; s += 32) {
+            const int sm = S - 1 - s;
+            int c = p.blank;
+            if (s & 1) {
+                long long cc = tgt[s >> 1];
+                c = (int)(cc < 0 ? 0 : (cc >= p.V ? p.V - 1 : cc));
+            }
+            const double e = (double)arow[s] + (double)brow[sm] + ca[s / perw] + cb[sm / perw] + nll2 -
+                             (double)(rowbuf[o_in + c] * AVCTC_LOG2E);
+            wbuf[s] = ex2_approx((float)e);
+        }
+        __syncwarp();
+        // class posteriors: blank = sum of even states; label c = sum along its repeat chain
+        float pb = 0.f;
+        for (int s = 2 * lane; s < S; s += 64) pb += wbuf[s];
+        pb = warp_sum(pb);
+        const int* chain = p.chain + (size_t)b * p.Lpad;
+        for (int j = lane; j < L; j += 32) {
+            const int ch = chain[j];
+            if (ch & kChainFirst) {
+                float acc = wbuf[2 * j + 1];
+                int k = ch & kChainNone;
+                while (k != kChainNone) {
+                    acc += wbuf[2 * k + 1];
+                    k = chain[k] & kChainNone;
+                }
+                wbuf[2 * j + 1] = acc;   // only this lane ever reads this chain's slots
+            }
+        }
+        // exp(lp) * g
+        for (int c = lane; c < p.V; c += 32)
+            outbuf[o_out + c] = ex2_approx(rowbuf[o_in + c] * AVCTC_LOG2E) * scale;
+        __syncwarp();
+        if (lane == 0) outbuf[o_out + p.blank] -= pb * scale;
+        for (int j = lane; j < L; j += 32) {
+            if (chain[j] & kChainFirst) {
+                long long c = tgt[j];
+                c = c < 0 ? 0 : (c >= p.V ? p.V - 1 : c);
+                outbuf[o_out + (int)c] -= wbuf[2 * j + 1] * scale;
+            }
+        }
+        __syncwarp();
+        write_row(grow, p.V, outbuf, o_out, lane);
+        __syncwarp();
+    }
+}
+
+__global__ void ctc_reduce_kernel(const float* __restrict__ nll, const int64_t* __restrict__ tl, int B,
+                                  int reduction, int zero_infinity, float* __restrict__ loss) {
+    __shared__ double part[32];
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float v = nll[b];
+        if (zero_infinity && v == CUDART_INF_F) v = 0.f;
+        if (reduction == AVCTC_REDUCE_NONE) { loss[b] = v; continue; }
+        if (reduction == AVCTC_REDUCE_MEAN) {
+            long long l = tl[b];
+            // ATen divides in fp32: (nll / clamp_min(L,1)).mean()
+            acc += (double)(v / (float)(l > 1 ? l : 1));
+        } else acc += (double)v;
+    }
+    if (reduction == AVCTC_REDUCE_NONE) return;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullMask, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w];
+        loss[0] = (float)(reduction == AVCTC_REDUCE_MEAN ? s / (double)B : s);
+    }
+}
+
+template <int K, typename TIn>
+static int launch_scan(const ScanParams& sp, int ndir, cudaStream_t st) {
+    dim3 grid(sp.B, ndir), block(32 * sp.W);
+    ctc_scan_kernel<K, TIn><<<grid, block, 0, st>>>(sp);
+    return (int)cudaGetLastError();
+}
+template <typename TIn>
+static int dispatch_scan(const ScanParams& sp, int K, int ndir, cudaStream_t st) {
+    switch (K) {
+        case 2: return launch_scan<2, TIn>(sp, ndir, st);
+        case 4: return launch_scan<4, TIn>(sp, ndir, st);
+        case 8: return launch_scan<8, TIn>(sp, ndir, st);
+        case 16: return launch_scan<16, TIn>(sp, ndir, st);
+    }
+    return AVCTC_ERR_UNSUPPORTED;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <typename TIn>
+static int launch_grad(const GradParams& gp_in, cudaStream_t st) {
+    GradParams gp = gp_in;
+    const size_t per_warp = (size_t)(2 * gp.row_floats + gp.w_floats) * sizeof(float);
+    int warps = 8;
+    while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+    if (per_warp * warps > 200 * 1024) return AVCTC_ERR_UNSUPPORTED;
+    const size_t smem = per_warp * warps;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        AVCTC_CUDA_RETURN(cudaFuncSetAttribute(ctc_grad_kernel<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               200 * 1024));
+        configured = 200 * 1024;
+    }
+    int occ = 1;
+    AVCTC_CUDA_RETURN(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ctc_grad_kernel<TIn>, warps * 32, smem));
+    if (occ < 1) occ = 1;
+    const long long rows = (long long)gp.T * gp.B;
+    long long blocks = (rows + warps - 1) / warps;
+    const long long cap = (long long)num_sms() * occ;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) return AVCTC_OK;
+    ctc_grad_kernel<TIn><<<(unsigned)blocks, warps * 32, smem, st>>>(gp);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace avctc
+
+using namespace avctc;
+
+extern "C" size_t avctc_ctc_workspace_bytes(int T, int B, int max_target_len) {
+    CtcPlan pl;
+    if (T < 0 || B < 0 || max_target_len < 0) return 0;
+    if (!make_plan(T, B, max_target_len, &pl)) return 0;
+    return pl.total;
+}
+
+extern "C" int avctc_ctc_forward(const void* log_probs, int dtype, int64_t stride_t, int64_t stride_b,
+                                 int T, int B, int V, const int64_t* targets, int64_t target_stride,
+                                 const int64_t* target_offsets, const int64_t* input_lengths,
+                                 const int64_t* target_lengths, int max_target_len, int blank, int need_grad,
+                                 float* nll, void* workspace, size_t workspace_bytes, void* stream) {
+    if (T < 0 || B < 0 || V <= 0 || max_target_len < 0 || blank < 0 || blank >= V) return AVCTC_ERR_BAD_ARG;
+    if (B == 0) return AVCTC_OK;
+    if (!log_probs || !targets || !input_lengths || !target_lengths || !nll) return AVCTC_ERR_BAD_ARG;
+    if (dtype != AVCTC_F32 && dtype != AVCTC_BF16) return AVCTC_ERR_BAD_ARG;
+    CtcPlan pl;
+    if (!make_plan(T, B, max_target_len, &pl)) return AVCTC_ERR_UNSUPPORTED;
+    if (need_grad && (!workspace || workspace_bytes < pl.total)) return AVCTC_ERR_WORKSPACE;
+    if (need_grad && (reinterpret_cast<uintptr_t>(workspace) & 255)) return AVCTC_ERR_ALIGNMENT;
+    ScanParams sp;
+    sp.lp = log_probs; sp.stride_t = stride_t; sp.stride_b = stride_b;
+    sp.T = T; sp.B = B; sp.V = V;
+    sp.targets = targets; sp.target_stride = target_stride; sp.target_offsets = target_offsets;
+    sp.input_lengths = input_lengths; sp.target_lengths = target_lengths;
+    sp.Lmax = max_target_len; sp.blank = blank; sp.store = need_grad ? 1 : 0;
+    sp.nll = nll;
+    char* w = reinterpret_cast<char*>(workspace);
+    sp.alpha = need_grad ? reinterpret_cast<float*>(w + pl.off_alpha) : nullptr;
+    sp.beta = need_grad ? reinterpret_cast<float*>(w + pl.off_beta) : nullptr;
+    sp.coff_a = need_grad ? reinterpret_cast<double*>(w + pl.off_coff_a) : nullptr;
+    sp.coff_b = need_grad ? reinterpret_cast<double*>(w + pl.off_coff_b) : nullptr;
+    sp.nll2 = need_grad ? reinterpret_cast<double*>(w + pl.off_nll2) : nullptr;
+    sp.chain = need_grad ? reinterpret_cast<int*>(w + pl.off_chain) : nullptr;
+    sp.W = pl.W; sp.S_pad = pl.S_pad; sp.Lpad = pl.Lpad;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int ndir = need_grad ? 2 : 1;
+    if (dtype == AVCTC_F32) return dispatch_scan<float>(sp, pl.K, ndir, st);
+    return dispatch_scan<__nv_bfloat16>(sp, pl.K, ndir, st);
+}
+
+extern "C" int avctc_ctc_reduce(const float* nll, const int64_t* target_lengths, int B, int reduction,
+                                int zero_infinity, float* loss, void* stream) {
+    if (B < 0 || !loss) return AVCTC_ERR_BAD_ARG;
+    if (reduction < AVCTC_REDUCE_NONE || reduction > AVCTC_REDUCE_SUM) return AVCTC_ERR_BAD_ARG;
+    if (B > 0 && (!nll || !target_lengths)) return AVCTC_ERR_BAD_ARG;
+    ctc_reduce_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(nll, target_lengths, B, reduction,
+                                                                           zero_infinity, loss);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int avctc_ctc_backward(const void* log_probs, int dtype, int64_t stride_t, int64_t stride_b,
+                                  int T, int B, int V, const int64_t* targets, int64_t target_stride,
+                                  const int64_t* target_offsets, const int64_t* input_lengths,
+                                  const int64_t* target_lengths, int max_target_len, int blank, int reduction,
+                                  int zero_infinity, const float* nll, const float* grad_out,
+                                  int64_t grad_out_stride, void* grad, const void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+    if (T < 0 || B < 0 || V <= 0 || max_target_len < 0 || blank < 0 || blank >= V) return AVCTC_ERR_BAD_ARG;
+    if (B == 0 || T == 0) return AVCTC_OK;
+    if (!log_probs || !targets || !input_lengths || !target_lengths || !nll || !grad_out || !grad || !workspace)
+        return AVCTC_ERR_BAD_ARG;
+    if (dtype != AVCTC_F32 && dtype != AVCTC_BF16) return AVCTC_ERR_BAD_ARG;
+    if (reduction < AVCTC_REDUCE_NONE || reduction > AVCTC_REDUCE_SUM) return AVCTC_ERR_BAD_ARG;
+    CtcPlan pl;
+    if (!make_plan(T, B, max_target_len, &pl)) return AVCTC_ERR_UNSUPPORTED;
+    if (workspace_bytes < pl.total) return AVCTC_ERR_WORKSPACE;
+    GradParams gp;
+    gp.lp = log_probs; gp.stride_t = stride_t; gp.stride_b = stride_b;
+    gp.T = T; gp.B = B; gp.V = V;
+    gp.targets = targets; gp.target_stride = target_stride; gp.target_offsets = target_offsets;
+    gp.input_lengths = input_lengths; gp.target_lengths = target_lengths;
+    gp.Lmax = max_target_len; gp.blank = blank; gp.reduction = reduction; gp.zero_infinity = zero_infinity;
+    gp.nll = nll; gp.grad_out = grad_out; gp.grad_out_stride = grad_out_stride; gp.grad = grad;
+    const char* w = reinterpret_cast<const char*>(workspace);
+    gp.alpha = reinterpret_cast<const float*>(w + pl.off_alpha);
+    gp.beta = reinterpret_cast<const float*>(w + pl.off_beta);
+    gp.coff_a = reinterpret_cast<const double*>(w + pl.off_coff_a);
+    gp.coff_b = reinterpret_cast<const double*>(w + pl.off_coff_b);
+    gp.nll2 = reinterpret_cast<const double*>(w + pl.off_nll2);
+    gp.chain = reinterpret_cast<const int*>(w + pl.off_chain);
+    gp.K = pl.K; gp.W = pl.W; gp.S_pad = pl.S_pad; gp.Lpad = pl.Lpad;
+    gp.row_floats = (V + 8 + 3) & ~3;
+    gp.w_floats = (2 * max_target_len + 1 + 3) & ~3;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == AVCTC_F32) return launch_grad<float>(gp, st);
+    return launch_grad<__nv_bfloat16>(gp, st);
+}

