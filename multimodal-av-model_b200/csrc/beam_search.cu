@@ -35,9 +35,10 @@ struct BeamParams {
     int32_t* out_ids; int32_t* out_len; double* dbg_scores; int32_t* dbg_paths;
     uint32_t* bp_global;   // [N][T][beam] when back-pointers do not fit shared memory, else nullptr
     int32_t* path_ws;      // [N][T]
-    int* status;           // device int, set to 1 on an unsupported tie (k*64 > V path)
+    int* status;           // device int error channel (0 = ok)
     int row_floats;        // smem floats per staged row
     int n_enum;            // number of (b,j) candidate pairs
+    int use_nth;           // k*64 > V: torch.topk's nth_element + sort route for tied rows
 };
 
 __device__ __forceinline__ bool ranks_before(float x, float y) {  // TopKImpl.h:56-58
@@ -109,6 +110,139 @@ __device__ void topk_exact(const float* row, int V, int k, volatile float* tv, v
     __syncwarp();
 }
 
+
+// ---- literal libstdc++ (GCC 13) std::nth_element + std::sort on (value,index) pairs, one lane, in place.
+// torch.topk takes this route when k*64 > V (TopKImpl.h:45,66-76); only reached when the fast path saw ties.
+struct PairQ { volatile float* v; volatile int* i; };
+__device__ __forceinline__ bool q_cmp(const PairQ& q, int a, int b) { return ranks_before(q.v[a], q.v[b]); }
+__device__ __forceinline__ void q_swap(const PairQ& q, int a, int b) {
+    const float x = q.v[a]; const int xi = q.i[a];
+    q.v[a] = q.v[b]; q.i[a] = q.i[b];
+    q.v[b] = x; q.i[b] = xi;
+}
+__device__ void q_make_heap(const PairQ& q, int first, int last) {
+    const int len = last - first;
+    if (len < 2) return;
+    int parent = (len - 2) / 2;
+    while (true) {
+        const float v = q.v[first + parent]; const int vi = q.i[first + parent];
+        adjust_heap(q.v + first, q.i + first, parent, len, v, vi);
+        if (parent == 0) return;
+        parent--;
+    }
+}
+__device__ void q_pop_heap(const PairQ& q, int first, int last, int result) {
+    const float v = q.v[result]; const int vi = q.i[result];
+    q.v[result] = q.v[first]; q.i[result] = q.i[first];
+    adjust_heap(q.v + first, q.i + first, 0, last - first, v, vi);
+}
+__device__ void q_heap_select(const PairQ& q, int first, int middle, int last) {
+    q_make_heap(q, first, middle);
+    for (int i = middle; i < last; ++i)
+        if (q_cmp(q, i, first)) q_pop_heap(q, first, middle, i);
+}
+__device__ void q_sort_heap(const PairQ& q, int first, int last) {
+    while (last - first > 1) { --last; q_pop_heap(q, first, last, last); }
+}
+__device__ void q_move_median_to_first(const PairQ& q, int result, int a, int b, int c) {
+    if (q_cmp(q, a, b)) {
+        if (q_cmp(q, b, c)) q_swap(q, result, b);
+        else if (q_cmp(q, a, c)) q_swap(q, result, c);
+        else q_swap(q, result, a);
+    } else if (q_cmp(q, a, c)) q_swap(q, result, a);
+    else if (q_cmp(q, b, c)) q_swap(q, result, c);
+    else q_swap(q, result, b);
+}
+__device__ int q_unguarded_partition(const PairQ& q, int first, int last, int pivot) {
+    while (true) {
+        while (q_cmp(q, first, pivot)) ++first;
+        --last;
+        while (q_cmp(q, pivot, last)) --last;
+        if (!(first < last)) return first;
+        q_swap(q, first, last);
+        ++first;
+    }
+}
+__device__ int q_partition_pivot(const PairQ& q, int first, int last) {
+    const int mid = first + (last - first) / 2;
+    q_move_median_to_first(q, first, first + 1, mid, last - 1);
+    return q_unguarded_partition(q, first + 1, last, first);
+}
+__device__ void q_unguarded_linear_insert(const PairQ& q, int last) {
+    const float v = q.v[last]; const int vi = q.i[last];
+    int next = last - 1;
+    while (ranks_before(v, q.v[next])) {
+        q.v[last] = q.v[next]; q.i[last] = q.i[next];
+        last = next; --next;
+    }
+    q.v[last] = v; q.i[last] = vi;
+}
+__device__ void q_insertion_sort(const PairQ& q, int first, int last) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (q_cmp(q, i, first)) {
+            const float v = q.v[i]; const int vi = q.i[i];
+            for (int j = i; j > first; --j) { q.v[j] = q.v[j - 1]; q.i[j] = q.i[j - 1]; }
+            q.v[first] = v; q.i[first] = vi;
+        } else {
+            q_unguarded_linear_insert(q, i);
+        }
+    }
+}
+__device__ __forceinline__ int q_lg(int n) { return 31 - __clz(n); }
+__device__ void q_nth_element(const PairQ& q, int first, int nth, int last) {
+    if (first == last || nth == last) return;
+    int depth = q_lg(last - first) * 2;
+    while (last - first > 3) {
+        if (depth == 0) {
+            q_heap_select(q, first, nth + 1, last);
+            q_swap(q, first, nth);
+            return;
+        }
+        --depth;
+        const int cut = q_partition_pivot(q, first, last);
+        if (cut <= nth) first = cut; else last = cut;
+    }
+    q_insertion_sort(q, first, last);
+}
+__device__ void q_sort(const PairQ& q, int first, int last) {
+    if (first == last) return;
+    // std::__introsort_loop with an explicit stack (the recursive call handles [cut,last))
+    int stk_f[40], stk_l[40], stk_d[40];
+    int sp = 0;
+    stk_f[0] = first; stk_l[0] = last; stk_d[0] = q_lg(last - first) * 2; sp = 1;
+    while (sp > 0) {
+        --sp;
+        int f = stk_f[sp], l = stk_l[sp], d = stk_d[sp];
+        while (l - f > 16) {
+            if (d == 0) { q_heap_select(q, f, l, l); q_sort_heap(q, f, l); break; }
+            --d;
+            const int cut = q_partition_pivot(q, f, l);
+            if (sp < 40) { stk_f[sp] = cut; stk_l[sp] = l; stk_d[sp] = d; ++sp; }
+            l = cut;
+        }
+    }
+    // std::__final_insertion_sort
+    if (last - first > 16) {
+        q_insertion_sort(q, first, first + 16);
+        for (int i = first + 16; i != last; ++i) q_unguarded_linear_insert(q, i);
+    } else {
+        q_insertion_sort(q, first, last);
+    }
+}
+// exact nth_element(queue, queue+k-1, queue+V) + sort(queue, queue+k-1); mutates the staged row.
+__device__ void topk_nth_exact(float* row, int* qi, int V, int k, volatile float* tv, volatile int* ti, int lane) {
+    for (int c = lane; c < V; c += 32) qi[c] = c;
+    __syncwarp();
+    if (lane == 0) {
+        PairQ q{row, qi};
+        q_nth_element(q, 0, k - 1, V);
+        q_sort(q, 0, k - 1);
+        for (int j = 0; j < k; ++j) { tv[j] = q.v[j]; ti[j] = q.i[j]; }
+    }
+    __syncwarp();
+}
+
 // threshold top-k; returns false when the result is not provably tie-free (caller runs topk_exact)
 __device__ bool topk_fast(const float* row, int V, int k, float* cv, int* ci, volatile float* tv,
                           volatile int* ti, int lane) {
@@ -173,8 +307,8 @@ __global__ void __launch_bounds__(32) beam_search_kernel(const BeamParams p) {
     int* ti = reinterpret_cast<int*>(tv + kBeamMax + 1);                    // kBeamMax + 1
     unsigned char* en_b = reinterpret_cast<unsigned char*>(ti + kBeamMax + 1);  // n_enum
     unsigned char* en_j = en_b + p.n_enum;                                  // n_enum
-    uint32_t* bp_s = reinterpret_cast<uint32_t*>(
-        (reinterpret_cast<uintptr_t>(en_j + p.n_enum) + 15) & ~(uintptr_t)15);
+    int* qi = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(en_j + p.n_enum) + 15) & ~(uintptr_t)15);
+    uint32_t* bp_s = reinterpret_cast<uint32_t*>(qi + (p.use_nth ? p.row_floats : 0));
 
     long long fl = p.lengths ? p.lengths[n] : p.T;
     const int frames = (int)(fl < 0 ? 0 : (fl > p.T ? p.T : fl));
@@ -217,13 +351,13 @@ __global__ void __launch_bounds__(32) beam_search_kernel(const BeamParams p) {
         int ob = 0;
 #pragma unroll
         for (int i = 0; i < kRowBufs; ++i) if (i == t % kRowBufs) ob = o_in[i];
-        const float* row = rows + (t % kRowBufs) * p.row_floats + ob;
+        float* row = rows + (t % kRowBufs) * p.row_floats + ob;
 
         bool ok = false;
         if (p.fast) ok = topk_fast(row, p.V, k, cv, ci, tv, ti, lane);
         if (!ok) {
-            if ((long long)k * 64 > p.V) { if (lane == 0) *p.status = 1; }
-            topk_exact(row, p.V, k, tv, ti, lane);
+            if (p.use_nth) topk_nth_exact(row, qi, p.V, k, tv, ti, lane);
+            else topk_exact(row, p.V, k, tv, ti, lane);
         }
         // ---- expand + prune
         int M = 0;  // candidates: prefix of the enumeration with b < nb
@@ -299,14 +433,16 @@ static int enum_count(int k) {
     return m;
 }
 
-struct BeamPlan { size_t off_bp, off_path, off_status, total; bool bp_in_smem; size_t smem; int row_floats, n_enum; };
+struct BeamPlan { size_t off_bp, off_path, off_status, total; bool bp_in_smem; size_t smem; int row_floats, n_enum, use_nth; };
 
 static bool beam_plan(int N, int T, int V, int beam, BeamPlan* pl) {
     if (beam < 1 || beam > kBeamMax || beam > V) return false;
     pl->row_floats = (V + 8 + 3) & ~3;
     pl->n_enum = enum_count(beam);
+    pl->use_nth = ((long long)beam * 64 > V) ? 1 : 0;
     size_t fixed = (size_t)kRowBufs * pl->row_floats * 4 + 2 * kBeamMax * 8 + (size_t)pl->n_enum * 8 +
-                   kCandMax * 8 + (kBeamMax + 1) * 8 + 2 * (size_t)pl->n_enum + 16;
+                   kCandMax * 8 + (kBeamMax + 1) * 8 + 2 * (size_t)pl->n_enum + 16 +
+                   (pl->use_nth ? (size_t)pl->row_floats * 4 : 0);
     const size_t bp_bytes = (size_t)(T > 0 ? T : 1) * beam * 4;
     pl->bp_in_smem = bp_bytes <= (size_t)kBpSmemBytes;
     pl->smem = fixed + (pl->bp_in_smem ? bp_bytes : 0);
@@ -352,7 +488,7 @@ extern "C" int avctc_beam_search(const float* log_probs, int64_t stride_n, int64
     bp.bp_global = pl.bp_in_smem ? nullptr : reinterpret_cast<uint32_t*>(w + pl.off_bp);
     bp.path_ws = reinterpret_cast<int32_t*>(w + pl.off_path);
     bp.status = reinterpret_cast<int*>(w + pl.off_status);
-    bp.row_floats = pl.row_floats; bp.n_enum = pl.n_enum;
+    bp.row_floats = pl.row_floats; bp.n_enum = pl.n_enum; bp.use_nth = pl.use_nth;
     AVCTC_CUDA_RETURN(cudaMemsetAsync(bp.status, 0, sizeof(int), st));
     static size_t configured = 0;
     if (pl.smem > 48 * 1024 && pl.smem > configured) {
