@@ -49,6 +49,26 @@ __device__ __forceinline__ float lse3_log2(float x, float y, float z) {
     return m + lg2_approx(1.f + ex2_approx(lo - ms) + ex2_approx(mid - ms));
 }
 
+// ---- sentinel-based variants for the CTC scan: "-inf" is the finite kNegBig (absorbing under every add the
+// scan performs), so no NaN guards sit on the dependent chain; FMNMX3 gives the 3-way max in one op and the
+// emission is pre-added to the max off the chain:  lse(x,y,z) + v = lg2(sum ex2(. - m)) + (m + v).
+#define AVCTC_NEG_BIG (-1.0e30f)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float lse2_plus(float x, float y, float v) {
+    const float m = fmaxf(x, y);
+    const float mv = m + v;
+    return lg2_approx(ex2_approx(x - m) + ex2_approx(y - m)) + mv;
+}
+__device__ __forceinline__ float lse3_plus(float x, float y, float z, float v) {
+    const float m = fmax3(x, y, z);
+    const float mv = m + v;
+    return lg2_approx(ex2_approx(x - m) + ex2_approx(y - m) + ex2_approx(z - m)) + mv;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
@@ -86,6 +106,17 @@ __device__ __forceinline__ int ld_volatile_shared_s32(const int* p) {
 __device__ __forceinline__ void st_volatile_shared_s32(int* p, int v) {
     unsigned s = (unsigned)__cvta_generic_to_shared(p);
     asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(s), "r"(v));
+}
+
+__device__ __forceinline__ int4 ld_volatile_shared_v4(const int4* p) {
+    int4 v;
+    unsigned s = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(s));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_shared_v4(int4* p, int4 v) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("st.volatile.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(s), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 
 // stage one row of V elements into fp32 shared memory at buf[o + c], o = element misalignment of the

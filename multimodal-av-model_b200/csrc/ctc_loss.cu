@@ -10,9 +10,9 @@
 //                   two CTAs that run concurrently.  Neighbour states come from __shfl_up; when the
 //                   lattice needs more than one warp the warps form a systolic chain through a
 //                   shared-memory ring (warp w works on frame t while warp w-1 is already ahead), so the
-//                   t-loop has no __syncthreads.  Emissions are gathered D frames ahead into a register
-//                   ring.  Arithmetic is log2-domain fp32 with MUFU ex2/lg2, and every warp keeps its
-//                   lattice slice relative to a running fp64 offset (renormalised every D frames) so
+//                   t-loop has no __syncthreads.  Emissions are gathered D frames ahead by cp.async
+//                   into a shared-memory ring.  Arithmetic is log2-domain fp32 with MUFU ex2/lg2, and every warp keeps its
+//                   lattice states relative to a lane-local running integer offset (renormalised every 4 frames) so
 //                   |alpha| stays O(100) instead of O(T*10): that is what lets fp32 meet 1e-4 against
 //                   the fp64 reference at T=1000.
 //  ctc_grad_kernel  one WARP per (t,b) row, all SMs: streams the log-prob row in (cp.async), combines
@@ -23,7 +23,8 @@
 
 namespace avctc {
 
-constexpr int kScanPrefetch = 8;   // D: emission prefetch depth == renormalisation period
+constexpr int kScanPrefetch = 16;  // D: emission prefetch depth (frames)
+constexpr int kRenorm = 4;         // renormalisation period (frames); lag = period/2
 constexpr int kRing = 32;          // handoff ring slots between neighbouring warps
 constexpr int kMaxWarps = 16;
 constexpr int kChainNone = 0x3fffffff;
@@ -58,8 +59,8 @@ static bool make_plan(int T, int B, int Lmax, CtcPlan* pl) {
     size_t o = 0;
     pl->off_alpha = o; o = align_up(o + TB * pl->S_pad * sizeof(float), 256);
     pl->off_beta = o; o = align_up(o + TB * pl->S_pad * sizeof(float), 256);
-    pl->off_coff_a = o; o = align_up(o + TB * W * sizeof(double), 256);
-    pl->off_coff_b = o; o = align_up(o + TB * W * sizeof(double), 256);
+    pl->off_coff_a = o; o = align_up(o + TB * W * 32 * sizeof(int), 256);   // one offset per LANE
+    pl->off_coff_b = o; o = align_up(o + TB * W * 32 * sizeof(int), 256);
     pl->off_nll2 = o; o = align_up(o + (size_t)B * sizeof(double), 256);
     pl->off_chain = o; o = align_up(o + (size_t)B * pl->Lpad * sizeof(int), 256);
     pl->total = o;
@@ -73,7 +74,7 @@ struct ScanParams {
     const int64_t* input_lengths; const int64_t* target_lengths;
     int Lmax, blank, store;
     float* nll;
-    float* alpha; float* beta; double* coff_a; double* coff_b; double* nll2; int* chain;
+    float* alpha; float* beta; int* coff_a; int* coff_b; double* nll2; int* chain;
     int W, S_pad, Lpad;
 };
 
@@ -88,16 +89,19 @@ __device__ __forceinline__ void store_states(float* dst, const float (&a)[K]) {
     }
 }
 
-template <int K, typename TIn>
+template <int K, typename TIn, bool MULTI>
 __global__ void __launch_bounds__(32 * kMaxWarps) ctc_scan_kernel(const ScanParams p) {
     constexpr int KL = K / 2;
-    constexpr int D = (K >= 8) ? kScanPrefetch / 2 : kScanPrefetch;
+    constexpr int D = (K >= 16) ? kScanPrefetch / 4 : (K >= 8) ? kScanPrefetch / 2 : kScanPrefetch;
+    constexpr int RN = (D < kRenorm) ? D : kRenorm;
     const int b = blockIdx.x;
     const int dir = blockIdx.y;  // 0: alpha (forward in time), 1: beta (mirrored problem)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    __shared__ float ring_v[kMaxWarps][kRing];
-    __shared__ double ring_c[kMaxWarps][kRing];
+    // handoff ring: one 16-byte slot {value bits, offset lo, offset hi, frame tag} per frame, written and read
+    // with single 128-bit shared accesses, so no fence is needed between payload and tag (a fence in the
+    // frame loop would also wait for the emission prefetches in flight).
+    __shared__ __align__(16) int4 ring[MULTI ? kMaxWarps : 1][kRing];
     __shared__ int progress[kMaxWarps];
     __shared__ double fin[2];
 
@@ -119,12 +123,11 @@ __global__ void __launch_bounds__(32 * kMaxWarps) ctc_scan_kernel(const ScanPara
     }
     if (tid < kMaxWarps) progress[tid] = 0;
     if (tid < 2) fin[tid] = -(double)CUDART_INF_F;
+    if (MULTI)
+        for (int i = tid; i < kMaxWarps * kRing; i += blockDim.x) ring[i / kRing][i % kRing] = make_int4(0, 0, 0, -1);
     __syncthreads();
 
     const int Wact = (S + 32 * K - 1) / (32 * K);  // warps that own at least one real state
-    const TIn* lp = reinterpret_cast<const TIn*>(p.lp) + (int64_t)b * p.stride_b;
-    float* ws = dir ? p.beta : p.alpha;
-    double* coff = dir ? p.coff_b : p.coff_a;
 
     if (warp < Wact) {
         const int g = tid;             // global lane: owns (mirrored) states g*K .. g*K+K-1
@@ -146,127 +149,185 @@ __global__ void __launch_bounds__(32 * kMaxWarps) ctc_scan_kernel(const ScanPara
                 }
             }
         }
-        auto row_of = [&](int tau) -> const TIn* {
-            const int t = dir ? (Tb - 1 - tau) : tau;
-            return lp + (int64_t)t * p.stride_t;
-        };
-        auto gather = [&](int tau, float& vb, float (&vl)[KL]) {
-            const TIn* row = row_of(tau);
-            vb = to_float(__ldg(row + p.blank)) * AVCTC_LOG2E;
+        // everything that depends on the frame is a running pointer / offset: the frame loop is issue-bound
+        // for a single warp, so no multiplies or 64-bit index math inside it.
+        long long fstep = dir ? -p.stride_t : p.stride_t;                      // elements per scan frame
+        asm volatile("" : "+l"(fstep));
+        const TIn* row0 = reinterpret_cast<const TIn*>(p.lp) + (int64_t)b * p.stride_b +
+                          (int64_t)(dir ? Tb - 1 : 0) * p.stride_t;           // scan frame 0
+        const TIn* gp_b = row0 + p.blank + fstep;                              // gather pointers, scan frame 1
+        const TIn* gp_l[KL];
 #pragma unroll
-            for (int i = 0; i < KL; ++i) vl[i] = to_float(__ldg(row + lab[i])) * AVCTC_LOG2E;
-        };
+        for (int i = 0; i < KL; ++i) gp_l[i] = row0 + lab[i] + fstep;
 
         // ---- frame 0
         float a[K];
 #pragma unroll
-        for (int j = 0; j < K; ++j) a[j] = AVCTC_NEG_INF;
-        {
-            float vb, vl[KL];
-            gather(0, vb, vl);
-            if (g == 0) {
-                a[0] = vb;
-                if (L > 0) a[1] = vl[0];
-            }
+        for (int j = 0; j < K; ++j) a[j] = AVCTC_NEG_BIG;   // finite "-inf" (see common.cuh)
+        if (g == 0) {
+            a[0] = to_float(__ldg(row0 + p.blank)) * AVCTC_LOG2E;
+            if (L > 0) a[1] = to_float(__ldg(row0 + lab[0])) * AVCTC_LOG2E;
         }
-        double C = 0.0;              // running offset of this warp's slice (log2 units), warp-uniform
-        bool empty = (warp > 0);     // no finite mass has entered this warp's slice yet
-        float mred = AVCTC_NEG_INF;
-        int avail = 0, cons = 0;
+        // Every LANE keeps its K states relative to its own running INTEGER offset C (log2 units): the states
+        // that carry posterior mass are often 2^-200 below the lattice maximum, so a warp-wide offset leaves
+        // them at |a| ~ 200 (ulp 1.5e-5) and the rounding random-walk over T=1000 frames reaches 2e-4; with
+        // lane-local offsets |a| stays O(10) and the error drops ~10x (emulated: 2e-5).
+        int C = 0;
+        float dC = 0.f;              // float(C of lane-1) - C, refreshed whenever offsets change
+        int cons = 0;
+        const size_t rowi0 = (size_t)b * p.T + (dir ? Tb - 1 : 0);
+        float* wsp = (dir ? p.beta : p.alpha) + (p.store ? rowi0 * p.S_pad + (size_t)g * K : 0);
+        int* cfp = (dir ? p.coff_b : p.coff_a) + (p.store ? rowi0 * (p.W * 32) + g : 0);
+        long long wstep = dir ? -(long long)p.S_pad : (long long)p.S_pad;
+        long long cstep = dir ? -(long long)p.W * 32 : (long long)p.W * 32;
+        asm volatile("" : "+l"(wstep), "+l"(cstep));   // keep the steps in registers (no per-frame recompute)
+        const bool do_store = p.store != 0;
+        const bool is_lane0 = (lane == 0);
 
         auto publish = [&](int tau) {
-            if (p.store) {
-                const int t = dir ? (Tb - 1 - tau) : tau;
-                const size_t rowi = (size_t)b * p.T + t;
-                store_states<K>(ws + rowi * p.S_pad + (size_t)g * K, a);
-                if (lane == 0) coff[rowi * p.W + warp] = C;
+            if (do_store) {
+                store_states<K>(wsp, a);
+                *cfp = C;
+                wsp += wstep; cfp += cstep;
             }
-            if (warp < Wact - 1) {
-                if (lane == 31) {
-                    const int need = tau - kRing + 2;
-                    while (cons < need) cons = ld_volatile_shared_s32(&progress[warp + 1]);
-                    const int slot = tau & (kRing - 1);
-                    *(volatile float*)&ring_v[warp][slot] = a[K - 1];
-                    *(volatile double*)&ring_c[warp][slot] = C;
-                    __threadfence_block();
-                    st_volatile_shared_s32(&progress[warp], tau + 1);
+            if (MULTI) {
+                if (warp < Wact - 1) {
+                    if (lane == 31) {
+                        const int need = tau - kRing + 2;   // consumer must have finished frame tau-kRing+1
+                        while (cons < need) cons = ld_volatile_shared_s32(&progress[warp + 1]);
+                        st_volatile_shared_v4(&ring[warp][tau & (kRing - 1)],
+                                              make_int4(__float_as_int(a[K - 1]), C, 0, tau));
+                    }
                 }
-                __syncwarp();
-            } else if (warp > 0 && lane == 0) {
-                // the last active warp still reports progress so its producer can recycle ring slots
-                st_volatile_shared_s32(&progress[warp], tau + 1);
+                if (warp > 0 && is_lane0) st_volatile_shared_s32(&progress[warp], tau + 1);
             }
         };
         publish(0);
 
-        // ---- emission prefetch ring
-        float pre_b[D], pre_l[D][KL];
+        // ---- emission staging: cp.async (LDGSTS) gathers D frames ahead into a shared-memory ring.
+        // (A register ring does not work here: 6 scoreboard slots cannot track D loads individually, so
+        // every frame ends up waiting for the newest load = one full memory latency per frame.)
+        extern __shared__ __align__(16) unsigned em_raw[];   // [D][blockDim.x][KL+1] 32-bit words
+        const int slot_words = blockDim.x * (KL + 1);
+        unsigned* em_mine = em_raw + tid * (KL + 1);
+        int par_b = 0, par_l[KL];                            // bf16: which half of the staged word
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            pre_b[d] = 0.f;
+        for (int i = 0; i < KL; ++i) par_l[i] = 0;
+        const int par_step = (int)(fstep & 1);
+        auto issue = [&](unsigned* dst, bool live) {          // gathers the frame gp_* point at, then advances
+            if (live) {
+                if constexpr (sizeof(TIn) == 4) {
+                    cp_async_4(dst, gp_b);
 #pragma unroll
-            for (int i = 0; i < KL; ++i) pre_l[d][i] = 0.f;
-            if (1 + d < Tb) gather(1 + d, pre_b[d], pre_l[d]);
-        }
-
-        for (int tau0 = 1; tau0 < Tb; tau0 += D) {
+                    for (int i = 0; i < KL; ++i) cp_async_4(dst + 1 + i, gp_l[i]);
+                } else {   // 2-byte elements: copy the aligned 4-byte word holding the element
+                    cp_async_4(dst, reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(gp_b) & ~(uintptr_t)3));
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const int tau = tau0 + d;
-                if (tau < Tb) {
-                    const float vb = pre_b[d];
-                    float vl[KL];
-#pragma unroll
-                    for (int i = 0; i < KL; ++i) vl[i] = pre_l[d][i];
-                    if (tau + D < Tb) gather(tau + D, pre_b[d], pre_l[d]);
-
-                    float prev_in = AVCTC_NEG_INF;
-                    if (warp > 0) {
-                        while (avail < tau) avail = ld_volatile_shared_s32(&progress[warp - 1]);
-                        __threadfence_block();
-                        const int slot = (tau - 1) & (kRing - 1);
-                        const float pv = *(volatile float*)&ring_v[warp - 1][slot];
-                        const double pc = *(volatile double*)&ring_c[warp - 1][slot];
-                        if (empty) {
-                            C = pc;  // adopt the producer's frame while this slice holds no mass
-                            if (pv > AVCTC_NEG_INF) empty = false;
-                        }
-                        prev_in = pv + (float)(pc - C);
-                    }
-                    if (d == 0) {
-                        float ml = a[0];
-#pragma unroll
-                        for (int j = 1; j < K; ++j) ml = fmaxf(ml, a[j]);
-                        mred = warp_max(ml);
-                    }
-                    const float up = __shfl_up_sync(kFullMask, a[K - 1], 1);
-                    const float prev = (lane == 0) ? prev_in : up;
-                    float nw[K];
-#pragma unroll
-                    for (int i = 0; i < KL; ++i) {
-                        const float below = (i == 0) ? prev : a[2 * i - 1];
-                        nw[2 * i] = lse2_log2(a[2 * i], below) + vb;
-                        nw[2 * i + 1] = lse3_log2(a[2 * i + 1], a[2 * i], skip[i] ? below : AVCTC_NEG_INF) + vl[i];
-                    }
-#pragma unroll
-                    for (int j = 0; j < K; ++j) a[j] = (j < nvalid) ? nw[j] : AVCTC_NEG_INF;
-                    if (d == D / 2) {
-                        if (mred > AVCTC_NEG_INF && mred < CUDART_INF_F) {
-#pragma unroll
-                            for (int j = 0; j < K; ++j) a[j] -= mred;
-                            C += (double)mred;
-                        }
-                    }
-                    publish(tau);
+                    for (int i = 0; i < KL; ++i)
+                        cp_async_4(dst + 1 + i,
+                                   reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(gp_l[i]) & ~(uintptr_t)3));
                 }
             }
+            cp_async_commit();
+            gp_b += fstep;
+#pragma unroll
+            for (int i = 0; i < KL; ++i) gp_l[i] += fstep;
+        };
+        if constexpr (sizeof(TIn) == 2) {   // parity of the element address at scan frame 1
+            par_b = (int)((reinterpret_cast<uintptr_t>(gp_b) >> 1) & 1);
+#pragma unroll
+            for (int i = 0; i < KL; ++i) par_l[i] = (int)((reinterpret_cast<uintptr_t>(gp_l[i]) >> 1) & 1);
         }
+        for (int d = 1; d <= D; ++d) issue(em_mine + (d & (D - 1)) * slot_words, d < Tb);
+
+        int slot = 1 & (D - 1);
+        int4 nxt_slot = make_int4(0, 0, 0, -1);
+        if (MULTI) {
+            if (warp > 0) nxt_slot = ld_volatile_shared_v4(&ring[warp - 1][0]);
+        }
+        int live_left = Tb - 1 - D;           // frames still to be gathered after the prologue
+#pragma unroll 1
+        for (int tau = 1; tau < Tb; ++tau) {
+            cp_async_wait<D - 1>();           // frames <= tau have landed (own copies only: no barrier needed)
+            unsigned* sl_ptr = em_mine + slot * slot_words;
+            float vb, vl[KL];
+            if constexpr (sizeof(TIn) == 4) {
+                if constexpr (KL == 1) {
+                    const uint2 w = *reinterpret_cast<const uint2*>(sl_ptr);
+                    vb = __uint_as_float(w.x) * AVCTC_LOG2E;
+                    vl[0] = __uint_as_float(w.y) * AVCTC_LOG2E;
+                } else {
+                    vb = __uint_as_float(sl_ptr[0]) * AVCTC_LOG2E;
+#pragma unroll
+                    for (int i = 0; i < KL; ++i) vl[i] = __uint_as_float(sl_ptr[1 + i]) * AVCTC_LOG2E;
+                }
+            } else {
+                auto pick = [](unsigned w, int par) { return __uint_as_float(par ? (w & 0xffff0000u) : (w << 16)); };
+                vb = pick(sl_ptr[0], par_b) * AVCTC_LOG2E;
+                par_b ^= par_step;
+#pragma unroll
+                for (int i = 0; i < KL; ++i) {
+                    vl[i] = pick(sl_ptr[1 + i], par_l[i]) * AVCTC_LOG2E;
+                    par_l[i] ^= par_step;
+                }
+            }
+            issue(sl_ptr, live_left > 0);     // refills the slot just read (frame tau + D)
+            --live_left;
+            slot = (slot + 1) & (D - 1);
+
+            float prev_in = AVCTC_NEG_BIG;
+            int pc = 0;
+            if (MULTI) {
+                if (warp > 0) {
+                    int4 sl = nxt_slot;               // read at the end of the previous frame
+                    while (sl.w != tau - 1) sl = ld_volatile_shared_v4(&ring[warp - 1][(tau - 1) & (kRing - 1)]);
+                    pc = sl.y;
+                    prev_in = __int_as_float(sl.x) + (float)(pc - C);
+                }
+            }
+            const float up = __shfl_up_sync(kFullMask, a[K - 1], 1);
+            const float prev = is_lane0 ? prev_in : up + dC;
+            float nw[K];
+#pragma unroll
+            for (int i = 0; i < KL; ++i) {
+                const float below = (i == 0) ? prev : a[2 * i - 1];
+                // invalid states get the sentinel as emission, which absorbs: no select on the chain
+                const float eb = (2 * i < nvalid) ? vb : AVCTC_NEG_BIG;
+                const float el = (2 * i + 1 < nvalid) ? vl[i] : AVCTC_NEG_BIG;
+                nw[2 * i] = lse2_plus(a[2 * i], below, eb);
+                nw[2 * i + 1] = lse3_plus(a[2 * i + 1], a[2 * i], skip[i] ? below : AVCTC_NEG_BIG, el);
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j) a[j] = nw[j];
+            if ((tau & (RN - 1)) == 0) {              // lane-local renormalisation, no reduction needed
+                float ml = a[0];
+#pragma unroll
+                for (int j = 1; j < K; ++j) ml = fmaxf(ml, a[j]);
+                const bool has_mass = ml > 0.5f * AVCTC_NEG_BIG;
+                const float mq = has_mass ? floorf(ml) : 0.f;   // integer shift: offsets stay exact in int32
+#pragma unroll
+                for (int j = 0; j < K; ++j) a[j] = fmaxf(a[j] - mq, AVCTC_NEG_BIG);
+                C += (int)mq;
+                int upC = __shfl_up_sync(kFullMask, C, 1);
+                if (is_lane0) upC = (MULTI && warp > 0) ? pc : C;
+                if (!has_mass) C = upC;               // empty lane: adopt the frame mass will arrive in
+                upC = __shfl_up_sync(kFullMask, C, 1);   // neighbours may have adopted too: re-read
+                if (is_lane0) upC = C;                // lane 0 converts explicitly from the ring slot
+                dC = (float)(upC - C);
+            }
+            publish(tau);
+            if (MULTI) {   // early read of the next frame's boundary slot (usually already published)
+                if (warp > 0) nxt_slot = ld_volatile_shared_v4(&ring[warp - 1][tau & (kRing - 1)]);
+            }
+        }
+        cp_async_wait<0>();
         // ---- the two terminal states (mirrored index S-1 / S-2 are terminal for alpha)
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const int s = g * K + j;
-            if (s == S - 1) fin[0] = (double)a[j] + C;
-            if (s == S - 2) fin[1] = (double)a[j] + C;
+            const double tv = (a[j] > 0.5f * AVCTC_NEG_BIG) ? (double)a[j] + (double)C : -(double)CUDART_INF_F;
+            if (s == S - 1) fin[0] = tv;
+            if (s == S - 2) fin[1] = tv;
         }
     }
     __syncthreads();
@@ -303,7 +364,7 @@ struct GradParams {
     int Lmax, blank, reduction, zero_infinity;
     const float* nll; const float* grad_out; int64_t grad_out_stride;
     void* grad;
-    const float* alpha; const float* beta; const double* coff_a; const double* coff_b;
+    const float* alpha; const float* beta; const int* coff_a; const int* coff_b;
     const double* nll2; const int* chain;
     int K, W, S_pad, Lpad;
     int row_floats;   // per-warp smem floats for one staged row (>= V + 8, multiple of 4)
@@ -417,10 +478,10 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const GradParams p) {
         const size_t rowi = (size_t)b * p.T + t;
         const float* arow = p.alpha + rowi * p.S_pad;
         const float* brow = p.beta + rowi * p.S_pad;
-        const double* ca = p.coff_a + rowi * p.W;
-        const double* cb = p.coff_b + rowi * p.W;
+        const int* ca = p.coff_a + rowi * (p.W * 32);
+        const int* cb = p.coff_b + rowi * (p.W * 32);
         const double nll2 = p.nll2[b];
-        const int perw = 32 * p.K;
+        const int perw = p.K;   // states per lane (offsets are per lane)
 
         // log2 of alpha_t(s)*beta_t(s)/P, offsets folded in fp64; loads issued before the row is waited on
         double e0[NS];
@@ -431,7 +492,7 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const GradParams p) {
             e0[i] = 0.0; cls[i] = p.blank;
             if (s < S) {
                 const int sm = S - 1 - s;
-                e0[i] = (double)arow[s] + (double)brow[sm] + ca[s / perw] + cb[sm / perw] + nll2;
+                e0[i] = (double)arow[s] + (double)brow[sm] + (double)(ca[s / perw] + cb[sm / perw]) + nll2;
                 if (s & 1) {
                     long long c = tgt[s >> 1];
                     cls[i] = (int)(c < 0 ? 0 : (c >= p.V ? p.V - 1 : c));
@@ -452,7 +513,7 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const GradParams p) {
                 long long cc = tgt[s >> 1];
                 c = (int)(cc < 0 ? 0 : (cc >= p.V ? p.V - 1 : cc));
             }
-            const double e = (double)arow[s] + (double)brow[sm] + ca[s / perw] + cb[sm / perw] + nll2 -
+            const double e = (double)arow[s] + (double)brow[sm] + (double)(ca[s / perw] + cb[sm / perw]) + nll2 -
                              (double)(rowbuf[o_in + c] * AVCTC_LOG2E);
             wbuf[s] = ex2_approx((float)e);
         }
@@ -517,11 +578,24 @@ __global__ void ctc_reduce_kernel(const float* __restrict__ nll, const int64_t* 
     }
 }
 
+template <int K, typename TIn, bool MULTI>
+static int launch_scan_impl(const ScanParams& sp, int ndir, cudaStream_t st) {
+    constexpr int D = (K >= 16) ? kScanPrefetch / 4 : (K >= 8) ? kScanPrefetch / 2 : kScanPrefetch;
+    dim3 grid(sp.B, ndir), block(32 * sp.W);
+    const size_t smem = (size_t)D * (K / 2 + 1) * block.x * sizeof(unsigned);
+    static bool configured = false;
+    if (smem > 32 * 1024 && !configured) {
+        AVCTC_CUDA_RETURN(cudaFuncSetAttribute(ctc_scan_kernel<K, TIn, MULTI>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        configured = true;
+    }
+    ctc_scan_kernel<K, TIn, MULTI><<<grid, block, smem, st>>>(sp);
+    return (int)cudaGetLastError();
+}
 template <int K, typename TIn>
 static int launch_scan(const ScanParams& sp, int ndir, cudaStream_t st) {
-    dim3 grid(sp.B, ndir), block(32 * sp.W);
-    ctc_scan_kernel<K, TIn><<<grid, block, 0, st>>>(sp);
-    return (int)cudaGetLastError();
+    if (sp.W > 1) return launch_scan_impl<K, TIn, true>(sp, ndir, st);
+    return launch_scan_impl<K, TIn, false>(sp, ndir, st);
 }
 template <typename TIn>
 static int dispatch_scan(const ScanParams& sp, int K, int ndir, cudaStream_t st) {
@@ -605,8 +679,8 @@ extern "C" int avctc_ctc_forward(const void* log_probs, int dtype, int64_t strid
     char* w = reinterpret_cast<char*>(workspace);
     sp.alpha = need_grad ? reinterpret_cast<float*>(w + pl.off_alpha) : nullptr;
     sp.beta = need_grad ? reinterpret_cast<float*>(w + pl.off_beta) : nullptr;
-    sp.coff_a = need_grad ? reinterpret_cast<double*>(w + pl.off_coff_a) : nullptr;
-    sp.coff_b = need_grad ? reinterpret_cast<double*>(w + pl.off_coff_b) : nullptr;
+    sp.coff_a = need_grad ? reinterpret_cast<int*>(w + pl.off_coff_a) : nullptr;
+    sp.coff_b = need_grad ? reinterpret_cast<int*>(w + pl.off_coff_b) : nullptr;
     sp.nll2 = need_grad ? reinterpret_cast<double*>(w + pl.off_nll2) : nullptr;
     sp.chain = need_grad ? reinterpret_cast<int*>(w + pl.off_chain) : nullptr;
     sp.W = pl.W; sp.S_pad = pl.S_pad; sp.Lpad = pl.Lpad;
@@ -652,8 +726,8 @@ extern "C" int avctc_ctc_backward(const void* log_probs, int dtype, int64_t stri
     const char* w = reinterpret_cast<const char*>(workspace);
     gp.alpha = reinterpret_cast<const float*>(w + pl.off_alpha);
     gp.beta = reinterpret_cast<const float*>(w + pl.off_beta);
-    gp.coff_a = reinterpret_cast<const double*>(w + pl.off_coff_a);
-    gp.coff_b = reinterpret_cast<const double*>(w + pl.off_coff_b);
+    gp.coff_a = reinterpret_cast<const int*>(w + pl.off_coff_a);
+    gp.coff_b = reinterpret_cast<const int*>(w + pl.off_coff_b);
     gp.nll2 = reinterpret_cast<const double*>(w + pl.off_nll2);
     gp.chain = reinterpret_cast<const int*>(w + pl.off_chain);
     gp.K = pl.K; gp.W = pl.W; gp.S_pad = pl.S_pad; gp.Lpad = pl.Lpad;
