@@ -103,6 +103,33 @@ AVCTC_API int avctc_beam_search(const float* log_probs, int64_t stride_n, int64_
                       int32_t* out_ids, int32_t* out_len, double* dbg_scores, int32_t* dbg_paths,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fusion path dense contraction (tcgen05 + TMEM + TMA) — replaces the cuBLAS GEMMs under
+ *   nn.Linear x4            /root/reference/model/fusion_module.py:57,58,63; model/decoder.py:24
+ *   nn.MultiheadAttention   /root/reference/model/fusion_module.py:61 (in/out projections, Q.K^T, P.V)
+ * and their backward passes.   C[z] = alpha * A[z] . B[z]^T (+ bias),   A: M x K,  B: N x K, bf16 in, fp32
+ * accumulate.  An operand is a 3-D bf16 tensor described by avctc_gemm_operand:
+ *   mn_major = 0: element (row r, k) at ptr[z*zstride + r*ld + k]   (row-major rows x K, e.g. activations, weights)
+ *   mn_major = 1: element (row r, k) at ptr[z*zstride + k*ld + r]   (the transposed view; no copy is made)
+ * rows/kdim/zdim are the tensor's full extents (TMA zero-fills reads outside them).  Batch entry
+ * z in [0,batch) is split as outer = z / inner_count, inner = z % inner_count and reads its slice at
+ * element offsets (k: outer*k_outer + inner*k_inner, row: outer*r_outer + inner*r_inner,
+ * z: outer*z_outer + inner*z_inner); C[z] starts at C + outer*c_outer + inner*c_inner, row stride ldc.
+ * ptr must be 16-byte aligned and ld, zstride multiples of 8 elements.
+ * bias_mode: 0 none, 1 bias[n] per output column, 2 bias[m] per output row (fp32).  accumulate != 0 adds
+ * into an fp32 C.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* ptr;
+    long long rows, kdim, zdim, ld, zstride;
+    int k_outer, k_inner, r_outer, r_inner, z_outer, z_inner;
+    int mn_major;
+} avctc_gemm_operand;
+
+AVCTC_API int avctc_gemm_bf16(const avctc_gemm_operand* a, const avctc_gemm_operand* b, int M, int N, int K, int batch,
+                    int inner_count, void* C, int out_dtype, long long ldc, long long c_outer, long long c_inner,
+                    const float* bias, int bias_mode, float alpha, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,7 +31,17 @@ SIGNATURES = {
                                 _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "avctc_beam_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "avctc_beam_search": (_i, [_vp, _i64, _i64, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "avctc_gemm_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, ctypes.c_longlong, ctypes.c_longlong,
+                             ctypes.c_longlong, _vp, _i, ctypes.c_float, _i, _vp]),
 }
+
+
+class GemmOperand(ctypes.Structure):
+    """Mirror of avctc_gemm_operand (include/avctc_b200.h)."""
+    _fields_ = [("ptr", ctypes.c_void_p), ("rows", ctypes.c_longlong), ("kdim", ctypes.c_longlong),
+                ("zdim", ctypes.c_longlong), ("ld", ctypes.c_longlong), ("zstride", ctypes.c_longlong),
+                ("k_outer", _i), ("k_inner", _i), ("r_outer", _i), ("r_inner", _i), ("z_outer", _i),
+                ("z_inner", _i), ("mn_major", _i)]
 
 
 def lib() -> ctypes.CDLL:
