@@ -130,6 +130,38 @@ AVCTC_API int avctc_gemm_bf16(const avctc_gemm_operand* a, const avctc_gemm_oper
                     int inner_count, void* C, int out_dtype, long long ldc, long long c_outer, long long c_inner,
                     const float* bias, int bias_mode, float alpha, int accumulate, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fusion glue — replaces the Python/ATen glue of CrossAttentionFusion.forward
+ *   /root/reference/model/fusion_module.py:40-55 (speech-frame select, pad_sequence, F.interpolate linear
+ *   align_corners=True for audio / nearest for the mask) and :66 (input_lengths), without host syncs.
+ * audio [B,Ta,D] (fp32 or bf16, contiguous), mask [B,Ta] int64 in {0,1,2,3} -> out [B,Tv,D] bf16,
+ * mask_out [B,Tv] int64, input_lengths [B] int64.  workspace keeps the compaction maps for backward.
+ * If no frame of the whole batch is speech the reference raises inside F.interpolate; here out = 0 and
+ * input_lengths = 0 (documented deviation, no host sync is spent on detecting it).
+ * ---------------------------------------------------------------------------------------------- */
+AVCTC_API size_t avctc_resample_workspace_bytes(int B, int Ta);
+AVCTC_API int avctc_resample_forward(const void* audio, int dtype, const int64_t* mask, int B, int Ta, int D, int Tv,
+                           void* out_bf16, int64_t* mask_out, int64_t* input_lengths, void* workspace,
+                           size_t workspace_bytes, void* stream);
+/* d_audio [B,Ta,D] (dtype fp32/bf16) from d_out [B,Tv,D] bf16; deterministic gather, zero for non-speech frames. */
+AVCTC_API int avctc_resample_backward(const void* dout_bf16, int B, int Ta, int D, int Tv, const void* workspace,
+                            void* daudio, int dtype, void* stream);
+
+/* softmax over the first T entries of each Tp-strided row (nn.MultiheadAttention, no key mask):
+ * S fp32 [rows,Tp] -> P bf16 [rows,Tp] with zero pad columns; backward dS = P*(dP - sum(dP*P)). */
+AVCTC_API int avctc_softmax_forward(const float* S, void* P_bf16, long long rows, int T, int Tp, void* stream);
+AVCTC_API int avctc_softmax_backward(const void* P_bf16, const float* dP, void* dS_bf16, long long rows, int T, int Tp,
+                           void* stream);
+/* out[n] (+)= sum_m X[m*ld + n]  (bias gradients). */
+AVCTC_API int avctc_colsum(const void* X, int dtype, long long M, int N, long long ld, float* out, int accumulate,
+                 void* stream);
+/* CTC head: F.log_softmax over V classes (/root/reference/model/decoder.py:25) and its backward
+ * dX = dY - exp(Y)*sum(dY), dX written as bf16 with row stride ldx. */
+AVCTC_API int avctc_log_softmax_forward(const void* X, int in_dtype, void* Y, int out_dtype, long long rows, int V,
+                              void* stream);
+AVCTC_API int avctc_log_softmax_backward(const void* Y, const void* dY, int dtype, void* dX_bf16, long long rows, int V,
+                               long long ldx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,14 @@ SIGNATURES = {
     "avctc_beam_search": (_i, [_vp, _i64, _i64, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "avctc_gemm_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, ctypes.c_longlong, ctypes.c_longlong,
                              ctypes.c_longlong, _vp, _i, ctypes.c_float, _i, _vp]),
+    "avctc_resample_workspace_bytes": (_sz, [_i, _i]),
+    "avctc_resample_forward": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "avctc_resample_backward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "avctc_softmax_forward": (_i, [_vp, _vp, ctypes.c_longlong, _i, _i, _vp]),
+    "avctc_softmax_backward": (_i, [_vp, _vp, _vp, ctypes.c_longlong, _i, _i, _vp]),
+    "avctc_colsum": (_i, [_vp, _i, ctypes.c_longlong, _i, ctypes.c_longlong, _vp, _i, _vp]),
+    "avctc_log_softmax_forward": (_i, [_vp, _i, _vp, _i, ctypes.c_longlong, _i, _vp]),
+    "avctc_log_softmax_backward": (_i, [_vp, _vp, _i, _vp, ctypes.c_longlong, _i, ctypes.c_longlong, _vp]),
 }
 
 

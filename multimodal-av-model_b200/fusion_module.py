@@ -1,0 +1,232 @@
+"""CrossAttentionFusion — drop-in for /root/reference/model/fusion_module.py:5-67 on sm_100a kernels.
+
+Same constructor, forward signature, return values and state_dict keys as the reference (its
+submodules are kept as parameter containers, so default initialisation consumes the RNG identically):
+
+    CrossAttentionFusion(visual_dim, audio_dim, fused_dim, num_heads=4)
+    forward(visual_feat[B,T_v,D_v], audio_feat[B,T_a,D_a], mask[B,T_a] int64) -> (fused_seq[B,T_v,2E], input_lengths[B])
+
+What runs where:
+  * speech-frame select + pad + linear/nearest resample + input_lengths (fusion_module.py:40-55,66):
+    avctc_resample_* (two launches, no host sync; the reference does B Python iterations and B .item()s)
+  * visual_proj, audio_proj, the MultiheadAttention in/out projections, Q.K^T, P.V, fusion_proj
+    (fusion_module.py:57-63) forward AND backward: avctc_gemm_bf16 = tcgen05.mma + TMEM + TMA, bf16 operands,
+    fp32 accumulation, transposed operands read in place (no transpose copies); softmax in fp32
+  * temporal_model (2-layer BiLSTM, fusion_module.py:64): torch.nn.LSTM / cuDNN, as SURVEY.md §7 scopes it
+    (row N1 of §8f is the follow-up)
+`cross_attn_visual` exists but is never used, exactly like the reference (its parameters get no gradient).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .gemm import gemm, operand
+
+_BF16 = torch.bfloat16
+
+
+def _bf16(t):
+    return t if t.dtype == _BF16 else t.to(_BF16)
+
+
+def _linear(x, w, b, out_dtype=_BF16):
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    return gemm(operand(x), operand(w), M, N, K, out, bias=b, bias_mode=1)
+
+
+def _dgrad(dy, w):
+    """dx[M,K] = dy[M,N] . W[N,K]   (W read in place as the MN-major operand)."""
+    M, N = dy.shape
+    K = w.shape[1]
+    out = torch.empty((M, K), dtype=_BF16, device=dy.device)
+    return gemm(operand(dy), operand(w, "mn"), M, K, N, out)
+
+
+def _wgrad(dy, x, out):
+    """out[N,K] (fp32) = dy[M,N]^T . x[M,K]   (both operands read in place as MN-major)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    return gemm(operand(dy, "mn"), operand(x, "mn"), N, K, M, out)
+
+
+def _colsum(x, out=None):
+    M, N = x.shape
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().avctc_colsum(x.data_ptr(), _lib.dtype_enum(x), M, N, x.stride(0), out.data_ptr(), 0,
+                                           _lib.stream_ptr(x.device)), "avctc_colsum")
+    return out
+
+
+class _FusionCoreFn(torch.autograd.Function):
+    """resample -> visual/audio projections -> cross attention (audio queries, visual keys/values) -> fusion_proj."""
+
+    @staticmethod
+    def forward(ctx, visual, audio, mask, num_heads, w_vp, b_vp, w_ap, b_ap, w_in, b_in, w_o, b_o, w_f, b_f):
+        _lib.require_cuda(visual, "visual_feat")
+        _lib.require_cuda(audio, "audio_feat")
+        if mask is None:
+            raise RuntimeError("mask is required (the reference indexes it unconditionally, fusion_module.py:44)")
+        dev = visual.device
+        B, T, Dv = visual.shape
+        _, Ta, Da = audio.shape
+        E = w_f.shape[0]
+        H = int(num_heads)
+        hd = E // H
+        if E % H or E % 8 or Dv % 8 or Da % 8:
+            raise RuntimeError("fused_dim, visual_dim and audio_dim must be multiples of 8 (TMA row alignment)")
+        M = B * T
+        L = _lib.lib()
+        st = _lib.stream_ptr(dev)
+        audio_c = audio.detach()
+        if audio_c.dtype not in (torch.float32, _BF16):
+            audio_c = audio_c.float()
+        audio_c = audio_c.contiguous()
+        mask_c = mask.to(device=dev, dtype=torch.long).contiguous()
+        xa = torch.empty((M, Da), dtype=_BF16, device=dev)
+        mask_out = torch.empty((B, T), dtype=torch.long, device=dev)
+        input_lengths = torch.empty(B, dtype=torch.long, device=dev)
+        rs_bytes = int(L.avctc_resample_workspace_bytes(B, Ta))
+        rs_ws = torch.empty(rs_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.avctc_resample_forward(audio_c.data_ptr(), _lib.dtype_enum(audio_c), mask_c.data_ptr(), B, Ta, Da,
+                                                T, xa.data_ptr(), mask_out.data_ptr(), input_lengths.data_ptr(),
+                                                rs_ws.data_ptr(), rs_bytes, st), "avctc_resample_forward")
+        xv = _bf16(visual.detach().reshape(M, Dv)).contiguous()
+        wb = [_bf16(w.detach()).contiguous() for w in (w_vp, w_ap, w_in, w_o, w_f)]
+        bs = [b.detach().float().contiguous() for b in (b_vp, b_ap, b_in, b_o, b_f)]
+        # The attention GEMMs address head h as 64-wide K blocks starting at column h*hd, so a head must own a
+        # multiple of 64 columns.  Other head sizes (toy configs) run on zero-padded in/out projection weights:
+        # the padded q/k/v columns are exactly 0, which changes no product.
+        hdp = (hd + 63) // 64 * 64
+        Ea = H * hdp
+        pad_idx = None
+        if hdp != hd:
+            pad_idx = (torch.arange(H, device=dev)[:, None] * hdp + torch.arange(hd, device=dev)[None, :]).reshape(-1)
+            w_in_p = torch.zeros((3 * Ea, E), dtype=_BF16, device=dev)
+            b_in_p = torch.zeros(3 * Ea, dtype=torch.float32, device=dev)
+            for part in range(3):
+                w_in_p[pad_idx + part * Ea] = wb[2][part * E:(part + 1) * E]
+                b_in_p[pad_idx + part * Ea] = bs[2][part * E:(part + 1) * E]
+            w_o_p = torch.zeros((E, Ea), dtype=_BF16, device=dev)
+            w_o_p[:, pad_idx] = wb[3]
+            wb[2], bs[2], wb[3] = w_in_p, b_in_p, w_o_p
+        Eo, E, hd = E, Ea, hdp          # from here on E / hd are the (possibly padded) attention widths
+        v = _linear(xv, wb[0], bs[0])
+        a = _linear(xa, wb[1], bs[1])
+        q = _linear(a, wb[2][:E], bs[2][:E])
+        kv = _linear(v, wb[2][E:], bs[2][E:])                     # [M, 2E]: keys | values
+        Tp = (T + 7) // 8 * 8
+        BH = B * H
+        alpha = float(Eo // H) ** -0.5
+        S = torch.empty((BH, T, Tp), dtype=torch.float32, device=dev)
+        gemm(operand(q, k_inner=hd, r_outer=T), operand(kv, k_inner=hd, r_outer=T), T, T, hd, S, batch=BH,
+             inner_count=H, ldc=Tp, c_outer=H * T * Tp, c_inner=T * Tp, alpha=alpha)
+        P = torch.empty((BH, T, Tp), dtype=_BF16, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.avctc_softmax_forward(S.data_ptr(), P.data_ptr(), BH * T, T, Tp, st), "avctc_softmax_forward")
+        o = torch.empty((M, E), dtype=_BF16, device=dev)
+        vv = kv[:, E:]
+        gemm(operand(P, z_outer=H, z_inner=1, kdim=T), operand(vv, "mn", k_outer=T, r_inner=hd), T, hd, T, o, batch=BH,
+             inner_count=H, ldc=E, c_outer=T * E, c_inner=hd)
+        ao = _linear(o, wb[3], bs[3])
+        f = _linear(ao, wb[4], bs[4], out_dtype=torch.float32)
+        ctx.save_for_backward(xv, xa, v, a, q, kv, P, o, ao, rs_ws, *wb)
+        ctx.dims = (B, T, Ta, Dv, Da, Eo, E, H, hd, Tp, alpha, audio.dtype, visual.dtype)
+        ctx.pad_idx = pad_idx
+        ctx.mark_non_differentiable(mask_out, input_lengths)
+        return f.view(B, T, Eo), mask_out, input_lengths
+
+    @staticmethod
+    def backward(ctx, df, _dm, _dl):
+        xv, xa, v, a, q, kv, P, o, ao, rs_ws, wb_vp, wb_ap, wb_in, wb_o, wb_f = ctx.saved_tensors
+        B, T, Ta, Dv, Da, Eo, E, H, hd, Tp, alpha, audio_dtype, visual_dtype = ctx.dims   # E, hd: padded widths
+        pad_idx = ctx.pad_idx
+        dev = df.device
+        M = B * T
+        BH = B * H
+        L = _lib.lib()
+        st = _lib.stream_ptr(dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        dfb = _bf16(df.reshape(M, Eo)).contiguous()
+        # fusion_proj
+        g_wf = _wgrad(dfb, ao, torch.empty((Eo, Eo), **f32)); g_bf = _colsum(dfb)
+        dao = _dgrad(dfb, wb_f)
+        # out_proj
+        g_wo = _wgrad(dao, o, torch.empty((Eo, E), **f32)); g_bo = _colsum(dao)
+        do = _dgrad(dao, wb_o)
+        # attention core
+        vv = kv[:, E:]
+        dP = torch.empty((BH, T, Tp), **f32)
+        gemm(operand(do, k_inner=hd, r_outer=T), operand(vv, k_inner=hd, r_outer=T), T, T, hd, dP, batch=BH,
+             inner_count=H, ldc=Tp, c_outer=H * T * Tp, c_inner=T * Tp)
+        dS = torch.empty((BH, T, Tp), dtype=_BF16, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.avctc_softmax_backward(P.data_ptr(), dP.data_ptr(), dS.data_ptr(), BH * T, T, Tp, st),
+                       "avctc_softmax_backward")
+        dq = torch.empty((M, E), dtype=_BF16, device=dev)
+        gemm(operand(dS, z_outer=H, z_inner=1, kdim=T), operand(kv[:, :E], "mn", k_outer=T, r_inner=hd), T, hd, T, dq,
+             batch=BH, inner_count=H, ldc=E, c_outer=T * E, c_inner=hd, alpha=alpha)
+        dkv = torch.empty((M, 2 * E), dtype=_BF16, device=dev)
+        gemm(operand(dS, "mn", z_outer=H, z_inner=1, rows=T, kdim=T), operand(q, "mn", k_outer=T, r_inner=hd), T, hd, T,
+             dkv[:, :E], batch=BH, inner_count=H, ldc=2 * E, c_outer=T * 2 * E, c_inner=hd, alpha=alpha)
+        gemm(operand(P, "mn", z_outer=H, z_inner=1, rows=T, kdim=T), operand(do, "mn", k_outer=T, r_inner=hd), T, hd, T,
+             dkv[:, E:], batch=BH, inner_count=H, ldc=2 * E, c_outer=T * 2 * E, c_inner=hd)
+        # in_proj (rows [0,E) = query projection of a; rows [E,3E) = key|value projections of v)
+        g_win = torch.empty((3 * E, Eo), **f32)
+        g_bin = torch.empty(3 * E, **f32)
+        _wgrad(dq, a, g_win[:E]); _colsum(dq, g_bin[:E])
+        _wgrad(dkv, v, g_win[E:]); _colsum(dkv, g_bin[E:])
+        da = _dgrad(dq, wb_in[:E])
+        dv = _dgrad(dkv, wb_in[E:])
+        if pad_idx is not None:          # drop the zero-padded head columns again
+            rows = torch.cat([pad_idx + part * E for part in range(3)])
+            g_win, g_bin, g_wo = g_win[rows].contiguous(), g_bin[rows].contiguous(), g_wo[:, pad_idx].contiguous()
+        # audio_proj / visual_proj
+        g_wap = _wgrad(da, xa, torch.empty((Eo, Da), **f32)); g_bap = _colsum(da)
+        g_wvp = _wgrad(dv, xv, torch.empty((Eo, Dv), **f32)); g_bvp = _colsum(dv)
+        d_visual = d_audio = None
+        if ctx.needs_input_grad[0]:
+            d_visual = _dgrad(dv, wb_vp).view(B, T, Dv).to(visual_dtype)
+        if ctx.needs_input_grad[1]:
+            dxa = _dgrad(da, wb_ap)
+            out_dtype = audio_dtype if audio_dtype in (torch.float32, _BF16) else torch.float32
+            d_audio = torch.empty((B, Ta, Da), dtype=out_dtype, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(L.avctc_resample_backward(dxa.data_ptr(), B, Ta, Da, T, rs_ws.data_ptr(), d_audio.data_ptr(),
+                                                     _lib.dtype_enum(d_audio), st), "avctc_resample_backward")
+            d_audio = d_audio.to(audio_dtype)
+        return (d_visual, d_audio, None, None, g_wvp, g_bvp, g_wap, g_bap, g_win, g_bin, g_wo, g_bo, g_wf, g_bf)
+
+
+class CrossAttentionFusion(nn.Module):
+    def __init__(self, visual_dim, audio_dim, fused_dim, num_heads=4):
+        super().__init__()
+        # same construction order as the reference (fusion_module.py:10-27): identical RNG use and state_dict keys
+        self.visual_proj = nn.Linear(visual_dim, fused_dim)
+        self.audio_proj = nn.Linear(audio_dim, fused_dim)
+        self.cross_attn_visual = nn.MultiheadAttention(embed_dim=fused_dim, num_heads=num_heads, batch_first=True)
+        self.cross_attn_audio = nn.MultiheadAttention(embed_dim=fused_dim, num_heads=num_heads, batch_first=True)
+        self.fusion_proj = nn.Linear(fused_dim, fused_dim)
+        self.temporal_model = nn.LSTM(input_size=fused_dim, hidden_size=fused_dim, num_layers=2, batch_first=True,
+                                      bidirectional=True)
+        self.num_heads = num_heads
+
+    def fused_projection(self, visual_feat, audio_feat, mask):
+        """Everything up to and including fusion_proj (fusion_module.py:40-63): (fused[B,T,E] fp32, mask[B,T], lengths)."""
+        at = self.cross_attn_audio
+        return _FusionCoreFn.apply(visual_feat, audio_feat, mask, self.num_heads,
+                                   self.visual_proj.weight, self.visual_proj.bias,
+                                   self.audio_proj.weight, self.audio_proj.bias,
+                                   at.in_proj_weight, at.in_proj_bias, at.out_proj.weight, at.out_proj.bias,
+                                   self.fusion_proj.weight, self.fusion_proj.bias)
+
+    def forward(self, visual_feat, audio_feat, mask=None):
+        fused, _mask_rs, input_lengths = self.fused_projection(visual_feat, audio_feat, mask)
+        fused_seq, _ = self.temporal_model(fused)          # cuDNN BiLSTM over all padded frames (fusion_module.py:64)
+        return fused_seq, input_lengths

@@ -1,0 +1,131 @@
+"""GPU: CrossAttentionFusion / CTCDecoder (tcgen05 GEMMs + glue kernels) against the reference fixtures
+(small dims) and the torch-CPU restatement (config-3 dims).  Tolerance (north_star): bf16 — operands are
+rounded to bf16 and accumulated in fp32, so activations agree to ~1e-2 relative of their scale; integer
+outputs (input_lengths, resampled mask) are exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_cases
+from oracle import torch_port as tp
+
+pytestmark = pytest.mark.gpu
+FUS = load_cases("fusion_cases.npz")
+
+
+def _pkg():
+    import multimodal_av_model_b200 as pkg
+    return pkg
+
+
+def relerr(a, b):
+    a = a.detach().float().cpu()
+    b = b.detach().float().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("name", sorted(FUS))
+def test_fusion_and_head_match_reference_fixture(name):
+    pkg = _pkg()
+    c = FUS[name]
+    dv, da = c["visual"].shape[-1], c["audio"].shape[-1]
+    e = c["param/fusion_proj.weight"].shape[0]
+    fus = pkg.CrossAttentionFusion(dv, da, e, num_heads=int(c["num_heads"]))
+    fus.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in c.items() if k.startswith("param/")})
+    dec = pkg.CTCDecoder(2 * e, c["dec/net.0.weight"].shape[0], blank_id=3)
+    dec.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in c.items() if k.startswith("dec/")})
+    fus.cuda(); dec.cuda()
+    vis = torch.from_numpy(c["visual"]).cuda().requires_grad_()
+    aud = torch.from_numpy(c["audio"]).cuda().requires_grad_()
+    fused, il = fus(vis, aud, mask=torch.from_numpy(c["mask"]).cuda())
+    lp = dec(fused)
+    (lp * torch.from_numpy(c["r"]).cuda()).sum().backward()
+    assert il.cpu().tolist() == c["input_lengths"].tolist()          # exact
+    assert relerr(fused, torch.from_numpy(c["fused"])) < 2e-2
+    assert (lp.cpu() - torch.from_numpy(c["log_probs"])).abs().max().item() < 3e-2
+    assert relerr(aud.grad, torch.from_numpy(c["grad_audio"])) < 5e-2
+    assert relerr(vis.grad, torch.from_numpy(c["grad_visual"])) < 5e-2
+    for k, p in list(fus.named_parameters()) + [("dec." + k, p) for k, p in dec.named_parameters()]:
+        g = c[f"dec_grad/{k[4:]}"] if k.startswith("dec.") else c[f"grad/{k}"]
+        if g.size == 0:
+            assert p.grad is None, k                                     # cross_attn_visual stays unused
+        else:
+            assert relerr(p.grad, torch.from_numpy(g)) < 5e-2, k
+
+
+def config3_inputs(B=32, Tv=150, Ta=249, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    vis = torch.randn(B, Tv, 512, generator=g)
+    aud = torch.randn(B, Ta, 1024, generator=g)
+    mask = torch.zeros(B, Ta, dtype=torch.long)
+    mask[:, :150] = 1
+    mask[:, 150:200] = 2
+    for b in range(B):
+        mask[b, Ta - (b % 7):] = 3               # per-sample padded tail; every sample keeps 200 speech frames
+    return vis, aud, mask
+
+
+def test_fusion_projection_config3_vs_torch_port():
+    pkg = _pkg()
+    torch.manual_seed(0)
+    ref = tp.FusionPort(512, 1024, 512)
+    ours = pkg.CrossAttentionFusion(512, 1024, 512)
+    ours.load_state_dict(ref.state_dict())
+    ours.cuda()
+    vis, aud, mask = config3_inputs(B=8)
+    v1, a1 = vis.clone().requires_grad_(), aud.clone().requires_grad_()
+    f_ref, m_ref = ref.projection(v1, a1, mask)
+    r = torch.randn_like(f_ref)
+    (f_ref * r).sum().backward()
+    v2, a2 = vis.cuda().requires_grad_(), aud.cuda().requires_grad_()
+    f, m, il = ours.fused_projection(v2, a2, mask.cuda())
+    (f * r.cuda()).sum().backward()
+    assert torch.equal(m.cpu(), m_ref)
+    assert il.cpu().tolist() == (m_ref != 0).sum(1).tolist()
+    assert relerr(f, f_ref) < 2e-2
+    assert relerr(a2.grad, a1.grad) < 5e-2
+    assert relerr(v2.grad, v1.grad) < 5e-2
+    for (k, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+        if q.grad is None:
+            assert p.grad is None
+        elif not k.startswith("temporal_model"):
+            assert relerr(p.grad, q.grad) < 5e-2, k
+
+
+def test_resample_edge_cases():
+    """equal lengths (no interpolation), a sample without speech, T_v > compacted length (upsampling)."""
+    pkg = _pkg()
+    torch.manual_seed(1)
+    for B, Tv, Ta, pattern in [(3, 9, 9, "all1"), (4, 12, 20, "one_empty"), (2, 40, 13, "up")]:
+        aud = torch.randn(B, Ta, 16)
+        mask = torch.ones(B, Ta, dtype=torch.long)
+        if pattern == "one_empty":
+            mask[1] = 0
+            mask[2, 5:] = 3
+            mask[3, ::2] = 2
+        if pattern == "up":
+            mask[0, 3:6] = 0
+            mask[1, 10:] = 3
+        a_ref, m_ref = tp.select_pad_resample(aud, mask, Tv)
+        ours = pkg.CrossAttentionFusion(8, 16, 8, num_heads=1).cuda()
+        vis = torch.zeros(B, Tv, 8).cuda()
+        f, m, il = ours.fused_projection(vis, aud.cuda(), mask.cuda())
+        assert torch.equal(m.cpu(), m_ref)
+        assert il.cpu().tolist() == (m_ref != 0).sum(1).tolist()
+
+
+def test_decoder_loss_branch_and_state_dict_keys():
+    pkg = _pkg()
+    torch.manual_seed(2)
+    dec = pkg.CTCDecoder(64, 30, blank_id=3).cuda()
+    assert list(dec.state_dict().keys()) == ["net.0.weight", "net.0.bias"]
+    x = torch.randn(2, 20, 64, device="cuda")
+    tg = torch.randint(4, 30, (2, 5), device="cuda")
+    il = torch.tensor([20, 18], device="cuda"); tl = torch.tensor([5, 4], device="cuda")
+    loss = dec(x, tg, il, tl)
+    lp = dec(x)
+    ref = torch.nn.functional.ctc_loss(lp.transpose(0, 1), tg, il, tl, blank=3, zero_infinity=True)
+    assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item())
+    fus = pkg.CrossAttentionFusion(512, 1024, 512)
+    want = tp.FusionPort(512, 1024, 512).state_dict()
+    assert {k: tuple(v.shape) for k, v in fus.state_dict().items()} == {k: tuple(v.shape) for k, v in want.items()}

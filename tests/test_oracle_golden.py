@@ -137,3 +137,72 @@ def test_interp_index_rules():
         x = torch.randn(2, n_in, 3, dtype=torch.float64)
         ref = F.interpolate(x.permute(0, 2, 1), size=n_out, mode="linear", align_corners=True).permute(0, 2, 1)
         assert np.abs(np_oracle.linear_align_corners(x.numpy(), n_out) - ref.numpy()).max() < 1e-12
+
+
+# ---------------------------------------------------------------- torch-CPU restatement (oracle/torch_port.py)
+def test_torch_port_fusion_and_head_match_reference():
+    import torch
+    from oracle import torch_port as tp
+    for name, c in FUS.items():
+        dv, da = c["visual"].shape[-1], c["audio"].shape[-1]
+        e = c["param/fusion_proj.weight"].shape[0]
+        fus = tp.FusionPort(dv, da, e, num_heads=int(c["num_heads"]))
+        fus.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in c.items() if k.startswith("param/")})
+        dec = tp.DecoderPort(2 * e, c["dec/net.0.weight"].shape[0], 3)
+        dec.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in c.items() if k.startswith("dec/")})
+        vis = torch.from_numpy(c["visual"]).requires_grad_()
+        aud = torch.from_numpy(c["audio"]).requires_grad_()
+        fused, il = fus(vis, aud, torch.from_numpy(c["mask"]))
+        lp = dec(fused)
+        (lp * torch.from_numpy(c["r"])).sum().backward()
+        assert il.tolist() == c["input_lengths"].tolist()
+        assert torch.allclose(fused, torch.from_numpy(c["fused"]), atol=1e-6)
+        assert torch.allclose(lp, torch.from_numpy(c["log_probs"]), atol=1e-5)
+        assert torch.allclose(aud.grad, torch.from_numpy(c["grad_audio"]), atol=1e-5)
+        assert torch.allclose(vis.grad, torch.from_numpy(c["grad_visual"]), atol=1e-5)
+        for k, p in fus.named_parameters():
+            g = c[f"grad/{k}"]
+            if g.size == 0:
+                assert p.grad is None           # cross_attn_visual is never used
+            else:
+                assert torch.allclose(p.grad, torch.from_numpy(g), atol=2e-5), k
+
+
+def test_torch_port_infonce_beam_and_step_match_reference():
+    import torch
+    from oracle import torch_port as tp
+    for name, c in NCE.items():
+        proj = None
+        if "w" in c:
+            proj = torch.nn.Linear(c["w"].shape[1], c["w"].shape[0])
+            proj.load_state_dict({"weight": torch.from_numpy(c["w"]), "bias": torch.from_numpy(c["b"])})
+        mid = torch.from_numpy(c["middle"]).requires_grad_()
+        loss = tp.contrastive_loss_with_mask(mid, torch.from_numpy(c["mask"]).reshape(-1), proj)
+        assert torch.allclose(loss, torch.from_numpy(c["loss"]), atol=1e-6)
+        if loss.grad_fn is not None:
+            loss.backward()
+            assert torch.allclose(mid.grad, torch.from_numpy(c["grad_middle"]), atol=1e-6)
+    for name, c in BEAM.items():
+        if name.startswith("topk"):
+            continue
+        assert tp.simple_beam_search(torch.from_numpy(c["lp"]), int(c["beam"]), int(c["blank"])) == c["ids"].tolist()
+    z = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "step_cases.npz"))
+    p = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param/")}
+    e = p["fusion_proj.weight"].shape[0]
+    fus = tp.FusionPort(p["visual_proj.weight"].shape[1], p["audio_proj.weight"].shape[1], e)
+    fus.load_state_dict(p)
+    dec = tp.DecoderPort(2 * e, z["dec/net.0.weight"].shape[0], 3)
+    dec.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("dec/")})
+    proj = torch.nn.Linear(z["proj/weight"].shape[1], z["proj/weight"].shape[0])
+    proj.load_state_dict({"weight": torch.from_numpy(z["proj/weight"]), "bias": torch.from_numpy(z["proj/bias"])})
+    feats = [dict(visual=torch.from_numpy(z[f"spk{s}/visual"]), audio=torch.from_numpy(z[f"spk{s}/audio"]),
+                  middle=torch.from_numpy(z[f"spk{s}/middle"]), mask=torch.from_numpy(z[f"spk{s}/mask"]),
+                  text=torch.from_numpy(z[f"spk{s}/text"]), text_len=torch.from_numpy(z[f"spk{s}/text_len"]))
+             for s in (1, 2)]
+    loss = tp.hot_path_losses(fus, dec, proj, feats, blank=3)
+    loss.backward()
+    assert torch.allclose(loss, torch.from_numpy(z["loss_total"]), atol=1e-6)
+    for k, prm in fus.named_parameters():
+        g = z[f"grad/{k}"]
+        if g.size:
+            assert torch.allclose(prm.grad, torch.from_numpy(g), atol=2e-5), k
