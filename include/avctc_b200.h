@@ -162,6 +162,22 @@ AVCTC_API int avctc_log_softmax_forward(const void* X, int in_dtype, void* Y, in
 AVCTC_API int avctc_log_softmax_backward(const void* Y, const void* dY, int dtype, void* dX_bf16, long long rows, int V,
                                long long ldx, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * InfoNCE — replaces contrastive_loss_with_mask after its optional projection
+ *   /root/reference/contrastive.py:13-44 (valid-row select, F.normalize, index sets, sim/TEMPERATURE,
+ *   -log_softmax(.).mean() for (weak,strong) * w_pos and (weak,neg) * w_neg), called at model/trainer.py:108-109.
+ * y [N,P] (fp32 or bf16, row stride ld): the projected (or raw) features of ALL B*T rows; flat_mask [N] int64 in
+ * {0,1,2,3}.  loss: 1 fp32.  Nothing is gathered on the host and no count leaves the device.  P <= 256.
+ * backward writes dy [N,P] (zero rows for mask==3) given the DEVICE scalar grad_out.
+ * ---------------------------------------------------------------------------------------------- */
+AVCTC_API size_t avctc_infonce_workspace_bytes(int N, int P);
+AVCTC_API int avctc_infonce_forward(const void* y, int dtype, long long ld, const int64_t* flat_mask, int N, int P,
+                          float temperature, float w_pos, float w_neg, float* loss, void* workspace,
+                          size_t workspace_bytes, void* stream);
+AVCTC_API int avctc_infonce_backward(const int64_t* flat_mask, int N, int P, float temperature, float w_pos, float w_neg,
+                           const float* grad_out, void* dy, int dtype, long long ld, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,3 +27,4 @@ def _optional(module, names):
 _optional("beam_search", ["simple_beam_search", "fast_decode", "beam_search_batch"])
 _optional("fusion_module", ["CrossAttentionFusion"])
 _optional("decoder", ["CTCDecoder"])
+_optional("contrastive", ["contrastive_loss_with_mask"])

@@ -41,6 +41,11 @@ SIGNATURES = {
     "avctc_colsum": (_i, [_vp, _i, ctypes.c_longlong, _i, ctypes.c_longlong, _vp, _i, _vp]),
     "avctc_log_softmax_forward": (_i, [_vp, _i, _vp, _i, ctypes.c_longlong, _i, _vp]),
     "avctc_log_softmax_backward": (_i, [_vp, _vp, _i, _vp, ctypes.c_longlong, _i, ctypes.c_longlong, _vp]),
+    "avctc_infonce_workspace_bytes": (_sz, [_i, _i]),
+    "avctc_infonce_forward": (_i, [_vp, _i, ctypes.c_longlong, _vp, _i, _i, ctypes.c_float, ctypes.c_float,
+                                   ctypes.c_float, _vp, _vp, _sz, _vp]),
+    "avctc_infonce_backward": (_i, [_vp, _i, _i, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp, _vp, _i,
+                                    ctypes.c_longlong, _vp, _sz, _vp]),
 }
 
 

@@ -1,0 +1,81 @@
+"""contrastive_loss_with_mask — drop-in for /root/reference/contrastive.py:8-44 on the fused sm_100a kernel.
+
+Same signature, same module constants, same result:
+
+    contrastive_loss_with_mask(middle_feat[B,T,D], flat_mask[B*T] int64, projection_layer=None) -> 0-dim tensor
+
+The optional projection is the caller's module, exactly as in the reference; when it is an nn.Linear fed with
+bf16 features (the training path under autocast) it runs on the tcgen05 GEMM, otherwise the module is simply
+called (fp32 features keep fp32 arithmetic for the 1e-4 parity bound).  It is applied to all B*T rows instead of
+the mask!=3 subset: rows with mask 3 are then ignored by the kernel, which avoids the reference's boolean-index
+host sync and changes no value.  Everything after the projection — normalise, row sets, similarity / 0.07,
+log-softmax, the two means and their weights — is one fused op (csrc/infonce.cu) with a hand-written backward.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .gemm import LinearFn
+
+TEMPERATURE = 0.07
+WEIGHT_POS_ALIGN = 1.0
+WEIGHT_NEG_SUPPRESS = 0.3
+
+
+class _InfoNCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, flat_mask, temperature, w_pos, w_neg):
+        _lib.require_cuda(y, "features")
+        dev = y.device
+        yd = y.detach()
+        if yd.dtype not in (torch.float32, torch.bfloat16):
+            yd = yd.float()
+        if yd.stride(-1) != 1:
+            yd = yd.contiguous()
+        N, P = yd.shape
+        mask = flat_mask.to(device=dev, dtype=torch.long).contiguous()
+        if mask.numel() != N:
+            raise RuntimeError("flat_mask must have B*T elements")
+        L = _lib.lib()
+        ws_bytes = int(L.avctc_infonce_workspace_bytes(N, P))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.avctc_infonce_forward(yd.data_ptr(), _lib.dtype_enum(yd), yd.stride(0), mask.data_ptr(), N, P,
+                                               float(temperature), float(w_pos), float(w_neg), loss.data_ptr(),
+                                               ws.data_ptr(), ws_bytes, _lib.stream_ptr(dev)), "avctc_infonce_forward")
+        ctx.save_for_backward(mask, ws)
+        ctx.meta = (N, P, float(temperature), float(w_pos), float(w_neg), y.dtype, ws_bytes)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        mask, ws = ctx.saved_tensors
+        N, P, temperature, w_pos, w_neg, ydtype, ws_bytes = ctx.meta
+        dev = gout.device
+        go = gout.detach().float().reshape(1).contiguous()
+        out_dtype = ydtype if ydtype in (torch.float32, torch.bfloat16) else torch.float32
+        dy = torch.empty((N, P), dtype=out_dtype, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().avctc_infonce_backward(mask.data_ptr(), N, P, temperature, w_pos, w_neg, go.data_ptr(),
+                                                         dy.data_ptr(), _lib.dtype_enum(dy), P, ws.data_ptr(), ws_bytes,
+                                                         _lib.stream_ptr(dev)), "avctc_infonce_backward")
+        return dy.to(ydtype), None, None, None, None
+
+
+def contrastive_loss_with_mask(middle_feat, flat_mask, projection_layer=None):
+    B, T_enc, D = middle_feat.shape
+    flat_feat = middle_feat.reshape(B * T_enc, D)
+    if projection_layer is not None:
+        use_tc = (isinstance(projection_layer, nn.Linear) and flat_feat.is_cuda and D % 8 == 0 and
+                  (flat_feat.dtype == torch.bfloat16 or
+                   (torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16)))
+        if use_tc:
+            flat_feat = LinearFn.apply(flat_feat, projection_layer.weight, projection_layer.bias)
+        else:
+            flat_feat = projection_layer(flat_feat)
+    loss = _InfoNCEFn.apply(flat_feat, flat_mask, TEMPERATURE, WEIGHT_POS_ALIGN, WEIGHT_NEG_SUPPRESS)
+    # the reference starts from a fresh requires-grad zero (contrastive.py:28), so the result always requires grad
+    return loss + torch.zeros((), device=loss.device, requires_grad=True)

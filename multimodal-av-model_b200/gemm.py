@@ -62,3 +62,43 @@ def linear_nt(x: torch.Tensor, w: torch.Tensor, bias=None, out_dtype=torch.bfloa
     N = w.shape[0]
     out = torch.empty((M, N), dtype=out_dtype, device=x.device)
     return gemm(operand(x), operand(w), M, N, K, out, bias=bias, bias_mode=1, alpha=alpha)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMM with its backward (dgrad, wgrad, bias colsum); bf16 operands."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        shp = x.shape
+        K = shp[-1]
+        xb = x.detach().reshape(-1, K)
+        xb = (xb if xb.dtype == torch.bfloat16 else xb.to(torch.bfloat16)).contiguous()
+        wb = w.detach().to(torch.bfloat16).contiguous()
+        y = linear_nt(xb, wb, b.detach().float().contiguous() if b is not None else None, out_dtype=torch.bfloat16)
+        ctx.save_for_backward(xb, wb)
+        ctx.meta = (shp, x.dtype, b is not None)
+        return y.view(*shp[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, wb = ctx.saved_tensors
+        shp, xdtype, has_b = ctx.meta
+        N, K = wb.shape
+        M = xb.shape[0]
+        d = dy.reshape(M, N)
+        d = (d if d.dtype == torch.bfloat16 else d.to(torch.bfloat16)).contiguous()
+        dev = d.device
+        g_w = torch.empty((N, K), dtype=torch.float32, device=dev)
+        gemm(operand(d, "mn"), operand(xb, "mn"), N, K, M, g_w)
+        g_b = None
+        if has_b:
+            g_b = torch.empty(N, dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().avctc_colsum(d.data_ptr(), _lib.BF16, M, N, N, g_b.data_ptr(), 0,
+                                                   _lib.stream_ptr(dev)), "avctc_colsum")
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dxb = torch.empty((M, K), dtype=torch.bfloat16, device=dev)
+            gemm(operand(d), operand(wb, "mn"), M, K, N, dxb)
+            dx = dxb.view(shp).to(xdtype)
+        return dx, g_w, g_b
