@@ -28,3 +28,5 @@ _optional("beam_search", ["simple_beam_search", "fast_decode", "beam_search_batc
 _optional("fusion_module", ["CrossAttentionFusion"])
 _optional("decoder", ["CTCDecoder"])
 _optional("contrastive", ["contrastive_loss_with_mask"])
+_optional("trainer", ["MultimodalTrainer"])
+_optional("encoders", ["VisualEncoder", "AudioEncoder"])

@@ -1,0 +1,124 @@
+"""Producers that feed the hot path: VisualEncoder and AudioEncoder.
+
+These are OUT OF SCOPE for hand-written kernels (frozen 3D-conv + ResNet-18 front-end; third-party wav2vec2)
+and stay PyTorch/cuDNN/HF, exactly as SURVEY.md §2 scopes them.  They exist here only so that a full training
+step (BASELINE config 4) can run end to end on the GPU box, where /root/reference is absent.  Module and
+parameter names follow /root/reference/model/encoder.py:6-100 so reference checkpoints load unchanged
+(`frontend3D.*`, `trunk.layer{1..4}.*`, `model.*`).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+
+def _act(kind, channels):
+    return nn.PReLU(channels) if kind == "prelu" else nn.ReLU(inplace=True)
+
+
+class BasicBlock(nn.Module):
+    """3x3-3x3 residual block with a per-channel PReLU (encoder.py:6-22)."""
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, relu_type="prelu"):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.relu = _act(relu_type, planes)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, stride=1, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = downsample
+
+    def forward(self, x):
+        skip = x if self.downsample is None else self.downsample(x)
+        y = self.bn2(self.conv2(self.relu(self.bn1(self.conv1(x)))))
+        return self.relu(y + skip)
+
+
+class ResNet(nn.Module):
+    """ResNet trunk without stem: four stages of `layers[i]` blocks, widths 64/128/256/512 (encoder.py:24-53)."""
+
+    def __init__(self, block, layers, relu_type="prelu"):
+        super().__init__()
+        self.inplanes = 64
+        widths, strides = (64, 128, 256, 512), (1, 2, 2, 2)
+        for i, (w, s, n) in enumerate(zip(widths, strides, layers), start=1):
+            setattr(self, f"layer{i}", self._stage(block, w, n, s, relu_type))
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+
+    def _stage(self, block, planes, blocks, stride, relu_type):
+        down = None
+        if stride != 1 or self.inplanes != planes:
+            down = nn.Sequential(nn.Conv2d(self.inplanes, planes, kernel_size=1, stride=stride, bias=False),
+                                 nn.BatchNorm2d(planes))
+        mods = [block(self.inplanes, planes, stride, down, relu_type)]
+        self.inplanes = planes
+        mods += [block(planes, planes, relu_type=relu_type) for _ in range(blocks - 1)]
+        return nn.Sequential(*mods)
+
+    def forward(self, x):
+        for i in range(1, 5):
+            x = getattr(self, f"layer{i}")(x)
+        return torch.flatten(self.avgpool(x), 1)
+
+
+class VisualEncoder(nn.Module):
+    """[B,1,T,96,96] -> [B,T,512]: Conv3d(1->64,(5,7,7),s(1,2,2)) + BN + PReLU + MaxPool3d, then a per-frame
+    ResNet-18 trunk (encoder.py:57-75)."""
+
+    def __init__(self, relu_type="prelu"):
+        super().__init__()
+        self.frontend3D = nn.Sequential(
+            nn.Conv3d(1, 64, kernel_size=(5, 7, 7), stride=(1, 2, 2), padding=(2, 3, 3), bias=False),
+            nn.BatchNorm3d(64),
+            _act(relu_type, 64),
+            nn.MaxPool3d(kernel_size=(1, 3, 3), stride=(1, 2, 2), padding=(0, 1, 1)))
+        self.trunk = ResNet(BasicBlock, [2, 2, 2, 2], relu_type=relu_type)
+        self.output_dim = 512
+
+    def forward(self, x):
+        b = x.shape[0]
+        y = self.frontend3D(x)                                   # [B,64,T,H',W']
+        t, h, w = y.shape[2:]
+        y = y.transpose(1, 2).reshape(b * t, 64, h, w)
+        return self.trunk(y).view(b, t, 512)
+
+
+def xlsr_large_config(**overrides):
+    """Wav2Vec2 XLSR-53-large layout (what kresnik/wav2vec2-large-xlsr-korean uses), for offline random init."""
+    from transformers import Wav2Vec2Config
+    cfg = dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096,
+               feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=True, num_conv_pos_embeddings=128,
+               num_conv_pos_embedding_groups=16)
+    cfg.update(overrides)
+    return Wav2Vec2Config(**cfg)
+
+
+class AudioEncoder(nn.Module):
+    """HF Wav2Vec2Model wrapper (encoder.py:80-100): returns (last_hidden_state, mean of hidden_states[6:10]).
+    `config=` builds a randomly initialised model without touching the network (bench / tests)."""
+
+    def __init__(self, model_name="kresnik/wav2vec2-large-xlsr-korean", freeze=True, config=None):
+        super().__init__()
+        from transformers import Wav2Vec2Model
+        if config is not None:
+            config.output_hidden_states = True
+            self.model = Wav2Vec2Model(config)
+        else:
+            self.model = Wav2Vec2Model.from_pretrained(model_name, output_hidden_states=True)
+        self.output_dim = self.model.config.hidden_size
+        if freeze:
+            self.model.requires_grad_(False)
+
+    def forward(self, x, attention_mask=None):
+        if attention_mask is not None:
+            attention_mask = attention_mask.long()
+        out = self.model(input_values=x, attention_mask=attention_mask, return_dict=True)
+        middle = torch.stack(out.hidden_states[6:10], dim=0).mean(dim=0)
+        return out.last_hidden_state, middle
+
+
+def unfreeze_middle_layers(model):
+    """main.py:26-31: only encoder.layers.6..9 of the wav2vec2 model train."""
+    tags = tuple(f"encoder.layers.{i}." for i in range(6, 10))
+    for name, p in model.named_parameters():
+        p.requires_grad = any(t in name for t in tags)

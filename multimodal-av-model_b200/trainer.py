@@ -1,0 +1,220 @@
+"""MultimodalTrainer — drop-in for /root/reference/model/trainer.py:12-252 with the hot path on sm_100a kernels.
+
+Same constructor, attributes and methods:
+
+    MultimodalTrainer(visual_encoder, audio_encoder, fusion_module, decoder1, tokenizer,
+                      learning_rate=1e-4, device="cuda", lambda_=0.1)
+    .train_epoch(dataloader) -> float          .evaluate(dataloader) -> (avg_loss, avg_wer)
+    .ctc_decode(pred_ids)                      .crop_or_pad_feat(feat, target_len)
+    attributes: visual_encoder audio_encoder fusion_module decoder1 tokenizer optimizer device lambda_ ctc_loss
+
+Differences that matter (all deliberate, none changes a result):
+  * the CTC loss, InfoNCE, fusion module, CTC head and beam search are this package's kernels
+  * mixed precision is bf16 autocast (no GradScaler needed); the reference uses fp16 + GradScaler (trainer.py:9,40)
+  * the reference's per-sample label sanity prints (trainer.py:77-85, 3B host syncs per step) are dropped
+  * evaluate() decodes a whole batch with one beam-search launch instead of 2B Python loops
+  * when torch.distributed is initialised the step is utterance-sharded data parallel: every rank runs its own
+    batch, gradients are averaged with a bucketed NCCL all-reduce overlapped with backward (ddp.py)
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .beam_search import beam_search_batch, fast_decode
+from .contrastive import contrastive_loss_with_mask
+from .ctc import CTCLoss
+from .ddp import GradBucketReducer, broadcast_module
+
+
+def word_error_rate(refs, hyps):
+    """jiwer.wer(refs, hyps) semantics: total word-level edit distance / total reference words."""
+    try:
+        from jiwer import wer as _wer
+        return _wer(refs, hyps)
+    except Exception:
+        pass
+    edits = words = 0
+    for r, h in zip(refs, hyps):
+        r, h = r.split(), h.split()
+        prev = list(range(len(h) + 1))
+        for i, rw in enumerate(r, 1):
+            cur = [i] + [0] * len(h)
+            for j, hw in enumerate(h, 1):
+                cur[j] = min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (rw != hw))
+            prev = cur
+        edits += prev[-1]
+        words += len(r)
+    return edits / words if words else (0.0 if edits == 0 else float("inf"))
+
+
+def _log_softmax_again(lp):
+    """evaluate() re-normalises the decoder's log-probs (trainer.py:212,221); kept for bit-faithful inputs to
+    the eval CTC loss and the beam search."""
+    x = lp.detach().float().contiguous()
+    out = torch.empty_like(x)
+    V = x.shape[-1]
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().avctc_log_softmax_forward(x.data_ptr(), _lib.F32, out.data_ptr(), _lib.F32, x.numel() // V, V,
+                                                        _lib.stream_ptr(x.device)), "avctc_log_softmax_forward")
+    return out
+
+
+class MultimodalTrainer:
+    def __init__(self, visual_encoder, audio_encoder, fusion_module, decoder1, tokenizer, learning_rate=1e-4,
+                 device="cuda", lambda_=0.1):
+        self.visual_encoder = visual_encoder.to(device)
+        self.audio_encoder = audio_encoder.to(device)
+        self.fusion_module = fusion_module.to(device)
+        self.decoder1 = decoder1.to(device)
+        self.tokenizer = tokenizer
+        self.device = device
+        self.lambda_ = lambda_
+        self.ctc_loss = CTCLoss(blank=tokenizer.blank_id, zero_infinity=True)
+        self.parameters = (list(self.visual_encoder.parameters()) + list(self.audio_encoder.parameters()) +
+                           list(self.fusion_module.parameters()) + list(self.decoder1.parameters()))
+        self.optimizer = torch.optim.Adam([
+            {"params": self.visual_encoder.parameters(), "lr": learning_rate},
+            {"params": self.audio_encoder.parameters(), "lr": 2e-5},
+            {"params": self.fusion_module.parameters(), "lr": learning_rate},
+            {"params": self.decoder1.parameters(), "lr": learning_rate}])
+        self.autocast_dtype = torch.bfloat16
+        self.projection_layer = None
+        self.verbose = True
+        self.beam_width = 5                       # trainer.py:230,237
+        self.world_size = dist.get_world_size() if dist.is_initialized() else 1
+        self._reducer = None
+        if self.world_size > 1:
+            for m in (self.visual_encoder, self.audio_encoder, self.fusion_module, self.decoder1):
+                broadcast_module(m)
+            self._reducer = GradBucketReducer(self.parameters)
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def crop_or_pad_feat(self, feat, target_len):
+        if feat.size(0) >= target_len:
+            return feat[:target_len]
+        pad = torch.zeros(target_len - feat.size(0), feat.size(1), device=feat.device)
+        return torch.cat([feat, pad], dim=0)
+
+    def ctc_decode(self, pred_ids):
+        """Greedy collapse of trainer.py:168-177: blanks are skipped WITHOUT resetting `prev`."""
+        out, prev = [], None
+        blank = self.tokenizer.blank_id
+        for idx in pred_ids:
+            if idx == blank:
+                continue
+            if idx != prev:
+                out.append(idx)
+            prev = idx
+        return out
+
+    def _to_dev(self, batch):
+        dev = self.device
+        g = lambda k: batch[k].to(dev, non_blocking=True)
+        lips = [g("lip1").permute(0, 2, 1, 3, 4).contiguous(), g("lip2").permute(0, 2, 1, 3, 4).contiguous()]
+        return dict(lips=lips, audio=g("audio"), masks=[g("mask1"), g("mask2")], texts=[g("text1"), g("text2")],
+                    lens=[g("text1_lengths"), g("text2_lengths")])
+
+    def _ensure_projection(self, D):
+        if self.projection_layer is None:           # trainer.py:105-106: created lazily, once per epoch
+            self.projection_layer = nn.Linear(D, 128).to(self.device)
+            if self.world_size > 1:
+                broadcast_module(self.projection_layer)
+
+    def hot_path_loss(self, visual_feats, audio_feats, middle_feats, masks, texts, lens):
+        """trainer.py:98-119 from encoder features on (two speakers): returns (total, ctc1, ctc2, con1, con2)."""
+        ctc, con = [], []
+        for s in range(2):
+            t_enc = audio_feats[s].shape[1]
+            mask_ds = F.interpolate(masks[s].unsqueeze(1).float(), size=t_enc, mode="nearest").squeeze(1).long()
+            self._ensure_projection(audio_feats[s].shape[2])
+            con.append(contrastive_loss_with_mask(middle_feats[s], mask_ds.reshape(-1), projection_layer=self.projection_layer))
+            fused, input_lengths = self.fusion_module(visual_feats[s], audio_feats[s], mask=mask_ds)
+            log_probs = self.decoder1(fused)
+            ctc.append(self.ctc_loss(log_probs.transpose(0, 1), texts[s], input_lengths, lens[s]))
+            if s == 0:
+                self._last_log_probs = log_probs
+        total = (ctc[0] + ctc[1]) / 2 + self.lambda_ * (con[0] + con[1]) / 2
+        return total, ctc[0], ctc[1], con[0], con[1]
+
+    def train_step(self, batch):
+        """One optimisation step on one collated batch (the body of the reference's loop, trainer.py:64-125).
+        Returns the detached total loss (device tensor; no host sync)."""
+        self.optimizer.zero_grad()
+        with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=str(self.device).startswith("cuda")):
+            d = self._to_dev(batch)
+            vis = [self.visual_encoder(d["lips"][0]), self.visual_encoder(d["lips"][1])]
+            aud, mid = [], []
+            for s in range(2):
+                a, m = self.audio_encoder(d["audio"], attention_mask=(d["masks"][s] != 3))
+                aud.append(a); mid.append(m)
+            total, c1, c2, k1, k2 = self.hot_path_loss(vis, aud, mid, d["masks"], d["texts"], d["lens"])
+        total.backward()
+        if self._reducer is not None:
+            self._reducer.finish()
+        self.optimizer.step()
+        self._last_parts = (c1.detach(), c2.detach(), k1.detach(), k2.detach())
+        return total.detach()
+
+    # ------------------------------------------------------------------------------------------ epochs
+    def train_epoch(self, dataloader):
+        for m in (self.visual_encoder, self.audio_encoder, self.fusion_module, self.decoder1):
+            m.train()
+        self.projection_layer = None
+        total_loss = torch.zeros((), device=self.device)
+        n = 0
+        for batch_idx, batch in enumerate(dataloader):
+            try:
+                loss = self.train_step(batch)
+                total_loss += loss.float()
+                if self.verbose and batch_idx % 100 == 0:
+                    c1, c2, k1, k2 = (float(x) for x in self._last_parts)
+                    print(f"[Batch {batch_idx}] CTC1: {c1:.4f}, CTC2: {c2:.4f}, Contrast1: {k1:.4f}, "
+                          f"Contrast2: {k2:.4f}, Total: {float(loss):.4f}", flush=True)
+                    pred = torch.argmax(self._last_log_probs[0], dim=-1).cpu().tolist()
+                    print(f"[pred] {self.tokenizer.decode(self.ctc_decode(pred))}", flush=True)
+            except Exception as e:                      # same policy as trainer.py:162-164
+                print(f"Error at batch {batch_idx}: {e}", flush=True)
+                continue
+            n += 1
+        return float(total_loss) / max(len(dataloader), 1)
+
+    def evaluate(self, dataloader):
+        for m in (self.visual_encoder, self.audio_encoder, self.fusion_module, self.decoder1):
+            m.eval()
+        refs, hyps = [[], []], [[], []]
+        total_loss = 0.0
+        blank = self.tokenizer.blank_id
+        with torch.no_grad():
+            for batch in dataloader:
+                d = self._to_dev(batch)
+                with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=str(self.device).startswith("cuda")):
+                    lps, losses = [], []
+                    for s in range(2):
+                        vis = self.visual_encoder(d["lips"][s])
+                        aud, _ = self.audio_encoder(d["audio"], attention_mask=(d["masks"][s] != 3))
+                        t_enc = aud.shape[1]
+                        mask_ds = F.interpolate(d["masks"][s].unsqueeze(1).float(), size=t_enc, mode="nearest").squeeze(1).long()
+                        fused, il = self.fusion_module(vis, aud, mask_ds)
+                        lp = _log_softmax_again(self.decoder1(fused))
+                        losses.append(self.ctc_loss(lp.transpose(0, 1), d["texts"][s], il, d["lens"][s]))
+                        lps.append(lp)
+                total_loss += (losses[0].item() + losses[1].item()) / 2
+                B = lps[0].shape[0]
+                ids = beam_search_batch(torch.cat(lps, 0), beam_width=self.beam_width, blank=blank)   # all 2B at once
+                lens_h = [d["lens"][0].cpu().tolist(), d["lens"][1].cpu().tolist()]
+                texts_h = [d["texts"][0].cpu(), d["texts"][1].cpu()]
+                for i in range(B):
+                    for s in range(2):
+                        hyps[s].append(fast_decode(ids[s * B + i], self.tokenizer))
+                        refs[s].append(self.tokenizer.decode(texts_h[s][i][:lens_h[s][i]].tolist()))
+        wer1 = word_error_rate(refs[0], hyps[0])
+        wer2 = word_error_rate(refs[1], hyps[1])
+        avg_wer = (wer1 + wer2) / 2
+        avg_loss = total_loss / max(len(dataloader), 1)
+        if self.verbose:
+            print(f"[Eval] WER1: {wer1:.3f}, WER2: {wer2:.3f}, Avg: {avg_wer:.3f}, Loss: {avg_loss:.4f}")
+        return avg_loss, avg_wer

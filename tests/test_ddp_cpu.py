@@ -1,0 +1,75 @@
+"""CPU (gloo, world_size 2): the N>1 host logic — utterance sharding and the bucketed gradient all-reduce."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, overlap, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from multimodal_av_model_b200 import ddp
+    r, _, w = ddp.init_distributed("gloo")
+    torch.manual_seed(0)                                   # identical init on both ranks
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    unused = torch.nn.Linear(4, 4)                          # never receives a gradient (cf. cross_attn_visual)
+    if rank == 1:
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(1.0)                                 # diverge on purpose; broadcast must repair it
+    ddp.broadcast_module(model)
+    params = list(model.parameters()) + list(unused.parameters())
+    red = ddp.GradBucketReducer(params, bucket_bytes=64, overlap=overlap)
+    g = torch.Generator().manual_seed(100)
+    x_all = torch.randn(8, 6, generator=g); y_all = torch.randn(8, 3, generator=g)
+    lo, hi = ddp.shard_range(8, r, w)
+    for step in range(2):
+        model.zero_grad()
+        loss = ((model(x_all[lo:hi]) - y_all[lo:hi]) ** 2).mean()
+        loss.backward()
+        red.finish()
+    grads = [p.grad.clone() for p in model.parameters()]
+    # single-process truth: average of the two shard gradients
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    acc = [torch.zeros_like(p) for p in ref.parameters()]
+    for rr in range(w):
+        a, b = ddp.shard_range(8, rr, w)
+        ref.zero_grad()
+        ((ref(x_all[a:b]) - y_all[a:b]) ** 2).mean().backward()
+        for t, p in zip(acc, ref.parameters()):
+            t += p.grad / w
+    ok = all(torch.allclose(a, b, atol=1e-6) for a, b in zip(grads, acc)) and all(p.grad is None for p in unused.parameters())
+    q.put((rank, bool(ok), red.grad_bytes()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_bucketed_allreduce_equals_averaged_shard_gradients(overlap):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29611 + int(overlap)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, overlap, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+
+
+def test_shard_range_partitions_everything():
+    sys.path.insert(0, ROOT)
+    from multimodal_av_model_b200 import ddp
+    for n in (0, 1, 7, 4096):
+        for w in (1, 2, 3, 8):
+            spans = [ddp.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
