@@ -1,0 +1,449 @@
+#!/usr/bin/env python
+"""bench.py — the AV-CTC hot path on B200, next to the reference's CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|ctc|beam|fusion]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Headline (BASELINE.json metric "train utt/s at 1/2/4/8 B200; CTC loss GB/s; beam-search decode utt/s"):
+  workload = BASELINE config 4: full AV-CTC + InfoNCE training step, 8 utterance pairs per GPU, 5 s of 16 kHz
+  audio (T_enc 249) + 150 lip frames, 800-piece vocab (blank 3), random-init encoders, utterance-sharded data
+  parallel.  "value" = utterances/s of the whole job with the batch resident in HBM; "e2e" = the same step fed
+  from pinned host memory through MultimodalTrainer.train_step (H2D of the batch and a D2H read of the loss
+  inside the timed region).  The same JSON line carries the other two parts of the metric measured live:
+  "ctc" (config 2, GB/s, the "roofline" object is this kernel pair), "beam" (config 5, utt/s), plus "fusion"
+  (config 3, tensor-pipe fraction) and "hot_path" (the step from encoder features on).
+  --impl reference times the oracle port of the reference (torch CPU ops, oracle/torch_port.py) on the host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+PAIRS_PER_GPU = 8          # main.py:88 batch_size=8 pairs -> 16 utterance streams per step per GPU
+SECONDS = 5.0
+T_V = 150
+VOCAB, BLANK = 800, 3
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def build_models(device, seed=0):
+    import multimodal_av_model_b200 as pkg
+    from multimodal_av_model_b200.encoders import unfreeze_middle_layers, xlsr_large_config
+    from multimodal_av_model_b200.synthetic import CharTokenizer
+    torch.manual_seed(seed)
+    vis = pkg.VisualEncoder(relu_type="prelu")
+    for p in vis.parameters():                 # main.py:100-103
+        p.requires_grad = False
+    aud = pkg.AudioEncoder(freeze=True, config=xlsr_large_config())
+    unfreeze_middle_layers(aud.model)          # main.py:105-106
+    fus = pkg.CrossAttentionFusion(512, 1024, 512)
+    dec = pkg.CTCDecoder(1024, VOCAB, blank_id=BLANK)
+    tr = pkg.MultimodalTrainer(vis, aud, fus, dec, CharTokenizer(VOCAB), device=device)
+    tr.verbose = False
+    for m in (vis, aud, fus, dec):
+        m.train()
+    return tr
+
+
+def timed_loop(fn, steps, warmup, device, world):
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([a.elapsed_time(b)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def bench_train(args, rank, local, world, device):
+    from multimodal_av_model_b200 import _lib
+    from multimodal_av_model_b200.synthetic import make_batch
+    tr = build_models(device)
+    host = make_batch(pairs=PAIRS_PER_GPU, seconds=SECONDS, t_v=T_V, vocab=VOCAB, seed=1234 + rank, pin=True)
+    dev_batch = {k: v.to(device) for k, v in host.items()}
+    utt_per_step = 2 * PAIRS_PER_GPU * world
+
+    def step_resident():
+        tr.train_step(dev_batch)
+
+    def step_e2e():
+        return float(tr.train_step(host))          # H2D of the pinned batch + D2H read of the loss
+
+    c0 = _lib.launch_count
+    with ClockSampler(local) as cs:
+        ms = timed_loop(step_resident, args.steps, args.warmup, device, world)
+    launches = (_lib.launch_count - c0) // (args.steps + args.warmup)
+    ms_e2e = timed_loop(step_e2e, args.steps, max(1, args.warmup // 2), device, world)
+    h2d = int(sum(v.numel() * v.element_size() for k, v in host.items() if not k.endswith("_lengths") or k.startswith("text")))
+    grad_params = sum(p.numel() for p in tr.parameters if p.requires_grad)
+    out = dict(value=utt_per_step * args.steps / (ms / 1e3), ms_per_step=ms / args.steps,
+               e2e=dict(value=utt_per_step * args.steps / (ms_e2e / 1e3), unit="utt/s", h2d_bytes_per_step=h2d,
+                        d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
+               gpu_launches=int(launches), clocks=cs.summary(), allreduce_bytes_per_step=grad_params * 4 if world > 1 else 0)
+    # hot path only (number A): from encoder features on, same trainer
+    from multimodal_av_model_b200.synthetic import make_features
+    f = make_features(pairs=PAIRS_PER_GPU, t_v=T_V, t_enc=249, seed=1234 + rank, dtype=torch.bfloat16)
+    fd = {k: [t.to(device) for t in v] for k, v in f.items()}
+    for k in ("audio", "middle"):
+        fd[k] = [t.requires_grad_() for t in fd[k]]
+
+    def hot_step():
+        tr.optimizer.zero_grad(set_to_none=True)
+        for k in ("audio", "middle"):
+            for t in fd[k]:
+                t.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            total = tr.hot_path_loss(fd["visual"], fd["audio"], fd["middle"], fd["masks"], fd["texts"], fd["lens"])[0]
+        total.backward()
+    ms_hot = timed_loop(hot_step, args.steps, args.warmup, device, world)
+    out["hot_path"] = dict(value=utt_per_step * args.steps / (ms_hot / 1e3), unit="utt/s", ms_per_step=ms_hot / args.steps,
+                           note="fusion+CTC head+CTC+InfoNCE fwd+bwd from encoder features on (no encoders, no optimizer)")
+    return out, tr
+
+
+def l2_flusher(device):
+    buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    return lambda: buf.zero_()
+
+
+def event_time(fn, iters, warm, flush, device):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize(device)
+        ts.append(a.elapsed_time(b))
+    return float(np.mean(ts)), float(np.min(ts))
+
+
+def ctc_case(T, device, B=64, V=801, blank=0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(T)
+    lp = torch.randn(T, B, V, generator=g).log_softmax(-1).to(dtype).to(device)
+    rng = np.random.default_rng(T)
+    hi = min(80, T // 2 - 1)
+    tl = rng.integers(10, hi + 1, size=B)
+    Lm = int(tl.max())
+    il = rng.integers(max(2 * Lm + 1, T // 2), T + 1, size=B)
+    ids = np.array([c for c in range(V) if c != blank])
+    tg = np.zeros((B, Lm), dtype=np.int64)
+    for b in range(B):
+        row = rng.choice(ids, size=tl[b])
+        for j in range(1, tl[b]):
+            if rng.random() < 0.1:
+                row[j] = row[j - 1]
+        tg[b, :tl[b]] = row
+    return lp, torch.from_numpy(tg).to(device), torch.from_numpy(il).to(device), torch.from_numpy(tl).to(device), Lm
+
+
+def bench_ctc(device, iters=10, Ts=(250, 1000)):
+    """BASELINE config 2 through the C ABI with preallocated buffers: fwd (alpha||beta scan) + bwd (grad)."""
+    from multimodal_av_model_b200 import _lib
+    L = _lib.lib()
+    flush = l2_flusher(device)
+    st = torch.cuda.current_stream(device).cuda_stream
+    res = {}
+    for T in Ts:
+        lp, tg, il, tl, Lm = ctc_case(T, device)
+        B, V = lp.shape[1], lp.shape[2]
+        wsb = L.avctc_ctc_workspace_bytes(T, B, Lm)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=device)
+        nll = torch.empty(B, device=device); go = torch.ones(1, device=device); grad = torch.empty_like(lp)
+        loss = torch.empty(1, device=device)
+
+        def fwd():
+            _lib.check(L.avctc_ctc_forward(lp.data_ptr(), 0, lp.stride(0), lp.stride(1), T, B, V, tg.data_ptr(), tg.stride(0),
+                                           None, il.data_ptr(), tl.data_ptr(), Lm, 0, 1, nll.data_ptr(), ws.data_ptr(), wsb, st), "fwd")
+            _lib.check(L.avctc_ctc_reduce(nll.data_ptr(), tl.data_ptr(), B, 1, 1, loss.data_ptr(), st), "reduce")
+
+        def bwd():
+            _lib.check(L.avctc_ctc_backward(lp.data_ptr(), 0, lp.stride(0), lp.stride(1), T, B, V, tg.data_ptr(), tg.stride(0),
+                                            None, il.data_ptr(), tl.data_ptr(), Lm, 0, 1, 1, nll.data_ptr(), go.data_ptr(), 0,
+                                            grad.data_ptr(), ws.data_ptr(), wsb, st), "bwd")
+        t_all, t_min = event_time(lambda: (fwd(), bwd()), iters, 3, flush, device)
+        t_f, _ = event_time(fwd, iters, 2, flush, device)
+        t_b, _ = event_time(bwd, iters, 2, flush, device)
+        x = lp.clone().requires_grad_()
+
+        def torch_ref():
+            x.grad = None
+            torch.nn.functional.ctc_loss(x, tg, il, tl, blank=0, reduction="mean", zero_infinity=True).backward()
+        t_torch, _ = event_time(torch_ref, max(3, iters // 2), 2, flush, device)
+        alg = 2 * T * B * V * 4
+        res[f"T{T}"] = dict(fwd_bwd_ms=t_all, scan_ms=t_f, grad_ms=t_b, gbs=alg / t_all / 1e6, utt_per_s=B / t_all * 1e3,
+                            grad_kernel_gbs=alg / t_b / 1e6, torch_cuda_ms=t_torch, speedup_vs_torch_cuda=t_torch / t_all,
+                            algorithmic_bytes=alg)
+    return res
+
+
+def bench_beam(device, rank, world, iters=5, N=4096, T=150, beam=10):
+    """BASELINE config 5: N utterances sharded contiguously over ranks, no collective."""
+    import multimodal_av_model_b200 as pkg
+    from multimodal_av_model_b200 import ddp
+    lo, hi = ddp.shard_range(N, rank, world)
+    g = torch.Generator().manual_seed(7 + rank)
+    n = hi - lo
+    lp_host = (3 * torch.randn(n, T, VOCAB, generator=g)).log_softmax(-1).pin_memory()
+    lp = lp_host.to(device)
+    flush = l2_flusher(device)
+    t_k, _ = event_time(lambda: pkg.beam_search_batch(lp, beam_width=beam, blank=BLANK), iters, 2, flush, device)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        pkg.beam_search_batch(lp_host.to(device, non_blocking=True), beam_width=beam, blank=BLANK)
+    t_e2e = (time.perf_counter() - t0) / 2 * 1e3
+    return dict(utterances=N, shard=n, beam=beam, ms=t_k, utt_per_s_shard=n / t_k * 1e3, e2e_ms=t_e2e,
+                e2e_utt_per_s_shard=n / t_e2e * 1e3, gbs=n * T * VOCAB * 4 / t_k / 1e6,
+                note="ms includes the D2H of token ids and Python list construction; e2e adds the H2D of log-probs")
+
+
+def bench_fusion(device, peaks, iters=10):
+    """BASELINE config 3: projections + cross attention fwd/bwd, bf16, B=32, T_v=150, T_a=249."""
+    import multimodal_av_model_b200 as pkg
+    torch.manual_seed(0)
+    fus = pkg.CrossAttentionFusion(512, 1024, 512).to(device)
+    B, Tv, Ta = 32, 150, 249
+    vis = torch.randn(B, Tv, 512, device=device, dtype=torch.bfloat16)
+    aud = torch.randn(B, Ta, 1024, device=device, dtype=torch.bfloat16, requires_grad=True)
+    mask = torch.zeros(B, Ta, dtype=torch.long, device=device)
+    mask[:, :150] = 1; mask[:, 150:200] = 2
+    for b in range(B):
+        mask[b, Ta - (b % 7):] = 3
+    flush = l2_flusher(device)
+    r = torch.randn(B, Tv, 512, device=device)
+
+    def fwd():
+        with torch.no_grad():
+            fus.fused_projection(vis, aud, mask)
+
+    def fwd_bwd():
+        fus.zero_grad(set_to_none=True); aud.grad = None
+        f, _, _ = fus.fused_projection(vis, aud, mask)
+        f.backward(r)
+    t_f, _ = event_time(fwd, iters, 3, flush, device)
+    t_fb, _ = event_time(fwd_bwd, iters, 3, flush, device)
+    M = B * Tv
+    flop_f = 2 * M * (512 * 512 * 4 + 1024 * 512 * 2) + 4 * B * Tv * Tv * 512
+    return dict(fwd_ms=t_f, fwd_bwd_ms=t_fb, fwd_tflops=flop_f / t_f / 1e9, fwd_bwd_tflops=3 * flop_f / t_fb / 1e9,
+                tensor_frac_fwd=flop_f / t_f / 1e9 / peaks["tf_burst"], tensor_frac_fwd_bwd=3 * flop_f / t_fb / 1e9 / peaks["tf_burst"],
+                peak_tflops=peaks["tf_burst"], peak_src=peaks["src"],
+                note="21.6 GFLOP fwd is ~13 us of tensor work; the path is launch/latency bound at this size")
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_train_sample(pairs, steps, warmup, threads):
+    """The reference's train step restated on torch CPU ops (oracle/torch_port.py + the PyTorch encoders)."""
+    from oracle import torch_port as tp
+    from multimodal_av_model_b200.encoders import AudioEncoder, VisualEncoder, unfreeze_middle_layers, xlsr_large_config
+    from multimodal_av_model_b200.synthetic import make_batch
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    vis = VisualEncoder()
+    for p in vis.parameters():
+        p.requires_grad = False
+    aud = AudioEncoder(freeze=True, config=xlsr_large_config())
+    unfreeze_middle_layers(aud.model)
+    fus = tp.FusionPort(512, 1024, 512)
+    dec = tp.DecoderPort(1024, VOCAB, BLANK)
+    proj = torch.nn.Linear(1024, 128)
+    params = [p for m in (vis, aud, fus, dec) for p in m.parameters()]
+    opt = torch.optim.Adam([p for p in params if p.requires_grad], lr=1e-4)
+    for m in (vis, aud, fus, dec):
+        m.train()
+    batch = make_batch(pairs=pairs, seconds=SECONDS, t_v=T_V, vocab=VOCAB, seed=1234)
+
+    def step():
+        opt.zero_grad()
+        feats = []
+        for s in ("1", "2"):
+            lip = batch["lip" + s].permute(0, 2, 1, 3, 4).contiguous()
+            v = vis(lip)
+            a, mid = aud(batch["audio"], attention_mask=(batch["mask" + s] != 3))
+            feats.append(dict(visual=v, audio=a, middle=mid, mask=batch["mask" + s], text=batch["text" + s],
+                              text_len=batch["text" + s + "_lengths"]))
+        loss = tp.hot_path_losses(fus, dec, proj, feats, blank=BLANK)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return 2 * pairs * steps / dt, dt / steps
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    pairs = 2
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    val, sec = cpu_train_sample(pairs, steps, warm, threads)
+    line = {"impl": "reference", "metric": "train_utt_per_s", "value": val, "unit": "utt/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config4: full AV-CTC + InfoNCE train step (encoders + fusion + CTC head + CTC + InfoNCE + Adam)",
+                       "pairs_per_step": pairs, "audio_s": SECONDS, "lip_frames": T_V, "vocab": VOCAB, "blank": BLANK},
+            "cpu_baseline": {"value": val, "unit": "utt/s", "cores": threads, "kind": "port",
+                             "sample": f"{steps} step(s) of {pairs} pairs (= {2 * pairs} utterances) of the config-4 step on torch CPU ops"},
+            "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "ctc", "beam", "fusion"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+    from multimodal_av_model_b200 import ddp
+    rank, local, world = ddp.init_distributed()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    peaks = measured_peaks()
+    line = {"metric": "train_utt_per_s", "unit": "utt/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "config4: full AV-CTC + InfoNCE train step (PyTorch encoders + sm_100a fusion/CTC head/CTC/InfoNCE "
+                                   "kernels + Adam), utterance-sharded data parallel",
+                       "pairs_per_gpu": PAIRS_PER_GPU, "utterances_per_step": 2 * PAIRS_PER_GPU * world, "audio_s": SECONDS,
+                       "lip_frames": T_V, "t_enc": 249, "vocab": VOCAB, "blank": BLANK, "encoders": "random-init ResNet-18 front-end + wav2vec2-large (XLSR layout)",
+                       "parallelism": f"dp{world}", "l2": "per-step working set (1.3 GB of parameters + activations) exceeds the 126 MB L2; "
+                                                       "sub-benchmarks flush L2 with a 256 MB write between iterations"}}
+    if args.workload == "train":
+        out, tr = bench_train(args, rank, local, world, device)
+        line.update(out)
+        del tr
+        torch.cuda.empty_cache()
+    ctc = bench_ctc(device) if args.workload in ("train", "ctc") else None
+    beam = bench_beam(device, rank, world) if args.workload in ("train", "beam") else None
+    fusion = bench_fusion(device, peaks) if args.workload in ("train", "fusion") else None
+    if beam is not None:
+        import torch.distributed as dist
+        t = torch.tensor([beam["ms"], beam["e2e_ms"]], device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        beam["utt_per_s"] = beam["utterances"] / float(t[0]) * 1e3
+        beam["e2e_utt_per_s"] = beam["utterances"] / float(t[1]) * 1e3
+        line["beam"] = beam
+    if ctc is not None:
+        line["ctc"] = ctc
+        top = ctc["T1000"]
+        line["roofline"] = {"bound": "hbm", "kernel": "ctc_scan_kernel + ctc_grad_kernel (CTC fwd+bwd, config 2: B=64 T=1000 V=801 fp32)",
+                            "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s", "frac": top["gbs"] / peaks["hbm"],
+                            "peak_src": peaks["src"], "traffic": None,
+                            "grad_kernel_frac": top["grad_kernel_gbs"] / peaks["hbm"],
+                            "note": "achieved = 2*T*B*V*4 bytes / (scan + grad) time; the scan is a 1000-step latency-bound recurrence over 128 CTAs"}
+    if fusion is not None:
+        line["fusion"] = fusion
+    if args.workload != "train":
+        line["metric"] = {"ctc": "ctc_fwd_bwd_gbs", "beam": "beam_decode_utt_per_s", "fusion": "fusion_tensor_frac"}[args.workload]
+        line["value"] = {"ctc": lambda: ctc["T1000"]["gbs"], "beam": lambda: beam["utt_per_s"], "fusion": lambda: fusion["tensor_frac_fwd_bwd"]}[args.workload]()
+    if rank == 0 and world == 1 and args.workload == "train" and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, sec = cpu_train_sample(2, 1, 1, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "utt/s", "cores": threads, "kind": "port",
+                                "sample": "1 step (after 1 warm-up) of 2 pairs (= 4 utterances) of the config-4 step on torch CPU ops "
+                                          f"(oracle/torch_port.py), {sec:.1f} s/step"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,34 @@ class GemmOperand(ctypes.Structure):
                 ("z_inner", _i), ("mn_major", _i)]
 
 
+# kernels launched by each entry point (bench.py reports "gpu_launches" from this table)
+KERNELS = {"avctc_ctc_forward": 1, "avctc_ctc_reduce": 1, "avctc_ctc_backward": 1, "avctc_beam_search": 1,
+           "avctc_gemm_bf16": 1, "avctc_resample_forward": 2, "avctc_resample_backward": 1, "avctc_softmax_forward": 1,
+           "avctc_softmax_backward": 1, "avctc_colsum": 1, "avctc_log_softmax_forward": 1,
+           "avctc_log_softmax_backward": 1, "avctc_infonce_forward": 5, "avctc_infonce_backward": 6}
+launch_count = 0
+
+
+class _Counted:
+    """Thin proxy over the CDLL that counts kernel launches per entry point."""
+
+    def __init__(self, cdll):
+        object.__setattr__(self, "_cdll", cdll)
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+        n = KERNELS.get(name, 0)
+        if n == 0:
+            return fn
+
+        def call(*a):
+            global launch_count
+            launch_count += n
+            return fn(*a)
+        object.__setattr__(self, name, call)
+        return call
+
+
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
@@ -69,7 +97,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(L, name)          # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        _lib = L
+        _lib = _Counted(L)
     return _lib
 
 
