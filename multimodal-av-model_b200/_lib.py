@@ -61,7 +61,7 @@ class GemmOperand(ctypes.Structure):
 KERNELS = {"avctc_ctc_forward": 1, "avctc_ctc_reduce": 1, "avctc_ctc_backward": 1, "avctc_beam_search": 1,
            "avctc_gemm_bf16": 1, "avctc_resample_forward": 2, "avctc_resample_backward": 1, "avctc_softmax_forward": 1,
            "avctc_softmax_backward": 1, "avctc_colsum": 1, "avctc_log_softmax_forward": 1,
-           "avctc_log_softmax_backward": 1, "avctc_infonce_forward": 5, "avctc_infonce_backward": 6}
+           "avctc_log_softmax_backward": 1, "avctc_infonce_forward": 4, "avctc_infonce_backward": 2}
 launch_count = 0
 
 

@@ -18,6 +18,9 @@
 namespace avctc {
 
 constexpr float kNceEps = 1e-12f;
+constexpr int kTile = 64;
+constexpr int kNceThreads = 256;
+constexpr int kSlots = 8;      // partial-gradient slots (fixed-order reduction keeps the result bit-reproducible)
 
 struct NceWs {
     int* idx[3];      // row lists: [0] mask==0 (neg), [1] mask==1 (weak anchors), [2] mask==2 (strong)
@@ -27,7 +30,7 @@ struct NceWs {
     float* nrm;       // [N] |y|
     float* lse[2];    // per anchor slot, pair 0 = (weak,strong), pair 1 = (weak,neg)
     float* ssum[2];
-    float* dz;        // [N][P]
+    float* dzp;       // [kSlots][N][P] partial gradients w.r.t. z
     size_t total;
 };
 
@@ -43,7 +46,7 @@ static NceWs carve(void* base, int N, int P) {
     w.nrm = reinterpret_cast<float*>(take(sizeof(float) * (size_t)N));
     for (int i = 0; i < 2; ++i) w.lse[i] = reinterpret_cast<float*>(take(sizeof(float) * (size_t)N));
     for (int i = 0; i < 2; ++i) w.ssum[i] = reinterpret_cast<float*>(take(sizeof(float) * (size_t)N));
-    w.dz = reinterpret_cast<float*>(take(sizeof(float) * (size_t)N * P));
+    w.dzp = reinterpret_cast<float*>(take(sizeof(float) * (size_t)kSlots * N * P));
     w.total = o;
     return w;
 }
@@ -101,37 +104,116 @@ __global__ void nce_normalize_kernel(const TIn* __restrict__ y, long long ld, in
     if (lane == 0) { invn[row] = inv; nrm[row] = n; }
 }
 
-// one warp per anchor slot i; lane-per-column dot products over the other set
-__global__ void nce_pair_fwd_kernel(const float* __restrict__ z, int P, const int* __restrict__ idxA,
-                                    const int* __restrict__ idxO, const int* __restrict__ cnt, int setA, int setO,
-                                    float inv_tau, float* __restrict__ lse, float* __restrict__ ssum) {
-    extern __shared__ float za_s[];              // [warps][P]
-    const int nA = cnt[setA], nO = cnt[setO];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (i >= nA || nO == 0) return;
-    float* za = za_s + warp * P;
-    const float* zi = z + (size_t)idxA[i] * P;
-    for (int d = lane; d < P; d += 32) za[d] = zi[d];
-    __syncwarp();
-    float m = AVCTC_NEG_INF, s = 0.f, tot = 0.f;
-    for (int j0 = 0; j0 < nO; j0 += 32) {
-        const int j = j0 + lane;
-        if (j < nO) {
-            const float* zj = z + (size_t)idxO[j] * P;
-            float dot = 0.f;
-            for (int d = 0; d < P; ++d) dot = fmaf(za[d], zj[d], dot);
-            const float sim = dot * inv_tau;
-            tot += sim;
-            const float mn = fmaxf(m, sim);
-            s = s * __expf(m - mn) + __expf(sim - mn);
-            m = mn;
+// ---- tiled pair kernels ------------------------------------------------------------------------------
+// A CTA owns a 64-row tile of one row set ("rows", kept in shared memory) and streams 64-row tiles of the other
+// set ("cols").  256 threads as 16 x 16: thread (ty,tx) holds the 4x4 similarities of rows ty+16i, cols tx+16j
+// (interleaved so that the float4 shared reads of 16 different cols hit 16 different bank groups).
+__device__ __forceinline__ void nce_load_tile(float* dst, int PS, int P4, const float* __restrict__ z, int P,
+                                              const int* __restrict__ idx, int first, int count) {
+    // rows first..first+63 of the compacted list -> dst[r][0..P4), zero rows / zero pad columns beyond
+    const int per_row = P4 >> 2;
+    for (int e = threadIdx.x; e < kTile * per_row; e += kNceThreads) {
+        const int r = e / per_row, q = (e - r * per_row) << 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (first + r < count) {
+            const float* src = z + (size_t)idx[first + r] * P + q;
+            if (((P & 3) == 0)) v = *reinterpret_cast<const float4*>(src);
+            else {
+                v.x = src[0];
+                if (q + 1 < P) v.y = src[1];
+                if (q + 2 < P) v.z = src[2];
+                if (q + 3 < P) v.w = src[3];
+            }
+        }
+        *reinterpret_cast<float4*>(dst + r * PS + q) = v;
+    }
+}
+
+__device__ __forceinline__ void nce_sim_tile(const float* __restrict__ zR, const float* __restrict__ zC, int PS, int P4,
+                                             int ty, int tx, float (&sim)[4][4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sim[i][j] = 0.f;
+    for (int d = 0; d < P4; d += 4) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(zR + (ty + 16 * i) * PS + d);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(zC + (tx + 16 * j) * PS + d);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                sim[i][j] = fmaf(a[i].x, b[j].x, sim[i][j]);
+                sim[i][j] = fmaf(a[i].y, b[j].y, sim[i][j]);
+                sim[i][j] = fmaf(a[i].z, b[j].z, sim[i][j]);
+                sim[i][j] = fmaf(a[i].w, b[j].w, sim[i][j]);
+            }
+    }
+}
+
+// forward: per anchor i of the weak set, lse_i = log sum_j exp(sim_ij) and ssum_i = sum_j sim_ij over the other set.
+// grid (anchor tiles, 2 pairs).
+__global__ void __launch_bounds__(kNceThreads)
+nce_pair_fwd_kernel(const float* __restrict__ z, int P, const int* __restrict__ idxW, const int* __restrict__ idxS,
+                    const int* __restrict__ idxN, const int* __restrict__ cnt, float inv_tau,
+                    float* __restrict__ lse0, float* __restrict__ ss0, float* __restrict__ lse1, float* __restrict__ ss1) {
+    extern __shared__ __align__(16) float nce_smem[];
+    const int pair = blockIdx.y;
+    const int nA = cnt[1], nO = pair ? cnt[0] : cnt[2];
+    const int first = blockIdx.x * kTile;
+    if (first >= nA || nO == 0) return;
+    const int* idxO = pair ? idxN : idxS;
+    const int P4 = (P + 3) & ~3, PS = P4 + 4;
+    float* zR = nce_smem;
+    float* zC = zR + kTile * PS;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    nce_load_tile(zR, PS, P4, z, P, idxW, first, nA);
+    float m[4], s[4], tot[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { m[i] = AVCTC_NEG_INF; s[i] = 0.f; tot[i] = 0.f; }
+    for (int c0 = 0; c0 < nO; c0 += kTile) {
+        __syncthreads();
+        nce_load_tile(zC, PS, P4, z, P, idxO, c0, nO);
+        __syncthreads();
+        float sim[4][4];
+        nce_sim_tile(zR, zC, PS, P4, ty, tx, sim);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float tm = AVCTC_NEG_INF, tt = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool ok = (c0 + tx + 16 * j) < nO;
+                sim[i][j] = ok ? sim[i][j] * inv_tau : AVCTC_NEG_INF;
+                tm = fmaxf(tm, sim[i][j]);
+                tt += ok ? sim[i][j] : 0.f;
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(kFullMask, tm, o));   // 16 lanes share a row
+            const float mn = fmaxf(m[i], tm);          // finite: every tile has at least one valid column
+            float ts = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ts += __expf(sim[i][j] - mn);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                ts += __shfl_xor_sync(kFullMask, ts, o);
+                tt += __shfl_xor_sync(kFullMask, tt, o);
+            }
+            s[i] = s[i] * __expf(m[i] - mn) + ts;
+            m[i] = mn;
+            tot[i] += tt;
         }
     }
-    const float mw = warp_max(m);
-    const float sw = warp_sum((m == AVCTC_NEG_INF) ? 0.f : s * __expf(m - mw));
-    const float tw = warp_sum(tot);
-    if (lane == 0) { lse[i] = mw + logf(sw); ssum[i] = tw; }
+    if (tx == 0) {
+        float* lse = pair ? lse1 : lse0;
+        float* ss = pair ? ss1 : ss0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = first + ty + 16 * i;
+            if (r < nA) { lse[r] = m[i] + logf(s[i]); ss[r] = tot[i]; }
+        }
+    }
 }
 
 // loss[0] = w0 * pair0 + w1 * pair1, pair = mean_i(lse_i) - sum_i(ssum_i)/(nA*nO); single CTA, fixed order
@@ -161,98 +243,161 @@ __global__ void nce_finalize_kernel(const int* __restrict__ cnt, const float* ls
     }
 }
 
-// gradient w.r.t. z for one side of one pair.  rows = the set this launch writes, cols = the set it sums
-// over; anchor_is_row says whose lse normalises p_ij.  One warp per row, lane-per-column coefficients,
-// lane-per-dimension accumulation.
-__global__ void nce_pair_bwd_kernel(const float* __restrict__ z, int P, const int* __restrict__ idxR,
-                                    const int* __restrict__ idxC, const int* __restrict__ cnt, int setR, int setC,
-                                    int anchor_is_row, const float* __restrict__ lse, float inv_tau, float weight,
-                                    const float* __restrict__ gout, float* __restrict__ dz, int accumulate) {
-    extern __shared__ float zr_s[];
-    const int nR = cnt[setR], nC = cnt[setC];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (r >= nR) return;
-    const int row = idxR[r];
-    float* drow = dz + (size_t)row * P;
-    if (nC == 0) {
-        if (!accumulate) for (int d = lane; d < P; d += 32) drow[d] = 0.f;
-        return;
-    }
-    float* zr = zr_s + warp * P;
-    const float* zg = z + (size_t)row * P;
-    for (int d = lane; d < P; d += 32) zr[d] = zg[d];
-    __syncwarp();
+// backward w.r.t. z.  grid (row tiles, kSlots, 3 sets).  A CTA owns 64 rows of `set` and a slot:
+//   set 1 (weak anchors): slots [0,4) stream the strong set (pair 0), slots [4,8) the neg set (pair 1)
+//   set 2 / 0 (strong / neg): every slot streams a strided share of the weak anchors
+// and writes  dzp[slot][row][:] = sum_cols coef(row,col) * z[col],  coef = g (p_ij/nA - 1/(nA nO)),
+// p_ij = exp(sim_ij - lse_anchor).  Every (slot,row) is written by exactly one CTA -> no atomics.
+template <int NE>    // second product: thread owns dims tx*4 + 64*e .. +3, e < NE  (P <= 64*NE)
+__global__ void __launch_bounds__(kNceThreads)
+nce_pair_bwd_kernel(const float* __restrict__ z, int P, int N, const int* __restrict__ idxN, const int* __restrict__ idxW,
+                    const int* __restrict__ idxS, const int* __restrict__ cnt, const float* __restrict__ lse0,
+                    const float* __restrict__ lse1, float inv_tau, float w_pos, float w_neg,
+                    const float* __restrict__ gout, float* __restrict__ dzp) {
+    extern __shared__ __align__(16) float nce_smem[];
+    const int set = blockIdx.z, slot = blockIdx.y;
+    const int nR = cnt[set];
+    const int first = blockIdx.x * kTile;
+    if (first >= nR) return;
+    int setC, pair, sub, nsub;
+    if (set == 1) { pair = slot / (kSlots / 2); sub = slot % (kSlots / 2); nsub = kSlots / 2; setC = pair ? 0 : 2; }
+    else { pair = (set == 2) ? 0 : 1; sub = slot; nsub = kSlots; setC = 1; }
+    const bool anchor_is_row = (set == 1);
+    const int nC = cnt[setC];
+    const int* idxR = (set == 0) ? idxN : (set == 1) ? idxW : idxS;
+    const int* idxC = (setC == 0) ? idxN : (setC == 1) ? idxW : idxS;
+    const float* lse = pair ? lse1 : lse0;
+    const int P4 = (P + 3) & ~3, PS = P4 + 4;
+    float* zR = nce_smem;
+    float* zC = zR + kTile * PS;
+    float* coef = zC + kTile * PS;            // [64][65]
+    float* lse_c = coef + kTile * (kTile + 1);  // [64]
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    nce_load_tile(zR, PS, P4, z, P, idxR, first, nR);
     const int nA = anchor_is_row ? nR : nC, nO = anchor_is_row ? nC : nR;
-    const float g = gout[0] * weight * inv_tau;
-    const float invA = 1.f / (float)nA, invAO = 1.f / ((float)nA * (float)nO);
-    const float lse_r = anchor_is_row ? lse[r] : 0.f;
-    // lane owns dims d = lane + 32*k
-    float acc[8];
+    const float g = gout[0] * (pair ? w_neg : w_pos) * inv_tau;
+    const float invA = nA > 0 ? 1.f / (float)nA : 0.f;
+    const float invAO = (nA > 0 && nO > 0) ? 1.f / ((float)nA * (float)nO) : 0.f;
+    float lse_r[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    const int nk = (P + 31) / 32;           // host guarantees P <= 256
-    for (int c0 = 0; c0 < nC; c0 += 32) {
-        const int c = c0 + lane;
-        float coef = 0.f;
-        int crow = 0;
-        if (c < nC) {
-            crow = idxC[c];
-            const float* zc = z + (size_t)crow * P;
-            float dot = 0.f;
-            for (int d = 0; d < P; ++d) dot = fmaf(zr[d], zc[d], dot);
-            const float sim = dot * inv_tau;
-            const float l = anchor_is_row ? lse_r : lse[c];
-            coef = g * (__expf(sim - l) * invA - invAO);
-        }
-        const int lim = min(32, nC - c0);
-        for (int t = 0; t < lim; ++t) {
-            const float cf = __shfl_sync(kFullMask, coef, t);
-            const int cr = __shfl_sync(kFullMask, crow, t);
-            const float* zc = z + (size_t)cr * P;
+    for (int i = 0; i < 4; ++i) {
+        const int r = first + ty + 16 * i;
+        lse_r[i] = (anchor_is_row && r < nR) ? lse[r] : 0.f;
+    }
+    float acc[4][NE][4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (k < nk) { const int d = lane + 32 * k; if (d < P) acc[k] = fmaf(cf, zc[d], acc[k]); }
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[i][e][k] = 0.f;
+
+    for (int c0 = sub * kTile; c0 < nC; c0 += nsub * kTile) {
+        __syncthreads();
+        nce_load_tile(zC, PS, P4, z, P, idxC, c0, nC);
+        if (!anchor_is_row && threadIdx.x < kTile) lse_c[threadIdx.x] = (c0 + threadIdx.x < nC) ? lse[c0 + threadIdx.x] : 0.f;
+        __syncthreads();
+        float sim[4][4];
+        nce_sim_tile(zR, zC, PS, P4, ty, tx, sim);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int rr = ty + 16 * i, cc = tx + 16 * j;
+                const bool ok = (first + rr < nR) && (c0 + cc < nC);
+                const float l = anchor_is_row ? lse_r[i] : lse_c[cc];
+                coef[rr * (kTile + 1) + cc] = ok ? g * (__expf(sim[i][j] * inv_tau - l) * invA - invAO) : 0.f;
+            }
+        __syncthreads();
+#pragma unroll 4
+        for (int c = 0; c < kTile; ++c) {
+            float cf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cf[i] = coef[(ty + 16 * i) * (kTile + 1) + c];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const int d = tx * 4 + 64 * e;
+                if (d < P4) {
+                    const float4 v = *reinterpret_cast<const float4*>(zC + c * PS + d);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[i][e][0] = fmaf(cf[i], v.x, acc[i][e][0]);
+                        acc[i][e][1] = fmaf(cf[i], v.y, acc[i][e][1]);
+                        acc[i][e][2] = fmaf(cf[i], v.z, acc[i][e][2]);
+                        acc[i][e][3] = fmaf(cf[i], v.w, acc[i][e][3]);
+                    }
+                }
+            }
         }
     }
+    float* out = dzp + (size_t)slot * N * P;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if (k < nk) { const int d = lane + 32 * k; if (d < P) drow[d] = accumulate ? drow[d] + acc[k] : acc[k]; }
+    for (int i = 0; i < 4; ++i) {
+        const int r = first + ty + 16 * i;
+        if (r >= nR) continue;
+        float* drow = out + (size_t)idxR[r] * P;
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int d = tx * 4 + 64 * e + k;
+                if (d < P) drow[d] = acc[i][e][k];
+            }
+    }
 }
 
-// rows that belong to no set (mask==3, or sets that never pair) must end with dz = 0
-__global__ void nce_zero_rows_kernel(const int64_t* __restrict__ mask, const int* __restrict__ cnt, int N, int P,
-                                     float* __restrict__ dz) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= N) return;
-    const long long m = mask[row];
-    const int nW = cnt[1], nS = cnt[2], nN = cnt[0];
-    bool used = false;
-    if (m == 1) used = (nS > 0 || nN > 0);
-    else if (m == 2) used = (nW > 0);      // written by the (weak,strong) other-side launch
-    else if (m == 0) used = (nW > 0);
-    if (!used) for (int d = threadIdx.x & 31; d < P; d += 32) dz[(size_t)row * P + d] = 0.f;
-}
-
+// dz[row] = sum over the kSlots partials (fixed order; rows with mask 3 get 0), then the F.normalize backward.
 template <typename TOut>
-__global__ void nce_normalize_bwd_kernel(const float* __restrict__ z, const float* __restrict__ dz,
-                                         const float* __restrict__ invn, const float* __restrict__ nrm, int N, int P,
-                                         TOut* __restrict__ dy, long long ld) {
+__global__ void nce_normalize_bwd_kernel(const float* __restrict__ z, const float* __restrict__ dzp,
+                                         const int64_t* __restrict__ mask, const float* __restrict__ invn,
+                                         const float* __restrict__ nrm, int N, int P, TOut* __restrict__ dy, long long ld) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= N) return;
     const int lane = threadIdx.x & 31;
     const float* zr = z + (size_t)row * P;
-    const float* dr = dz + (size_t)row * P;
+    const long long mk = mask[row];
+    const bool used = (mk >= 0 && mk <= 2);
+    float dr[8];                                   // P <= 256
     float dot = 0.f;
-    for (int d = lane; d < P; d += 32) dot += zr[d] * dr[d];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int d = lane + 32 * k;
+        float v = 0.f;
+        if (used && d < P) {
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) v += dzp[((size_t)s * N + row) * P + d];
+            dot += zr[d] * v;
+        }
+        dr[k] = v;
+    }
     dot = warp_sum(dot);
     const float inv = invn[row];
     const bool clamped = !(nrm[row] > kNceEps);   // F.normalize: y / clamp_min(|y|, eps); clamp has zero slope
-    for (int d = lane; d < P; d += 32) {
-        const float v = clamped ? dr[d] * inv : (dr[d] - zr[d] * dot) * inv;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int d = lane + 32 * k;
+        if (d >= P) continue;
+        const float v = clamped ? dr[k] * inv : (dr[k] - zr[d] * dot) * inv;
         if constexpr (sizeof(TOut) == 4) dy[(long long)row * ld + d] = v;
         else dy[(long long)row * ld + d] = __float2bfloat16(v);
     }
+}
+
+static size_t nce_tile_smem(int P) {
+    const int P4 = (P + 3) & ~3, PS = P4 + 4;
+    return sizeof(float) * ((size_t)2 * kTile * PS + (size_t)kTile * (kTile + 1) + kTile);
+}
+static int nce_configure_smem() {
+    static bool done = false;
+    if (done) return 0;
+    const int maxb = (int)nce_tile_smem(256);
+    AVCTC_CUDA_RETURN(cudaFuncSetAttribute(nce_pair_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    AVCTC_CUDA_RETURN(cudaFuncSetAttribute(nce_pair_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    AVCTC_CUDA_RETURN(cudaFuncSetAttribute(nce_pair_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    AVCTC_CUDA_RETURN(cudaFuncSetAttribute(nce_pair_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    AVCTC_CUDA_RETURN(cudaFuncSetAttribute(nce_pair_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+    done = true;
+    return 0;
 }
 
 }  // namespace avctc
@@ -282,9 +427,11 @@ extern "C" int avctc_infonce_forward(const void* y, int dtype, long long ld, con
     else
         nce_normalize_kernel<__nv_bfloat16><<<rgrid, wpb * 32, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(y), ld, N, P, w.z, w.invn, w.nrm);
     const float inv_tau = 1.f / temperature;
-    const size_t smem = (size_t)wpb * P * sizeof(float);
-    nce_pair_fwd_kernel<<<rgrid, wpb * 32, smem, st>>>(w.z, P, w.idx[1], w.idx[2], w.cnt, 1, 2, inv_tau, w.lse[0], w.ssum[0]);
-    nce_pair_fwd_kernel<<<rgrid, wpb * 32, smem, st>>>(w.z, P, w.idx[1], w.idx[0], w.cnt, 1, 0, inv_tau, w.lse[1], w.ssum[1]);
+    const size_t smem = nce_tile_smem(P);
+    { const int rc_ = nce_configure_smem(); if (rc_) return rc_; }
+    dim3 fgrid((N + kTile - 1) / kTile, 2);
+    nce_pair_fwd_kernel<<<fgrid, kNceThreads, smem, st>>>(w.z, P, w.idx[1], w.idx[2], w.idx[0], w.cnt, inv_tau,
+                                                         w.lse[0], w.ssum[0], w.lse[1], w.ssum[1]);
     nce_finalize_kernel<<<1, 256, 0, st>>>(w.cnt, w.lse[0], w.ssum[0], w.lse[1], w.ssum[1], w_pos, w_neg, loss);
     return (int)cudaGetLastError();
 }
@@ -301,16 +448,20 @@ extern "C" int avctc_infonce_backward(const int64_t* flat_mask, int N, int P, fl
     const int wpb = 8;
     const unsigned rgrid = (N + wpb - 1) / wpb;
     const float inv_tau = 1.f / temperature;
-    const size_t smem = (size_t)wpb * P * sizeof(float);
-    // anchors (weak rows): pair 0 writes, pair 1 accumulates; others: each set written by exactly one launch
-    nce_pair_bwd_kernel<<<rgrid, wpb * 32, smem, st>>>(w.z, P, w.idx[1], w.idx[2], w.cnt, 1, 2, 1, w.lse[0], inv_tau, w_pos, grad_out, w.dz, 0);
-    nce_pair_bwd_kernel<<<rgrid, wpb * 32, smem, st>>>(w.z, P, w.idx[1], w.idx[0], w.cnt, 1, 0, 1, w.lse[1], inv_tau, w_neg, grad_out, w.dz, 1);
-    nce_pair_bwd_kernel<<<rgrid, wpb * 32, smem, st>>>(w.z, P, w.idx[2], w.idx[1], w.cnt, 2, 1, 0, w.lse[0], inv_tau, w_pos, grad_out, w.dz, 0);
-    nce_pair_bwd_kernel<<<rgrid, wpb * 32, smem, st>>>(w.z, P, w.idx[0], w.idx[1], w.cnt, 0, 1, 0, w.lse[1], inv_tau, w_neg, grad_out, w.dz, 0);
-    nce_zero_rows_kernel<<<rgrid, wpb * 32, 0, st>>>(flat_mask, w.cnt, N, P, w.dz);
+    const size_t smem = nce_tile_smem(P);
+    { const int rc_ = nce_configure_smem(); if (rc_) return rc_; }
+    dim3 bgrid((N + kTile - 1) / kTile, kSlots, 3);
+#define AVCTC_NCE_BWD(NE)                                                                                            \
+    nce_pair_bwd_kernel<NE><<<bgrid, kNceThreads, smem, st>>>(w.z, P, N, w.idx[0], w.idx[1], w.idx[2], w.cnt, w.lse[0], \
+                                                             w.lse[1], inv_tau, w_pos, w_neg, grad_out, w.dzp)
+    if (P <= 64) AVCTC_NCE_BWD(1);
+    else if (P <= 128) AVCTC_NCE_BWD(2);
+    else if (P <= 192) AVCTC_NCE_BWD(3);
+    else AVCTC_NCE_BWD(4);
+#undef AVCTC_NCE_BWD
     if (dtype == AVCTC_F32)
-        nce_normalize_bwd_kernel<float><<<rgrid, wpb * 32, 0, st>>>(w.z, w.dz, w.invn, w.nrm, N, P, reinterpret_cast<float*>(dy), ld);
+        nce_normalize_bwd_kernel<float><<<rgrid, wpb * 32, 0, st>>>(w.z, w.dzp, flat_mask, w.invn, w.nrm, N, P, reinterpret_cast<float*>(dy), ld);
     else
-        nce_normalize_bwd_kernel<__nv_bfloat16><<<rgrid, wpb * 32, 0, st>>>(w.z, w.dz, w.invn, w.nrm, N, P, reinterpret_cast<__nv_bfloat16*>(dy), ld);
+        nce_normalize_bwd_kernel<__nv_bfloat16><<<rgrid, wpb * 32, 0, st>>>(w.z, w.dzp, flat_mask, w.invn, w.nrm, N, P, reinterpret_cast<__nv_bfloat16*>(dy), ld);
     return (int)cudaGetLastError();
 }

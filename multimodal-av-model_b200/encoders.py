@@ -75,11 +75,24 @@ class VisualEncoder(nn.Module):
         self.trunk = ResNet(BasicBlock, [2, 2, 2, 2], relu_type=relu_type)
         self.output_dim = 512
 
+    def _channels_last(self):
+        """cuDNN's NHWC tensor-core kernels and ATen's channels-last BatchNorm are ~2x faster here than NCHW on B200
+        (measured: 20.4 -> 10.8 ms per [8,1,150,96,96] call); values are unchanged up to bf16 rounding."""
+        if not getattr(self, "_cl_done", False):
+            self.trunk.to(memory_format=torch.channels_last)
+            self.frontend3D.to(memory_format=torch.channels_last_3d)
+            self._cl_done = True
+
     def forward(self, x):
         b = x.shape[0]
+        if x.is_cuda:
+            self._channels_last()
+            x = x.contiguous(memory_format=torch.channels_last_3d)
         y = self.frontend3D(x)                                   # [B,64,T,H',W']
         t, h, w = y.shape[2:]
         y = y.transpose(1, 2).reshape(b * t, 64, h, w)
+        if x.is_cuda:
+            y = y.contiguous(memory_format=torch.channels_last)
         return self.trunk(y).view(b, t, 512)
 
 
