@@ -45,7 +45,8 @@ AVCTC_API const char* avctc_version(void);
 /* Human-readable text for a status returned by any entry point (host pointer, static storage). */
 AVCTC_API const char* avctc_status_string(int status);
 /* Tuning knobs for benchmarking (host-side process-global ints; not needed for correctness).
- * key: "ctc_k" (states per lane: 0 = auto, 2/4/8/16), "beam_fast" (1 = threshold top-k fast path). */
+ * key: "ctc_lin" (1 = probability-domain single-warp CTC scan when 2L+1 <= 512, 0 = log-domain scan),
+ * "ctc_k" (log-domain scan, states per lane: 0 = auto, 2/4/8/16), "beam_fast" (1 = threshold top-k fast path). */
 AVCTC_API int avctc_set_tuning(const char* key, int value);
 
 /* ------------------------------------------------------------------------------------------------

@@ -31,7 +31,7 @@ constexpr int kChainNone = 0x3fffffff;
 constexpr int kChainFirst = 0x40000000;
 
 struct CtcPlan {
-    int K, W, S_pad, Lpad;
+    int K, W, S_pad, Lpad, linear;
     size_t off_alpha, off_beta, off_coff_a, off_coff_b, off_nll2, off_chain, total;
 };
 
@@ -40,7 +40,16 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 static bool make_plan(int T, int B, int Lmax, CtcPlan* pl) {
     const int S = 2 * Lmax + 1;
     int K = 0, W = 0;
-    const int forced = avctc_tuning_get("ctc_k", 0);
+    pl->linear = 0;
+    // probability-domain single-warp scan (ctc_scan_lin_kernel): K states per lane, S <= 32*K <= 512
+    if (S <= 512 && avctc_tuning_get("ctc_lin", 1) != 0) {
+        const int need = (S + 31) / 32;
+        static const int ks[6] = {2, 4, 6, 8, 12, 16};
+        for (int i = 0; i < 6; ++i) if (ks[i] >= need) { K = ks[i]; break; }
+        W = 1;
+        pl->linear = 1;
+    }
+    const int forced = pl->linear ? 0 : avctc_tuning_get("ctc_k", 0);
     if (forced == 2 || forced == 4 || forced == 8 || forced == 16) {
         int w = (S + 32 * forced - 1) / (32 * forced);
         if (w <= kMaxWarps) { K = forced; W = w; }
@@ -356,6 +365,268 @@ __global__ void __launch_bounds__(32 * kMaxWarps) ctc_scan_kernel(const ScanPara
 }
 
 // ------------------------------------------------------------------------------------------------
+// ctc_scan_lin_kernel — the same recurrence in the PROBABILITY domain, one warp per (sample, direction).
+//
+// A lane holds K consecutive lattice states as fp32 mantissas a[j] relative to a lane-local integer exponent C:
+// alpha(s) = a[j] * 2^C.  A frame is then   a' = (a[s] + a[s-1] + skip * a[s-2]) * p   — two adds and one multiply
+// per state instead of a 3-way log-sum-exp (3 MUFU ex2 + 1 lg2 on the dependent chain), with
+//   * emissions p = 2^(lp*log2e - E), E = floor of the lane's largest emission exponent this frame (computed one
+//     frame ahead, off the chain), so the best class of the lane has p in (0.5, 1];
+//   * an exact power-of-two renormalisation of the lane every frame (lane maximum back into [1,2)), exponents
+//     accumulated in C as integers — no rounding is introduced by scaling, and fp32 products carry a relative
+//     error of 2^-24 per frame instead of an absolute error in the log domain;
+//   * the neighbour lane's last state arrives by __shfl_up together with its exponent and is converted with an
+//     exact 2^(C_up - C) factor; a lane that is empty adopts the upstream exponent, a lane whose upstream is more
+//     than 2^40 larger is rescaled down first (its own mass is then below fp32 resolution of the incoming mass).
+// States that fall more than 2^-126 below their lane's maximum flush to zero; they are re-fed by their lower
+// neighbours on the next frame, and a flushed state cannot carry posterior mass unless two classes of the label
+// set differ by more than e^-87 in the same frame.
+template <int K, typename TIn>
+__global__ void __launch_bounds__(32) ctc_scan_lin_kernel(const ScanParams p) {
+    constexpr int KL = K / 2;
+    constexpr int D = (K >= 12) ? 8 : 16;     // emission prefetch depth (frames)
+    constexpr int EW = KL + 1;                // staged words per lane per frame: blank + KL labels
+    const int b = blockIdx.x;
+    const int dir = blockIdx.y;               // 0: alpha, 1: beta (time- and label-mirrored problem)
+    const int lane = threadIdx.x;
+    __shared__ double fin[2];
+
+    long long tbl = p.input_lengths[b];
+    long long tll = p.target_lengths[b];
+    const int Tb = (int)(tbl < 0 ? 0 : (tbl > p.T ? p.T : tbl));
+    const int L = (int)(tll < 0 ? 0 : (tll > p.Lmax ? p.Lmax : tll));
+    const int S = 2 * L + 1;
+    const int64_t* tgt = p.targets + (p.target_offsets ? p.target_offsets[b] : (int64_t)b * p.target_stride);
+
+    if (Tb == 0) {  // ATen: input_length 0 -> nll = 0 if L == 0 else inf
+        if (dir == 0 && lane == 0) {
+            p.nll[b] = (L == 0) ? 0.f : CUDART_INF_F;
+            if (p.nll2) p.nll2[b] = (L == 0) ? 0.0 : (double)CUDART_INF_F;
+        }
+        if (dir == 0 && p.chain)
+            for (int j = lane; j < L; j += 32) p.chain[(size_t)b * p.Lpad + j] = kChainFirst | kChainNone;
+        return;
+    }
+    if (lane < 2) fin[lane] = -(double)CUDART_INF_F;
+    __syncwarp();
+
+    const int g = lane;                        // owns (mirrored) states g*K .. g*K+K-1
+    const int nvalid = min(max(S - g * K, 0), K);
+    int lab[KL];
+    bool skip[KL];
+#pragma unroll
+    for (int i = 0; i < KL; ++i) {
+        const int j = g * KL + i;
+        lab[i] = p.blank; skip[i] = false;
+        if (j < L) {
+            long long c = tgt[dir ? (L - 1 - j) : j];
+            c = c < 0 ? 0 : (c >= p.V ? p.V - 1 : c);
+            lab[i] = (int)c;
+            if (j >= 1) {
+                long long cp = tgt[dir ? (L - j) : (j - 1)];
+                cp = cp < 0 ? 0 : (cp >= p.V ? p.V - 1 : cp);
+                skip[i] = (cp != c);
+            }
+        }
+    }
+    long long fstep = dir ? -p.stride_t : p.stride_t;
+    asm volatile("" : "+l"(fstep));
+    const TIn* row0 = reinterpret_cast<const TIn*>(p.lp) + (int64_t)b * p.stride_b +
+                      (int64_t)(dir ? Tb - 1 : 0) * p.stride_t;
+    const TIn* gp_b = row0 + p.blank + fstep;
+    const TIn* gp_l[KL];
+#pragma unroll
+    for (int i = 0; i < KL; ++i) gp_l[i] = row0 + lab[i] + fstep;
+
+    // ---- frame 0
+    float a[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) a[j] = 0.f;
+    int C = 0;
+    bool has_mass = false;
+    if (g == 0) {
+        const float xb = to_float(__ldg(row0 + p.blank)) * AVCTC_LOG2E;
+        const float xl = (L > 0) ? to_float(__ldg(row0 + lab[0])) * AVCTC_LOG2E : AVCTC_NEG_INF;
+        const float mx = fmaxf(xb, xl);
+        const float Ef = (mx > -1.0e29f) ? floorf(mx) : 0.f;
+        a[0] = ex2_approx(xb - Ef);
+        a[1] = ex2_approx(xl - Ef);
+        C = (int)Ef;
+        has_mass = fmaxf(a[0], a[1]) > 0.f;
+    }
+    const size_t rowi0 = (size_t)b * p.T + (dir ? Tb - 1 : 0);
+    float* wsp = (dir ? p.beta : p.alpha) + (p.store ? rowi0 * p.S_pad + (size_t)g * K : 0);
+    int* cfp = (dir ? p.coff_b : p.coff_a) + (p.store ? rowi0 * 32 + g : 0);
+    long long wstep = dir ? -(long long)p.S_pad : (long long)p.S_pad;
+    long long cstep = dir ? -32ll : 32ll;
+    asm volatile("" : "+l"(wstep), "+l"(cstep));
+    const bool do_store = p.store != 0;
+    auto publish = [&]() {
+        if (do_store) {
+            if constexpr (K % 4 == 0) {
+#pragma unroll
+                for (int i = 0; i < K / 4; ++i)
+                    reinterpret_cast<float4*>(wsp)[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < K / 2; ++i) reinterpret_cast<float2*>(wsp)[i] = make_float2(a[2 * i], a[2 * i + 1]);
+            }
+            *cfp = C;
+            wsp += wstep; cfp += cstep;
+        }
+    };
+    publish();
+
+    // ---- emission staging (cp.async gathers, D frames ahead)
+    extern __shared__ __align__(16) unsigned em_raw[];   // [D][32][EW]
+    constexpr int slot_words = 32 * EW;
+    unsigned* em_mine = em_raw + lane * EW;
+    int par_b = 0, par_l[KL];
+#pragma unroll
+    for (int i = 0; i < KL; ++i) par_l[i] = 0;
+    const int par_step = (int)(fstep & 1);
+    const bool gathers = nvalid > 0;
+    auto issue = [&](unsigned* dst, bool live) {
+        if (live && gathers) {
+            if constexpr (sizeof(TIn) == 4) {
+                cp_async_4(dst, gp_b);
+#pragma unroll
+                for (int i = 0; i < KL; ++i) cp_async_4(dst + 1 + i, gp_l[i]);
+            } else {
+                cp_async_4(dst, reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(gp_b) & ~(uintptr_t)3));
+#pragma unroll
+                for (int i = 0; i < KL; ++i)
+                    cp_async_4(dst + 1 + i,
+                               reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(gp_l[i]) & ~(uintptr_t)3));
+            }
+        }
+        cp_async_commit();
+        gp_b += fstep;
+#pragma unroll
+        for (int i = 0; i < KL; ++i) gp_l[i] += fstep;
+    };
+    if constexpr (sizeof(TIn) == 2) {
+        par_b = (int)((reinterpret_cast<uintptr_t>(gp_b) >> 1) & 1);
+#pragma unroll
+        for (int i = 0; i < KL; ++i) par_l[i] = (int)((reinterpret_cast<uintptr_t>(gp_l[i]) >> 1) & 1);
+    }
+    for (int d = 1; d <= D; ++d) issue(em_mine + (d & (D - 1)) * slot_words, d < Tb);
+
+    // emissions of one frame -> per-state probabilities relative to the lane exponent E
+    float pb[KL], pl[KL];
+    int E = 0;
+    int slot = 1 & (D - 1);
+    int live_left = Tb - 1 - D;
+    auto prepare = [&]() {          // consumes the staged frame in `slot`, refills it, advances
+        cp_async_wait<D - 1>();
+        unsigned* sl_ptr = em_mine + slot * slot_words;
+        float xb, xl[KL];
+        if constexpr (sizeof(TIn) == 4) {
+            xb = __uint_as_float(sl_ptr[0]);
+#pragma unroll
+            for (int i = 0; i < KL; ++i) xl[i] = __uint_as_float(sl_ptr[1 + i]);
+        } else {
+            auto pick = [](unsigned w, int par) { return __uint_as_float(par ? (w & 0xffff0000u) : (w << 16)); };
+            xb = pick(sl_ptr[0], par_b);
+            par_b ^= par_step;
+#pragma unroll
+            for (int i = 0; i < KL; ++i) { xl[i] = pick(sl_ptr[1 + i], par_l[i]); par_l[i] ^= par_step; }
+        }
+        issue(sl_ptr, live_left > 0);
+        --live_left;
+        slot = (slot + 1) & (D - 1);
+        xb = (nvalid > 0) ? xb * AVCTC_LOG2E : AVCTC_NEG_INF;
+        float mx = xb;
+#pragma unroll
+        for (int i = 0; i < KL; ++i) {
+            xl[i] = (2 * i + 1 < nvalid) ? xl[i] * AVCTC_LOG2E : AVCTC_NEG_INF;
+            mx = fmaxf(mx, xl[i]);
+        }
+        const float Ef = (mx > -1.0e29f) ? floorf(mx) : 0.f;
+        E = (int)Ef;
+        const float pblank = ex2_approx(xb - Ef);
+#pragma unroll
+        for (int i = 0; i < KL; ++i) {
+            pb[i] = (2 * i < nvalid) ? pblank : 0.f;
+            pl[i] = ex2_approx(xl[i] - Ef);
+        }
+    };
+    if (Tb > 1) prepare();
+
+#pragma unroll 1
+    for (int tau = 1; tau < Tb; ++tau) {
+        const float up_a = __shfl_up_sync(kFullMask, a[K - 1], 1);
+        const int up_C = __shfl_up_sync(kFullMask, C, 1);
+        // this frame's probabilities (prepared one frame ahead)
+        float cb_[KL], cl_[KL];
+#pragma unroll
+        for (int i = 0; i < KL; ++i) { cb_[i] = pb[i]; cl_[i] = pl[i]; }
+        const int Ecur = E;
+        if (tau + 1 < Tb) prepare();                     // next frame's emissions, off the dependent chain
+        // incoming boundary state: exact power-of-two conversion between lane exponents
+        const bool has_up = (lane > 0) && (up_a > 0.f);
+        int d = has_up ? up_C - C : 0;
+        if (!has_mass && has_up) { C = up_C; d = 0; }
+        if (d > 40) {
+            const int sh = d - 40;
+            const float k = (sh < 126) ? __int_as_float((127 - sh) << 23) : 0.f;
+#pragma unroll
+            for (int j = 0; j < K; ++j) a[j] *= k;
+            C += sh; d = 40;
+        }
+        const float sc = (has_up && d > -126) ? __int_as_float((127 + d) << 23) : 0.f;
+        const float prev = up_a * sc;
+        float nw[K];
+#pragma unroll
+        for (int i = 0; i < KL; ++i) {
+            const float below = (i == 0) ? prev : a[2 * i - 1];
+            nw[2 * i] = (a[2 * i] + below) * cb_[i];
+            nw[2 * i + 1] = (a[2 * i + 1] + a[2 * i] + (skip[i] ? below : 0.f)) * cl_[i];
+        }
+        float mm = nw[0];
+#pragma unroll
+        for (int j = 1; j < K; ++j) mm = fmaxf(mm, nw[j]);
+        has_mass = mm > 0.f;
+        const int e = has_mass ? ((__float_as_int(mm) >> 23) - 127) : 0;
+        const float sn = __int_as_float((127 - e) << 23);
+#pragma unroll
+        for (int j = 0; j < K; ++j) a[j] = nw[j] * sn;
+        C += Ecur + e;
+        publish();
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const int st = g * K + j;
+        const double tv = (a[j] > 0.f) ? log2((double)a[j]) + (double)C : -(double)CUDART_INF_F;
+        if (st == S - 1) fin[0] = tv;
+        if (st == S - 2) fin[1] = tv;
+    }
+    __syncwarp();
+    if (dir == 0) {
+        if (lane == 0) {
+            const double x = fin[0], y = fin[1];
+            const double m = fmax(x, y), n = fmin(x, y);
+            double ll2;
+            if (m == -(double)CUDART_INF_F) ll2 = m;
+            else ll2 = m + log2(1.0 + exp2(n - m));
+            p.nll[b] = (float)(-ll2 * AVCTC_LN2_D);
+            if (p.nll2) p.nll2[b] = -ll2;
+        }
+        if (p.chain) {
+            for (int j = lane; j < L; j += 32) {
+                const long long c = tgt[j];
+                bool first = true;
+                for (int k = 0; k < j; ++k) if (tgt[k] == c) { first = false; break; }
+                int nxt = kChainNone;
+                for (int k = j + 1; k < L; ++k) if (tgt[k] == c) { nxt = k; break; }
+                p.chain[(size_t)b * p.Lpad + j] = nxt | (first ? kChainFirst : 0);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct GradParams {
     const void* lp; int64_t stride_t, stride_b;
     int T, B, V;
@@ -366,7 +637,7 @@ struct GradParams {
     void* grad;
     const float* alpha; const float* beta; const int* coff_a; const int* coff_b;
     const double* nll2; const int* chain;
-    int K, W, S_pad, Lpad;
+    int K, W, S_pad, Lpad, linear;
     int row_floats;   // per-warp smem floats for one staged row (>= V + 8, multiple of 4)
     int w_floats;     // per-warp smem floats for state weights (>= 2*Lmax+1, multiple of 4)
 };
@@ -484,15 +755,30 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const GradParams p) {
         const int perw = p.K;   // states per lane (offsets are per lane)
 
         // log2 of alpha_t(s)*beta_t(s)/P, offsets folded in fp64; loads issued before the row is waited on
+        // state weight = alpha*beta/(P*p): (mantissa product, log2 exponent) pairs; linear workspaces hold fp32
+        // mantissas relative to integer lane exponents, log workspaces hold log2 values (mantissa 1).
+        auto state_term = [&](int s, float& mant) -> double {
+            const int sm = S - 1 - s;
+            const int cexp = ca[s / perw] + cb[sm / perw];
+            if (p.linear) {
+                const float av = arow[s], bv = brow[sm];
+                if (!(av >= 1.17549435e-38f) || !(bv >= 1.17549435e-38f)) { mant = 0.f; return 0.0; }
+                const int ia = __float_as_int(av), ib = __float_as_int(bv);
+                mant = __int_as_float((ia & 0x007fffff) | 0x3f800000) * __int_as_float((ib & 0x007fffff) | 0x3f800000);
+                return (double)((ia >> 23) + (ib >> 23) - 254 + cexp) + nll2;
+            }
+            mant = 1.f;
+            return (double)arow[s] + (double)brow[sm] + (double)cexp + nll2;
+        };
         double e0[NS];
+        float mt[NS];
         int cls[NS];
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const int s = lane + 32 * i;
-            e0[i] = 0.0; cls[i] = p.blank;
+            e0[i] = 0.0; mt[i] = 0.f; cls[i] = p.blank;
             if (s < S) {
-                const int sm = S - 1 - s;
-                e0[i] = (double)arow[s] + (double)brow[sm] + (double)(ca[s / perw] + cb[sm / perw]) + nll2;
+                e0[i] = state_term(s, mt[i]);
                 if (s & 1) {
                     long long c = tgt[s >> 1];
                     cls[i] = (int)(c < 0 ? 0 : (c >= p.V ? p.V - 1 : c));
@@ -504,18 +790,17 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const GradParams p) {
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const int s = lane + 32 * i;
-            if (s < S) wbuf[s] = ex2_approx((float)(e0[i] - (double)(rowbuf[o_in + cls[i]] * AVCTC_LOG2E)));
+            if (s < S) wbuf[s] = mt[i] * ex2_approx((float)(e0[i] - (double)(rowbuf[o_in + cls[i]] * AVCTC_LOG2E)));
         }
         for (int s = lane + 32 * NS; s < S; s += 32) {
-            const int sm = S - 1 - s;
             int c = p.blank;
             if (s & 1) {
                 long long cc = tgt[s >> 1];
                 c = (int)(cc < 0 ? 0 : (cc >= p.V ? p.V - 1 : cc));
             }
-            const double e = (double)arow[s] + (double)brow[sm] + (double)(ca[s / perw] + cb[sm / perw]) + nll2 -
-                             (double)(rowbuf[o_in + c] * AVCTC_LOG2E);
-            wbuf[s] = ex2_approx((float)e);
+            float mant;
+            const double e = state_term(s, mant) - (double)(rowbuf[o_in + c] * AVCTC_LOG2E);
+            wbuf[s] = mant * ex2_approx((float)e);
         }
         __syncwarp();
         // class posteriors: blank = sum of even states; label c = sum along its repeat chain
@@ -550,6 +835,219 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const GradParams p) {
         __syncwarp();
         write_row(grow, p.V, outbuf, o_out, lane);
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ctc_grad_lin_kernel — gradient pass for the probability-domain workspaces (ctc_scan_lin_kernel).
+//
+// A warp owns ONE sample and a strided set of its frames, so everything that depends only on the sample (labels,
+// repeat chains, lengths, scale, -log2 P split into integer + fraction) is set up once and lives in registers.
+// Lane l owns the same K lattice states as scan lane l (alpha is read as K contiguous floats + one exponent).
+// Per frame: state weights alpha*beta/(P*p) = mantissa product * 2^(integer exponents + frac - lp*log2e) with the
+// exponents summed as integers; class posteriors go into a per-warp shared "delta" row that is all-zero between
+// rows; then the log-prob row streams through registers once:  grad = exp(lp)*g - delta*g  with 16-byte loads and
+// 16-byte streaming stores (no shared-memory staging of the row).  Algorithmic traffic: one read of log_probs,
+// one write of grad (+ alpha/beta once).
+template <typename TIn, bool POS>
+__device__ __forceinline__ void grad_stream_row(const TIn* __restrict__ lrow, TIn* __restrict__ grow, int V,
+                                                const float* __restrict__ delta, int o_out, float scale, float lscale,
+                                                int lane) {
+    constexpr int kVec = VecTraits<TIn>::kVec;
+    const int o_in = (int)((reinterpret_cast<uintptr_t>(lrow) / sizeof(TIn)) & (kVec - 1));
+    const int nq = (o_out + V + kVec - 1) / kVec;
+    const bool same = (o_in == o_out);
+    for (int q = lane; q < nq; q += 32) {
+        const int c0 = q * kVec - o_out;
+        const bool full = (c0 >= 0) && (c0 + kVec <= V);
+        float x[kVec];
+        if (full && same) {
+            if constexpr (sizeof(TIn) == 4) {
+                const float4 v = __ldcs(reinterpret_cast<const float4*>(lrow + c0));
+                x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+            } else {
+                const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(lrow + c0));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); x[2 * k] = f.x; x[2 * k + 1] = f.y; }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kVec; ++k) {
+                const int c = c0 + k;
+                x[k] = (c >= 0 && c < V) ? to_float(lrow[c]) : 0.f;
+            }
+        }
+        float o[kVec];
+#pragma unroll
+        for (int k4 = 0; k4 < kVec / 4; ++k4) {
+            const float4 d = *reinterpret_cast<const float4*>(delta + q * kVec + 4 * k4);
+            const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float e = ex2_approx(fmaf(x[4 * k4 + k], AVCTC_LOG2E, lscale));   // |scale| * exp(lp)
+                o[4 * k4 + k] = POS ? fmaf(dd[k], -scale, e) : -fmaf(dd[k], scale, e);  // scale < 0: -( |s|e + d s )
+            }
+        }
+        if (full) {
+            if constexpr (sizeof(TIn) == 4) {
+                __stcs(reinterpret_cast<float4*>(grow + c0), make_float4(o[0], o[1], o[2], o[3]));
+            } else {
+                uint4 raw;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
+                __stcs(reinterpret_cast<uint4*>(grow + c0), raw);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kVec; ++k) {
+                const int c = c0 + k;
+                if (c >= 0 && c < V) {
+                    if constexpr (sizeof(TIn) == 4) grow[c] = o[k];
+                    else grow[c] = __float2bfloat16(o[k]);
+                }
+            }
+        }
+    }
+}
+
+template <int K, typename TIn>
+__global__ void __launch_bounds__(256) ctc_grad_lin_kernel(const GradParams p) {
+    constexpr int KL = K / 2;
+    constexpr int kVec = VecTraits<TIn>::kVec;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    float* delta = smem + (size_t)warp * (p.row_floats + p.w_floats);   // class posteriors; all-zero between rows
+    float* wbuf = delta + p.row_floats;                                  // label-state weights of the current row
+    for (int i = lane; i < p.row_floats; i += 32) delta[i] = 0.f;
+    __syncwarp();
+    const int gw = blockIdx.x * nwarp + warp, Wtot = gridDim.x * nwarp;
+    const int WS = max(1, Wtot / p.B);                                   // warps per sample
+    const long long nitems = (long long)p.B * WS;
+    TIn* grad = reinterpret_cast<TIn*>(p.grad);
+    const TIn* lpbase = reinterpret_cast<const TIn*>(p.lp);
+
+    for (long long item = gw; item < nitems; item += Wtot) {
+        const int b = (int)(item % p.B), r = (int)(item / p.B);
+        long long tbl = p.input_lengths[b], tll = p.target_lengths[b];
+        const int Tb = (int)(tbl < 0 ? 0 : (tbl > p.T ? p.T : tbl));
+        const int L = (int)(tll < 0 ? 0 : (tll > p.Lmax ? p.Lmax : tll));
+        const int S = 2 * L + 1;
+        const float nllb = p.nll[b];
+        const bool zero_all = (p.zero_infinity && nllb == CUDART_INF_F);
+        const double nll2 = p.nll2[b];                                   // -log2 P
+        const bool bad = !(fabs(nll2) < 1.0e300);                        // infeasible without zero_infinity: NaN rows
+        const double nfl = bad ? 0.0 : floor(nll2);
+        const int nll2_i = (int)nfl;
+        const float nll2_f = bad ? 0.f : (float)(nll2 - nfl);
+        float scale = p.grad_out[(int64_t)b * p.grad_out_stride];
+        if (p.reduction == AVCTC_REDUCE_MEAN) scale /= ((float)p.B * (float)(L > 1 ? L : 1));
+        if (bad) scale = __int_as_float(0x7fc00000);
+        const float lscale = lg2_approx(fabsf(scale));
+        const int64_t* tgt = p.targets + (p.target_offsets ? p.target_offsets[b] : (int64_t)b * p.target_stride);
+        const int* chain = p.chain + (size_t)b * p.Lpad;
+        int cls[KL], chn[KL];
+#pragma unroll
+        for (int i = 0; i < KL; ++i) {
+            const int pos = lane * KL + i;
+            cls[i] = p.blank; chn[i] = 0;
+            if (pos < L) {
+                long long c = tgt[pos];
+                cls[i] = (int)(c < 0 ? 0 : (c >= p.V ? p.V - 1 : c));
+                chn[i] = chain[pos];
+            }
+        }
+        const int s0 = lane * K;
+        const int nval = min(max(S - s0, 0), K);
+        const int sm0 = S - 1 - s0;              // beta (mirrored) index of state s0; state s0+j -> sm0 - j
+
+        for (int t = r; t < p.T; t += WS) {
+            const long long row = (long long)t * p.B + b;
+            TIn* grow = grad + (size_t)row * p.V;
+            const int o_out = (int)((reinterpret_cast<uintptr_t>(grow) / sizeof(TIn)) & (kVec - 1));
+            if (t >= Tb || zero_all) {
+                const int nq = (o_out + p.V + kVec - 1) / kVec;
+                for (int q = lane; q < nq; q += 32) {
+                    const int c0 = q * kVec - o_out;
+                    if (c0 >= 0 && c0 + kVec <= p.V) __stcs(reinterpret_cast<uint4*>(grow + c0), make_uint4(0, 0, 0, 0));
+                    else
+                        for (int k = 0; k < kVec; ++k)
+                            if (c0 + k >= 0 && c0 + k < p.V) {
+                                if constexpr (sizeof(TIn) == 4) grow[c0 + k] = 0.f;
+                                else grow[c0 + k] = __float2bfloat16(0.f);
+                            }
+                }
+                continue;
+            }
+            const TIn* lrow = lpbase + (int64_t)t * p.stride_t + (int64_t)b * p.stride_b;
+            const size_t rowi = (size_t)b * p.T + t;
+            const float* arow = p.alpha + rowi * p.S_pad + s0;
+            const float* brow = p.beta + rowi * p.S_pad;
+            const int* cbp = p.coff_b + rowi * 32;
+            const int caL = p.coff_a[rowi * 32 + lane];
+            float av[K], bv[K];
+            int cbv[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                av[j] = 0.f; bv[j] = 0.f; cbv[j] = 0;
+                if (j < nval) {
+                    const int sm = sm0 - j;
+                    av[j] = arow[j];
+                    bv[j] = brow[sm];
+                    cbv[j] = cbp[sm / K];
+                }
+            }
+            const float xb = to_float(__ldg(lrow + p.blank)) * AVCTC_LOG2E;
+            float xl[KL];
+#pragma unroll
+            for (int i = 0; i < KL; ++i) xl[i] = to_float(__ldg(lrow + cls[i])) * AVCTC_LOG2E;
+            float w[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                w[j] = 0.f;
+                if (av[j] >= 1.17549435e-38f && bv[j] >= 1.17549435e-38f) {
+                    const int ia = __float_as_int(av[j]), ib = __float_as_int(bv[j]);
+                    const float mant = __int_as_float((ia & 0x007fffff) | 0x3f800000) *
+                                       __int_as_float((ib & 0x007fffff) | 0x3f800000);
+                    const int ei = (ia >> 23) + (ib >> 23) - 254 + caL + cbv[j] + nll2_i;
+                    const float x = (float)ei + (nll2_f - ((j & 1) ? xl[j >> 1] : xb));
+                    w[j] = mant * ex2_approx(x);
+                }
+            }
+            float pbs = 0.f;
+#pragma unroll
+            for (int i = 0; i < KL; ++i) pbs += w[2 * i];
+            pbs = warp_sum(pbs);
+#pragma unroll
+            for (int i = 0; i < KL; ++i) {
+                const int pos = lane * KL + i;
+                if (pos < L) wbuf[pos] = w[2 * i + 1];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < KL; ++i) {
+                if (chn[i] & kChainFirst) {
+                    float acc = w[2 * i + 1];
+                    int k = chn[i] & kChainNone;
+                    while (k != kChainNone) {
+                        acc += wbuf[k];
+                        k = chain[k] & kChainNone;
+                    }
+                    delta[o_out + cls[i]] = acc;
+                }
+            }
+            if (lane == 0) delta[o_out + p.blank] = pbs;
+            __syncwarp();
+            if (scale > 0.f) grad_stream_row<TIn, true>(lrow, grow, p.V, delta, o_out, scale, lscale, lane);
+            else grad_stream_row<TIn, false>(lrow, grow, p.V, delta, o_out, scale, lscale, lane);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < KL; ++i)
+                if (chn[i] & kChainFirst) delta[o_out + cls[i]] = 0.f;
+            if (lane == 0) delta[o_out + p.blank] = 0.f;
+            __syncwarp();
+        }
     }
 }
 
@@ -608,6 +1106,27 @@ static int dispatch_scan(const ScanParams& sp, int K, int ndir, cudaStream_t st)
     return AVCTC_ERR_UNSUPPORTED;
 }
 
+template <int K, typename TIn>
+static int launch_scan_lin(const ScanParams& sp, int ndir, cudaStream_t st) {
+    constexpr int D = (K >= 12) ? 8 : 16;
+    dim3 grid(sp.B, ndir), block(32);
+    const size_t smem = (size_t)D * 32 * (K / 2 + 1) * sizeof(unsigned);
+    ctc_scan_lin_kernel<K, TIn><<<grid, block, smem, st>>>(sp);
+    return (int)cudaGetLastError();
+}
+template <typename TIn>
+static int dispatch_scan_lin(const ScanParams& sp, int K, int ndir, cudaStream_t st) {
+    switch (K) {
+        case 2: return launch_scan_lin<2, TIn>(sp, ndir, st);
+        case 4: return launch_scan_lin<4, TIn>(sp, ndir, st);
+        case 6: return launch_scan_lin<6, TIn>(sp, ndir, st);
+        case 8: return launch_scan_lin<8, TIn>(sp, ndir, st);
+        case 12: return launch_scan_lin<12, TIn>(sp, ndir, st);
+        case 16: return launch_scan_lin<16, TIn>(sp, ndir, st);
+    }
+    return AVCTC_ERR_UNSUPPORTED;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {
@@ -643,6 +1162,41 @@ static int launch_grad(const GradParams& gp_in, cudaStream_t st) {
     if (blocks < 1) return AVCTC_OK;
     ctc_grad_kernel<TIn><<<(unsigned)blocks, warps * 32, smem, st>>>(gp);
     return (int)cudaGetLastError();
+}
+
+template <int K, typename TIn>
+static int launch_grad_lin(const GradParams& gp, cudaStream_t st) {
+    const int warps = 8;
+    const size_t smem = (size_t)(gp.row_floats + gp.w_floats) * sizeof(float) * warps;
+    if (smem > 200 * 1024) return AVCTC_ERR_UNSUPPORTED;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        AVCTC_CUDA_RETURN(cudaFuncSetAttribute(ctc_grad_lin_kernel<K, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               200 * 1024));
+        configured = 200 * 1024;
+    }
+    int occ = 1;
+    AVCTC_CUDA_RETURN(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ctc_grad_lin_kernel<K, TIn>, warps * 32, smem));
+    if (occ < 1) occ = 1;
+    const long long rows = (long long)gp.T * gp.B;
+    long long blocks = (rows + warps - 1) / warps;
+    const long long cap = (long long)num_sms() * occ;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) return AVCTC_OK;
+    ctc_grad_lin_kernel<K, TIn><<<(unsigned)blocks, warps * 32, smem, st>>>(gp);
+    return (int)cudaGetLastError();
+}
+template <typename TIn>
+static int dispatch_grad_lin(const GradParams& gp, cudaStream_t st) {
+    switch (gp.K) {
+        case 2: return launch_grad_lin<2, TIn>(gp, st);
+        case 4: return launch_grad_lin<4, TIn>(gp, st);
+        case 6: return launch_grad_lin<6, TIn>(gp, st);
+        case 8: return launch_grad_lin<8, TIn>(gp, st);
+        case 12: return launch_grad_lin<12, TIn>(gp, st);
+        case 16: return launch_grad_lin<16, TIn>(gp, st);
+    }
+    return AVCTC_ERR_UNSUPPORTED;
 }
 
 }  // namespace avctc
@@ -686,6 +1240,10 @@ extern "C" int avctc_ctc_forward(const void* log_probs, int dtype, int64_t strid
     sp.W = pl.W; sp.S_pad = pl.S_pad; sp.Lpad = pl.Lpad;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int ndir = need_grad ? 2 : 1;
+    if (pl.linear) {
+        if (dtype == AVCTC_F32) return dispatch_scan_lin<float>(sp, pl.K, ndir, st);
+        return dispatch_scan_lin<__nv_bfloat16>(sp, pl.K, ndir, st);
+    }
     if (dtype == AVCTC_F32) return dispatch_scan<float>(sp, pl.K, ndir, st);
     return dispatch_scan<__nv_bfloat16>(sp, pl.K, ndir, st);
 }
@@ -730,10 +1288,14 @@ extern "C" int avctc_ctc_backward(const void* log_probs, int dtype, int64_t stri
     gp.coff_b = reinterpret_cast<const int*>(w + pl.off_coff_b);
     gp.nll2 = reinterpret_cast<const double*>(w + pl.off_nll2);
     gp.chain = reinterpret_cast<const int*>(w + pl.off_chain);
-    gp.K = pl.K; gp.W = pl.W; gp.S_pad = pl.S_pad; gp.Lpad = pl.Lpad;
+    gp.K = pl.K; gp.W = pl.W; gp.S_pad = pl.S_pad; gp.Lpad = pl.Lpad; gp.linear = pl.linear;
     gp.row_floats = (V + 8 + 3) & ~3;
     gp.w_floats = (2 * max_target_len + 1 + 3) & ~3;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (pl.linear) {
+        if (dtype == AVCTC_F32) return dispatch_grad_lin<float>(gp, st);
+        return dispatch_grad_lin<__nv_bfloat16>(gp, st);
+    }
     if (dtype == AVCTC_F32) return launch_grad<float>(gp, st);
     return launch_grad<__nv_bfloat16>(gp, st);
 }
