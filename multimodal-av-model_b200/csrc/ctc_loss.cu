@@ -839,6 +839,433 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const GradParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// ctc_scan_ws_kernel — the probability-domain scan, warp-specialised.  The frame loop of one (sample, direction)
+// is a dependent chain on a single in-order warp (~0.25-0.5 instructions/cycle), so everything that is not the
+// recurrence itself runs on the other three SM sub-partitions of the CTA:
+//   warps 0,1  producers  (even / odd frame groups) whole log-prob rows arrive by TMA bulk copies (cp.async.bulk,
+//                         kWsGroup rows per mbarrier phase, 2*kWsGroup*kWsGroups frames ahead); each lane picks its
+//                         lattice states' emissions out of shared memory and publishes 2^(lp*log2e - E) per state plus
+//                         the lane exponent E into the ring "pring"
+//   warp 2     recurrence the dependent chain only: shuffle, exponent conversion, adds/multiplies, exact power-of-two
+//                         renormalisation every second frame -> ring "sring" (lane states + exponent)
+//   warp 3     writer     sring -> alpha/beta workspace in HBM
+// Lane l of a role talks only to lane l of its neighbour role through per-lane progress words (volatile shared
+// accesses, payload before progress in program order), so neither fences nor block barriers sit in the frame loop.
+// Per-lane 4-byte gathers straight from HBM (ctc_scan_lin_kernel) are bound by DRAM random-access efficiency
+// (measured ~1 TB/s of 32-byte sectors); full rows stream at HBM speed and are also what the hardware prefetches.
+constexpr int kWsRing = 8;   // frames per ring (power of two)
+constexpr int kWsGroup = 4;  // frames per TMA mbarrier phase
+constexpr int kWsGroups = 4; // groups in flight per producer warp
+
+__device__ __forceinline__ int ws_wait_ge(const int* word, int need) {
+    int v = ld_volatile_shared_s32(word);
+    int spins = 0;
+    while (v < need) {
+        v = ld_volatile_shared_s32(word);
+        if (++spins > (1 << 26)) __trap();      // never hang the GPU on a protocol bug
+    }
+    asm volatile("" ::: "memory");              // payload accesses stay after the poll
+    return v;
+}
+__device__ __forceinline__ uint32_t ws_smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void ws_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    int spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (++spins > (1 << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void ws_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int K, typename TIn>
+__global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, const int row_stride_bytes) {
+    constexpr int KL = K / 2;
+    constexpr int G = kWsGroup, NG = kWsGroups;
+    constexpr int PW = (K + 1 + 3) & ~3;      // payload words per lane per frame: K floats + one int
+    constexpr int RD = kWsRing;
+    constexpr int ES = (int)sizeof(TIn);
+    const int b = blockIdx.x, dir = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    extern __shared__ __align__(128) unsigned char ws_smem[];
+    unsigned char* rowbuf = ws_smem;                                               // [2][NG][G][row_stride_bytes]
+    float* pring = reinterpret_cast<float*>(ws_smem + (size_t)2 * NG * G * row_stride_bytes);   // [RD][32][PW]
+    float* sring = pring + RD * 32 * PW;                                           // [RD][32][PW]
+    int* prog = reinterpret_cast<int*>(sring + RD * 32 * PW);                      // [4][32]: P0, P1, R, W next frame
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(prog + 128);  // [2][NG]
+    __shared__ double fin[2];
+
+    long long tbl = p.input_lengths[b];
+    long long tll = p.target_lengths[b];
+    const int Tb = (int)(tbl < 0 ? 0 : (tbl > p.T ? p.T : tbl));
+    const int L = (int)(tll < 0 ? 0 : (tll > p.Lmax ? p.Lmax : tll));
+    const int S = 2 * L + 1;
+    const int64_t* tgt = p.targets + (p.target_offsets ? p.target_offsets[b] : (int64_t)b * p.target_stride);
+
+    if (Tb == 0) {
+        if (dir == 0 && threadIdx.x == 0) {
+            p.nll[b] = (L == 0) ? 0.f : CUDART_INF_F;
+            if (p.nll2) p.nll2[b] = (L == 0) ? 0.0 : (double)CUDART_INF_F;
+        }
+        if (dir == 0 && p.chain)
+            for (int j = threadIdx.x; j < L; j += blockDim.x) p.chain[(size_t)b * p.Lpad + j] = kChainFirst | kChainNone;
+        return;
+    }
+    prog[threadIdx.x] = 1;
+    if (threadIdx.x < 2) fin[threadIdx.x] = -(double)CUDART_INF_F;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2 * NG; ++i) ws_mbar_init(ws_smem_u32(&mbar[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int g = lane;
+    const int nvalid = min(max(S - g * K, 0), K);
+    const bool do_store = p.store != 0;
+    const TIn* row0 = reinterpret_cast<const TIn*>(p.lp) + (int64_t)b * p.stride_b +
+                      (int64_t)(dir ? Tb - 1 : 0) * p.stride_t;
+    const long long fstep = dir ? -p.stride_t : p.stride_t;
+    float* pmine = pring + lane * PW;
+    float* smine = sring + lane * PW;
+
+    if (warp < 2) {
+        // ================================================================ producers (warp pw: groups pw, pw+2, ...)
+        const int pw = warp;
+        int lab[KL];
+#pragma unroll
+        for (int i = 0; i < KL; ++i) {
+            const int j = g * KL + i;
+            lab[i] = p.blank;
+            if (j < L) {
+                long long c = tgt[dir ? (L - 1 - j) : j];
+                lab[i] = (int)(c < 0 ? 0 : (c >= p.V ? p.V - 1 : c));
+            }
+        }
+        // A row's 16-byte aligned window may read up to 15 bytes of its neighbours.  Below the tensor that is always
+        // inside the allocation (an unaligned base is an interior pointer); above it only the row with the highest
+        // address can leave the tensor: that single frame (if any) is copied by plain loads instead.
+        const uintptr_t hi = reinterpret_cast<uintptr_t>(p.lp) +
+                             (uintptr_t)(((long long)(p.T - 1) * p.stride_t + (long long)(p.B - 1) * p.stride_b + p.V) * ES);
+        const long long fstep_b = fstep * ES;
+        const uint32_t VB = (uint32_t)p.V * ES;
+        int bad_f = -1;
+        if (fstep >= 0 && Tb > 1) {
+            const uintptr_t sl_ = reinterpret_cast<uintptr_t>(row0) + (uintptr_t)((long long)(Tb - 1) * fstep_b);
+            if ((sl_ & ~(uintptr_t)15) + (((sl_ & 15) + VB + 15) & ~(uintptr_t)15) > hi) bad_f = Tb - 1;
+        }
+        unsigned char* myrows = rowbuf + (size_t)pw * NG * G * row_stride_bytes;
+        const uint32_t myrows_s = ws_smem_u32(myrows);
+        unsigned long long* mybar = mbar + pw * NG;
+        // frames of my k-th group: 1 + (2k + pw)*G + j
+        uintptr_t src_arm = reinterpret_cast<uintptr_t>(row0) + (uintptr_t)(fstep_b * (1 + pw * G));
+        int f_arm = 1 + pw * G;
+        auto arm = [&](int sl) {             // warp-wide: start the copies of frames f_arm .. f_arm+G-1 into slot group sl
+            const uint32_t bar = ws_smem_u32(&mybar[sl]);
+            __syncwarp();                    // every lane is done reading the rows this group replaces
+            if (bad_f >= f_arm && bad_f < f_arm + G) {
+                const int j = bad_f - f_arm;
+                const uintptr_t src = src_arm + (uintptr_t)((long long)j * fstep_b);
+                unsigned char* dst = myrows + (size_t)(sl * G + j) * row_stride_bytes + (src & 15);
+                const TIn* srow = reinterpret_cast<const TIn*>(src);
+                for (int c = lane; c < p.V; c += 32) reinterpret_cast<TIn*>(dst)[c] = srow[c];
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+            }
+            if (lane == 0) {
+                uint32_t total = 0;
+                uintptr_t src = src_arm;
+                uint32_t dst = myrows_s + (uint32_t)(sl * G * row_stride_bytes);
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    const int f = f_arm + j;
+                    if (f < Tb && f != bad_f) {
+                        const uint32_t nb = (uint32_t)(((uint32_t)(src & 15) + VB + 15u) & ~15u);
+                        ws_bulk_g2s(dst, reinterpret_cast<const void*>(src & ~(uintptr_t)15), nb, bar);
+                        total += nb;
+                    }
+                    src += (uintptr_t)fstep_b;
+                    dst += (uint32_t)row_stride_bytes;
+                }
+                ws_mbar_expect_tx(bar, total);       // the one arrival of this phase; tx may complete before it
+            }
+            src_arm += (uintptr_t)(fstep_b * 2 * G);
+            f_arm += 2 * G;
+        };
+        const int ngroups_all = (Tb - 1 + G - 1) / G;
+        const int mygroups = (ngroups_all - pw + 1) / 2;       // groups pw, pw+2, ... < ngroups_all
+        for (int k = 0; k < NG && k < mygroups; ++k) arm(k);
+        const uint32_t off_b = (uint32_t)p.blank * ES;
+        uint32_t off_l[KL];
+        float ninf_l[KL], one_b[KL];                            // validity as arithmetic (no predicate re-materialisation)
+#pragma unroll
+        for (int i = 0; i < KL; ++i) {
+            off_l[i] = (uint32_t)lab[i] * ES;
+            ninf_l[i] = (2 * i + 1 < nvalid) ? 0.f : AVCTC_NEG_INF;
+            one_b[i] = (2 * i < nvalid) ? 1.f : 0.f;
+        }
+        const float ninf_b = (nvalid > 0) ? 0.f : AVCTC_NEG_INF;
+        auto lds_val = [&](uint32_t addr) -> float {
+            if constexpr (ES == 4) {
+                float v;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+                return v;
+            } else {
+                unsigned short h;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+                return __uint_as_float((unsigned)h << 16);
+            }
+        };
+        int cons = 1;
+        int sl = 0;
+        uint32_t par = 0;
+        uintptr_t src_c = reinterpret_cast<uintptr_t>(row0) + (uintptr_t)(fstep_b * (1 + pw * G));
+        int f = 1 + pw * G;
+#pragma unroll 1
+        for (int k = 0; k < mygroups; ++k) {
+            ws_mbar_wait(ws_smem_u32(&mybar[sl]), par);
+            uint32_t rbase = myrows_s + (uint32_t)(sl * G * row_stride_bytes);
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                if (f < Tb) {
+                    const uint32_t rb = rbase + (uint32_t)(src_c & 15);
+                    float xb = lds_val(rb + off_b) + ninf_b;
+                    float xl[KL];
+                    float mx = xb;
+#pragma unroll
+                    for (int i = 0; i < KL; ++i) { xl[i] = lds_val(rb + off_l[i]) + ninf_l[i]; mx = fmaxf(mx, xl[i]); }
+                    const float ms = mx * AVCTC_LOG2E;
+                    const float Ef = (ms > -1.0e29f) ? floorf(ms) : 0.f;
+                    const float pblank = ex2_approx(fmaf(xb, AVCTC_LOG2E, -Ef));
+                    float pay[PW];
+#pragma unroll
+                    for (int i = 0; i < KL; ++i) {
+                        pay[2 * i] = pblank * one_b[i];
+                        pay[2 * i + 1] = ex2_approx(fmaf(xl[i], AVCTC_LOG2E, -Ef));
+                    }
+                    pay[K] = __int_as_float((int)Ef);
+#pragma unroll
+                    for (int i = K + 1; i < PW; ++i) pay[i] = 0.f;
+                    if (f - cons >= RD) cons = ws_wait_ge(&prog[64 + lane], f - RD + 1);
+                    float4* dst = reinterpret_cast<float4*>(pmine + (f & (RD - 1)) * 32 * PW);
+#pragma unroll
+                    for (int i = 0; i < PW / 4; ++i)
+                        dst[i] = make_float4(pay[4 * i], pay[4 * i + 1], pay[4 * i + 2], pay[4 * i + 3]);
+                    asm volatile("" ::: "memory");
+                    st_volatile_shared_s32(&prog[pw * 32 + lane], f + 1);
+                }
+                ++f;
+                src_c += (uintptr_t)fstep_b;
+                rbase += (uint32_t)row_stride_bytes;
+            }
+            f += G;                                   // skip the other producer's group
+            src_c += (uintptr_t)(fstep_b * G);
+            if (k + NG < mygroups) arm(sl);
+            if (++sl == NG) { sl = 0; par ^= 1u; }
+        }
+        return;
+    }
+
+    if (warp == 3) {
+        // ================================================================ writer
+        if (!do_store || Tb < 2) return;
+        const size_t rowi1 = (size_t)b * p.T + (dir ? Tb - 2 : 1);       // scan frame 1
+        float* wsp = (dir ? p.beta : p.alpha) + rowi1 * p.S_pad + (size_t)g * K;
+        int* cfp = (dir ? p.coff_b : p.coff_a) + rowi1 * 32 + g;
+        long long wstep = dir ? -(long long)p.S_pad : (long long)p.S_pad;
+        long long cstep = dir ? -32ll : 32ll;
+        asm volatile("" : "+l"(wstep), "+l"(cstep));
+        int avail = 1;
+#pragma unroll 1
+        for (int f = 1; f < Tb; ++f) {
+            if (avail <= f) avail = ws_wait_ge(&prog[64 + lane], f + 1);
+            const float4* src = reinterpret_cast<const float4*>(smine + (f & (RD - 1)) * 32 * PW);
+            float pay[PW];
+#pragma unroll
+            for (int i = 0; i < PW / 4; ++i) {
+                const float4 v = src[i];
+                pay[4 * i] = v.x; pay[4 * i + 1] = v.y; pay[4 * i + 2] = v.z; pay[4 * i + 3] = v.w;
+            }
+            asm volatile("" ::: "memory");
+            st_volatile_shared_s32(&prog[96 + lane], f + 1);
+            if constexpr (K % 4 == 0) {
+#pragma unroll
+                for (int i = 0; i < K / 4; ++i)
+                    reinterpret_cast<float4*>(wsp)[i] = make_float4(pay[4 * i], pay[4 * i + 1], pay[4 * i + 2], pay[4 * i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < K / 2; ++i) reinterpret_cast<float2*>(wsp)[i] = make_float2(pay[2 * i], pay[2 * i + 1]);
+            }
+            *cfp = __float_as_int(pay[K]);
+            wsp += wstep; cfp += cstep;
+        }
+        return;
+    }
+
+    // ==================================================================== recurrence (warp 2)
+    float skipf[KL];
+#pragma unroll
+    for (int i = 0; i < KL; ++i) {
+        const int j = g * KL + i;
+        skipf[i] = 0.f;
+        if (j < L && j >= 1) {
+            long long c = tgt[dir ? (L - 1 - j) : j];
+            c = c < 0 ? 0 : (c >= p.V ? p.V - 1 : c);
+            long long cp = tgt[dir ? (L - j) : (j - 1)];
+            cp = cp < 0 ? 0 : (cp >= p.V ? p.V - 1 : cp);
+            skipf[i] = (cp != c) ? 1.f : 0.f;
+        }
+    }
+    float a[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) a[j] = 0.f;
+    int C = 0;
+    bool has_mass = false;
+    if (g == 0) {
+        int lab0 = p.blank;
+        if (L > 0) {
+            long long c = tgt[dir ? (L - 1) : 0];
+            lab0 = (int)(c < 0 ? 0 : (c >= p.V ? p.V - 1 : c));
+        }
+        const float xb = to_float(__ldg(row0 + p.blank)) * AVCTC_LOG2E;
+        const float xl = (L > 0) ? to_float(__ldg(row0 + lab0)) * AVCTC_LOG2E : AVCTC_NEG_INF;
+        const float mx = fmaxf(xb, xl);
+        const float Ef = (mx > -1.0e29f) ? floorf(mx) : 0.f;
+        a[0] = ex2_approx(xb - Ef);
+        a[1] = ex2_approx(xl - Ef);
+        C = (int)Ef;
+        has_mass = fmaxf(a[0], a[1]) > 0.f;
+    }
+    if (do_store) {     // frame 0 goes straight to the workspace
+        const size_t rowi0 = (size_t)b * p.T + (dir ? Tb - 1 : 0);
+        float* w0 = (dir ? p.beta : p.alpha) + rowi0 * p.S_pad + (size_t)g * K;
+#pragma unroll
+        for (int j = 0; j < K; ++j) w0[j] = a[j];
+        ((dir ? p.coff_b : p.coff_a) + rowi0 * 32)[g] = C;
+    }
+    const bool not_lane0 = lane > 0;
+    int availP[2] = {1, 1};
+    int doneW = 1;
+    // one frame of the chain; RENORM frames bring the lane maximum back into [1,2) (exact power of two), the frames
+    // in between only accumulate the emission exponent — two frames cannot move a lane by more than fp32's range
+    // unless a class the mass sits on is > e^-40 below the best class of its lane twice in a row.
+    auto frame = [&](const int tau, const int owner, const bool renorm) {
+        const float up_a = __shfl_up_sync(kFullMask, a[K - 1], 1);
+        const int up_C = __shfl_up_sync(kFullMask, C, 1);
+        if (availP[owner] <= tau) availP[owner] = ws_wait_ge(&prog[owner * 32 + lane], tau + 1);
+        if (do_store && tau - doneW >= RD) doneW = ws_wait_ge(&prog[96 + lane], tau - RD + 1);
+        const int roff = (tau & (RD - 1)) * 32 * PW;
+        float pr[PW];
+        {
+            const float4* src = reinterpret_cast<const float4*>(pmine + roff);
+#pragma unroll
+            for (int i = 0; i < PW / 4; ++i) {
+                const float4 v = src[i];
+                pr[4 * i] = v.x; pr[4 * i + 1] = v.y; pr[4 * i + 2] = v.z; pr[4 * i + 3] = v.w;
+            }
+        }
+        const int Ecur = __float_as_int(pr[K]);
+        const bool has_up = not_lane0 && (up_a > 0.f);
+        int d = has_up ? up_C - C : 0;
+        if (!has_mass && has_up) { C = up_C; d = 0; }
+        if (d > 40) {
+            const int sh = d - 40;
+            const float k = (sh < 126) ? __int_as_float((127 - sh) << 23) : 0.f;
+#pragma unroll
+            for (int j = 0; j < K; ++j) a[j] *= k;
+            C += sh; d = 40;
+        }
+        const float sc = (has_up && d > -126) ? __int_as_float((127 + d) << 23) : 0.f;
+        const float prev = up_a * sc;
+        float nw[K];
+#pragma unroll
+        for (int i = 0; i < KL; ++i) {
+            const float below = (i == 0) ? prev : a[2 * i - 1];
+            nw[2 * i] = (a[2 * i] + below) * pr[2 * i];
+            nw[2 * i + 1] = fmaf(skipf[i], below, a[2 * i + 1] + a[2 * i]) * pr[2 * i + 1];
+        }
+        if (renorm) {
+            float mm = nw[0];
+#pragma unroll
+            for (int j = 1; j < K; ++j) mm = fmaxf(mm, nw[j]);
+            has_mass = mm > 0.f;
+            const int e = has_mass ? ((__float_as_int(mm) >> 23) - 127) : 0;
+            const float sn = __int_as_float((127 - e) << 23);
+#pragma unroll
+            for (int j = 0; j < K; ++j) a[j] = nw[j] * sn;
+            C += Ecur + e;
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) a[j] = nw[j];
+            has_mass = has_mass || has_up;
+            C += Ecur;
+        }
+        if (do_store) {
+            float pay[PW];
+#pragma unroll
+            for (int j = 0; j < K; ++j) pay[j] = a[j];
+            pay[K] = __int_as_float(C);
+#pragma unroll
+            for (int i = K + 1; i < PW; ++i) pay[i] = 0.f;
+            float4* dst = reinterpret_cast<float4*>(smine + roff);
+#pragma unroll
+            for (int i = 0; i < PW / 4; ++i) dst[i] = make_float4(pay[4 * i], pay[4 * i + 1], pay[4 * i + 2], pay[4 * i + 3]);
+        }
+        asm volatile("" ::: "memory");
+        st_volatile_shared_s32(&prog[64 + lane], tau + 1);
+    };
+#pragma unroll 1
+    for (int base = 1; base < Tb; base += 2 * G) {
+#pragma unroll
+        for (int u = 0; u < 2 * G; ++u) {
+            const int tau = base + u;
+            if (tau < Tb) frame(tau, (u / G) & 1, (u & 1) == 1);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const int st = g * K + j;
+        const double tv = (a[j] > 0.f) ? log2((double)a[j]) + (double)C : -(double)CUDART_INF_F;
+        if (st == S - 1) fin[0] = tv;
+        if (st == S - 2) fin[1] = tv;
+    }
+    __syncwarp();
+    if (dir == 0) {
+        if (lane == 0) {
+            const double x = fin[0], y = fin[1];
+            const double m = fmax(x, y), n = fmin(x, y);
+            double ll2;
+            if (m == -(double)CUDART_INF_F) ll2 = m;
+            else ll2 = m + log2(1.0 + exp2(n - m));
+            p.nll[b] = (float)(-ll2 * AVCTC_LN2_D);
+            if (p.nll2) p.nll2[b] = -ll2;
+        }
+        if (p.chain) {
+            for (int j = lane; j < L; j += 32) {
+                const long long c = tgt[j];
+                bool first = true;
+                for (int k = 0; k < j; ++k) if (tgt[k] == c) { first = false; break; }
+                int nxt = kChainNone;
+                for (int k = j + 1; k < L; ++k) if (tgt[k] == c) { nxt = k; break; }
+                p.chain[(size_t)b * p.Lpad + j] = nxt | (first ? kChainFirst : 0);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // ctc_grad_lin_kernel — gradient pass for the probability-domain workspaces (ctc_scan_lin_kernel).
 //
 // A warp owns ONE sample and a strided set of its frames, so everything that depends only on the sample (labels,
@@ -1114,8 +1541,38 @@ static int launch_scan_lin(const ScanParams& sp, int ndir, cudaStream_t st) {
     ctc_scan_lin_kernel<K, TIn><<<grid, block, smem, st>>>(sp);
     return (int)cudaGetLastError();
 }
+template <int K, typename TIn>
+static int launch_scan_ws(const ScanParams& sp, int ndir, cudaStream_t st) {
+    constexpr int PW = (K + 1 + 3) & ~3;
+    constexpr int D = 2 * kWsGroup * kWsGroups;
+    dim3 grid(sp.B, ndir), block(128);
+    const int row_stride = (int)(((size_t)sp.V * sizeof(TIn) + 32 + 127) & ~(size_t)127);
+    const size_t smem = (size_t)D * row_stride + sizeof(float) * 2 * kWsRing * 32 * PW + sizeof(int) * 128 +
+                        sizeof(unsigned long long) * 2 * kWsGroups;
+    if (smem > 200 * 1024) return -1000;     // rows too long for the shared-memory ring: caller falls back
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        AVCTC_CUDA_RETURN(cudaFuncSetAttribute(ctc_scan_ws_kernel<K, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               200 * 1024));
+        configured = 200 * 1024;
+    }
+    ctc_scan_ws_kernel<K, TIn><<<grid, block, smem, st>>>(sp, row_stride);
+    return (int)cudaGetLastError();
+}
 template <typename TIn>
 static int dispatch_scan_lin(const ScanParams& sp, int K, int ndir, cudaStream_t st) {
+    if (avctc_tuning_get("ctc_ws", 1) != 0 && sp.stride_t >= 0 && sp.stride_b >= 0) {
+        int rc = -1000;
+        switch (K) {
+            case 2: rc = launch_scan_ws<2, TIn>(sp, ndir, st); break;
+            case 4: rc = launch_scan_ws<4, TIn>(sp, ndir, st); break;
+            case 6: rc = launch_scan_ws<6, TIn>(sp, ndir, st); break;
+            case 8: rc = launch_scan_ws<8, TIn>(sp, ndir, st); break;
+            case 12: rc = launch_scan_ws<12, TIn>(sp, ndir, st); break;
+            case 16: rc = launch_scan_ws<16, TIn>(sp, ndir, st); break;
+        }
+        if (rc != -1000) return rc;
+    }
     switch (K) {
         case 2: return launch_scan_lin<2, TIn>(sp, ndir, st);
         case 4: return launch_scan_lin<4, TIn>(sp, ndir, st);
