@@ -58,7 +58,7 @@ class GemmOperand(ctypes.Structure):
 
 
 # kernels launched by each entry point (bench.py reports "gpu_launches" from this table)
-KERNELS = {"avctc_ctc_forward": 1, "avctc_ctc_reduce": 1, "avctc_ctc_backward": 1, "avctc_beam_search": 1,
+KERNELS = {"avctc_ctc_forward": 1, "avctc_ctc_reduce": 1, "avctc_ctc_backward": 1, "avctc_beam_search": 2,
            "avctc_gemm_bf16": 1, "avctc_resample_forward": 2, "avctc_resample_backward": 1, "avctc_softmax_forward": 1,
            "avctc_softmax_backward": 1, "avctc_colsum": 1, "avctc_log_softmax_forward": 1,
            "avctc_log_softmax_backward": 1, "avctc_infonce_forward": 4, "avctc_infonce_backward": 2}

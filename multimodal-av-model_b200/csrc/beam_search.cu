@@ -39,6 +39,8 @@ struct BeamParams {
     int row_floats;        // smem floats per staged row
     int n_enum;            // number of (b,j) candidate pairs
     int use_nth;           // k*64 > V: torch.topk's nth_element + sort route for tied rows
+    float* tk_val;         // [N][T][beam] per-frame top-k values (two-phase path)
+    int32_t* tk_idx;       // [N][T][beam] per-frame top-k indices
 };
 
 __device__ __forceinline__ bool ranks_before(float x, float y) {  // TopKImpl.h:56-58
@@ -425,6 +427,214 @@ __global__ void __launch_bounds__(32) beam_search_kernel(const BeamParams p) {
     if (lane == 0) p.out_len[n] = count;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Two-phase decode (default): the per-frame torch.topk does not depend on the beam state, so it runs for ALL
+// N*T rows at once, HBM-bound (phase 1: one warp per row, the row lives in registers); the beam recurrence then
+// only touches the [N,T,beam] top-k lists (phase 2: one warp per utterance, fp64 scores, back-pointers).
+// Algorithmic traffic: one read of log_probs (T*V*4 bytes per utterance).
+constexpr int kTopkWarps = 8;
+
+__device__ __forceinline__ unsigned f2key(float v) {       // order-preserving float -> uint (no NaNs here)
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kTopkWarps * 32) beam_topk_kernel(const BeamParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = p.beam;
+    // per-warp scratch: candidates, sorted top-(k+1), and (slow path only) a staged row + index queue
+    const size_t per_warp = (size_t)kCandMax * 8 + (size_t)(kBeamMax + 1) * 8 +
+                            (size_t)p.row_floats * 4 * (p.use_nth ? 2 : 1);
+    unsigned char* mine = smem_raw + (size_t)warp * per_warp;
+    float* cv = reinterpret_cast<float*>(mine);
+    int* ci = reinterpret_cast<int*>(cv + kCandMax);
+    float* tv = reinterpret_cast<float*>(ci + kCandMax);
+    int* ti = reinterpret_cast<int*>(tv + kBeamMax + 1);
+    float* srow = reinterpret_cast<float*>(ti + kBeamMax + 1);
+    int* qi = reinterpret_cast<int*>(srow + p.row_floats);
+    const long long rows = (long long)p.N * p.T;
+    for (long long r = (long long)blockIdx.x * kTopkWarps + warp; r < rows; r += (long long)gridDim.x * kTopkWarps) {
+        const int n = (int)(r / p.T), t = (int)(r % p.T);
+        if (p.lengths) {
+            const long long fl = p.lengths[n];
+            if (t >= fl) continue;
+        }
+        const float* row = p.lp + (int64_t)n * p.stride_n + (int64_t)t * p.stride_t;
+        float x[NV];
+        bool bad = false;
+        float ml = AVCTC_NEG_INF;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = lane + 32 * j;
+            x[j] = (c < p.V) ? __ldcs(row + c) : AVCTC_NEG_INF;
+            bad |= (x[j] != x[j]);
+            ml = fmaxf(ml, x[j]);
+        }
+        bool ok = p.fast && (k + 1 <= 32) && (p.V >= k + 1) && !__any_sync(kFullMask, bad);
+        if (ok) {
+            // (k+1)-th largest lane maximum = lower bound of the (k+1)-th largest element
+            unsigned key = f2key(ml), m = 0;
+            for (int i = 0; i <= k; ++i) {
+                m = __reduce_max_sync(kFullMask, key);
+                const unsigned who = __ballot_sync(kFullMask, key == m);
+                if (lane == __ffs(who) - 1) key = 0u;
+            }
+            // everything >= tau, in (slot, lane) order
+            int count = 0;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const bool take = (lane + 32 * j < p.V) && (f2key(x[j]) >= m);
+                const unsigned bm = __ballot_sync(kFullMask, take);
+                if (bm) {
+                    const int pos = count + __popc(bm & ((1u << lane) - 1));
+                    if (take && pos < kCandMax) { cv[pos] = x[j]; ci[pos] = lane + 32 * j; }
+                    count += __popc(bm);
+                }
+            }
+            ok = (count <= kCandMax) && (count >= k + 1);
+            if (ok) {
+                __syncwarp();
+                for (int i = lane; i < count; i += 32) {        // rank: value desc, index asc; keep ranks 0..k
+                    const float v = cv[i]; const int idx = ci[i];
+                    int rk = 0;
+                    for (int j = 0; j < count; ++j) {
+                        const float o = cv[j];
+                        rk += (o > v) || (o == v && ci[j] < idx);
+                    }
+                    if (rk <= k) { tv[rk] = v; ti[rk] = idx; }
+                }
+                __syncwarp();
+                const bool tie = (lane < k) && (tv[lane] == tv[lane + 1]);
+                ok = !__any_sync(kFullMask, tie);      // k+1 distinct values: the top-k is unique, any algorithm agrees
+            }
+        }
+        if (!ok) {     // ties / NaNs: literal libstdc++ order on a staged copy of the row
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < NV; ++j) { const int c = lane + 32 * j; if (c < p.V) srow[c] = x[j]; }
+            __syncwarp();
+            if (p.use_nth) topk_nth_exact(srow, qi, p.V, k, tv, ti, lane);
+            else topk_exact(srow, p.V, k, tv, ti, lane);
+        }
+        __syncwarp();
+        if (lane < k) {
+            p.tk_val[(size_t)r * k + lane] = tv[lane];
+            p.tk_idx[(size_t)r * k + lane] = ti[lane];
+        }
+        __syncwarp();
+    }
+}
+
+// phase 2: beam recurrence over the top-k lists; one warp per utterance, kRecurWarps utterances per CTA
+constexpr int kRecurWarps = 4;
+
+__global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const BeamParams p, const int per_warp_bytes,
+                                                                      const int bp_in_smem) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.x * kRecurWarps + warp;
+    if (n >= p.N) return;
+    const int k = p.beam;
+    unsigned char* mine = smem_raw + (size_t)warp * per_warp_bytes;
+    double* score = reinterpret_cast<double*>(mine);                        // 2 * kBeamMax
+    double* cand_s = score + 2 * kBeamMax;                                  // n_enum
+    unsigned char* en_b = reinterpret_cast<unsigned char*>(cand_s + p.n_enum);
+    unsigned char* en_j = en_b + p.n_enum;
+    uint32_t* bp_s = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(en_j + p.n_enum) + 15) & ~(uintptr_t)15);
+
+    long long fl = p.lengths ? p.lengths[n] : p.T;
+    const int frames = (int)(fl < 0 ? 0 : (fl > p.T ? p.T : fl));
+    uint32_t* bp = bp_in_smem ? bp_s : p.bp_global + (size_t)n * p.T * k;
+    int32_t* path = p.path_ws + (size_t)n * p.T;
+    if (lane == 0) {
+        int m = 0;
+        for (int b = 0; b < k; ++b)
+            for (int j = 0; j < k; ++j)
+                if ((b + 1) * (j + 1) <= k) { en_b[m] = (unsigned char)b; en_j[m] = (unsigned char)j; ++m; }
+        score[0] = 0.0;
+    }
+    __syncwarp();
+    int nb = 1, cur = 0;
+    const float* tvp = p.tk_val + (size_t)n * p.T * k;
+    const int32_t* tip = p.tk_idx + (size_t)n * p.T * k;
+    float tv_n = 0.f; int ti_n = 0;
+    if (frames > 0 && lane < k) { tv_n = tvp[lane]; ti_n = tip[lane]; }
+    for (int t = 0; t < frames; ++t) {
+        const float tvv = tv_n; const int tii = ti_n;
+        if (t + 1 < frames && lane < k) { tv_n = tvp[(size_t)(t + 1) * k + lane]; ti_n = tip[(size_t)(t + 1) * k + lane]; }
+        int M = 0;
+        for (int m0 = 0; m0 < p.n_enum; m0 += 32) {
+            const int m = m0 + lane;
+            const bool in = (m < p.n_enum) && (en_b[m] < nb);
+            M += __popc(__ballot_sync(kFullMask, in));
+        }
+        const double* sc = score + cur * kBeamMax;
+        double* sn = score + (cur ^ 1) * kBeamMax;
+        for (int m0 = 0; m0 < M; m0 += 32) {
+            const int m = m0 + lane;
+            const int jj = (m < M) ? en_j[m] : 0;
+            const float lpv = __shfl_sync(kFullMask, tvv, jj);
+            if (m < M) cand_s[m] = sc[en_b[m]] + (double)lpv;
+        }
+        __syncwarp();
+        const int keep = min(k, M);
+        for (int m0 = 0; m0 < M; m0 += 32) {
+            const int m = m0 + lane;
+            const int jj = (m < M) ? en_j[m] : 0;
+            const int tok = __shfl_sync(kFullMask, tii, jj);
+            if (m < M) {
+                const double s = cand_s[m];
+                int r = 0;
+                for (int q = 0; q < M; ++q) {
+                    const double o = cand_s[q];
+                    r += (o > s) || (o == s && q < m);
+                }
+                if (r < keep) {
+                    sn[r] = s;
+                    bp[(size_t)t * k + r] = ((uint32_t)en_b[m] << 24) | (uint32_t)tok;
+                }
+            }
+        }
+        __syncwarp();
+        cur ^= 1;
+        nb = keep;
+    }
+    if (frames > 0) {
+        const bool dbg = (p.dbg_paths != nullptr);
+        if (lane == 0 || (dbg && lane < nb)) {
+            int32_t* dst = dbg ? p.dbg_paths + ((size_t)n * k + lane) * p.T : path;
+            int idx = lane;
+            for (int t = frames - 1; t >= 0; --t) {
+                const uint32_t e = bp[(size_t)t * k + idx];
+                dst[t] = (int32_t)(e & 0xffffffu);
+                idx = (int)(e >> 24);
+            }
+            if (dbg && lane == 0)
+                for (int t = 0; t < frames; ++t) path[t] = dst[t];
+        }
+        if (p.dbg_scores && lane < nb) p.dbg_scores[(size_t)n * k + lane] = score[cur * kBeamMax + lane];
+    }
+    __syncwarp();
+    __threadfence_block();
+    int count = 0;
+    int32_t* out = p.out_ids + (size_t)n * p.T;
+    for (int t0 = 0; t0 < frames; t0 += 32) {
+        const int t = t0 + lane;
+        bool keepit = false;
+        int c = 0;
+        if (t < frames) {
+            c = path[t];
+            keepit = (c != p.blank) && (t == 0 || path[t - 1] != c);
+        }
+        const unsigned m = __ballot_sync(kFullMask, keepit);
+        if (keepit) out[count + __popc(m & ((1u << lane) - 1))] = c;
+        count += __popc(m);
+    }
+    if (lane == 0) p.out_len[n] = count;
+}
+
 static int enum_count(int k) {
     int m = 0;
     for (int b = 0; b < k; ++b)
@@ -433,7 +643,8 @@ static int enum_count(int k) {
     return m;
 }
 
-struct BeamPlan { size_t off_bp, off_path, off_status, total; bool bp_in_smem; size_t smem; int row_floats, n_enum, use_nth; };
+struct BeamPlan { size_t off_bp, off_path, off_status, off_tv, off_ti, total; bool bp_in_smem; size_t smem; int row_floats, n_enum, use_nth;
+                  bool two_phase; size_t smem_topk, smem_recur_per_warp; bool bp_in_smem2; };
 
 static bool beam_plan(int N, int T, int V, int beam, BeamPlan* pl) {
     if (beam < 1 || beam > kBeamMax || beam > V) return false;
@@ -450,7 +661,17 @@ static bool beam_plan(int N, int T, int V, int beam, BeamPlan* pl) {
     size_t o = 0;
     pl->off_status = o; o += 256;
     pl->off_path = o; o = (o + (size_t)N * (T > 0 ? T : 1) * 4 + 255) / 256 * 256;
-    pl->off_bp = o; if (!pl->bp_in_smem) o = (o + (size_t)N * bp_bytes + 255) / 256 * 256;
+    // two-phase path: rows of up to 1024 classes live in registers (32 per lane)
+    pl->two_phase = (V <= 1024) && (avctc_tuning_get("beam_two_phase", 1) != 0);
+    pl->smem_topk = (size_t)kTopkWarps * ((size_t)kCandMax * 8 + (size_t)(kBeamMax + 1) * 8 +
+                                          (size_t)pl->row_floats * 4 * (pl->use_nth ? 2 : 1));
+    const size_t recur_fixed = 2 * kBeamMax * 8 + (size_t)pl->n_enum * 8 + 2 * (size_t)pl->n_enum + 16;
+    pl->bp_in_smem2 = bp_bytes <= (size_t)kBpSmemBytes / 2;
+    pl->smem_recur_per_warp = (recur_fixed + (pl->bp_in_smem2 ? bp_bytes : 0) + 15) / 16 * 16;
+    const bool need_bp_global = pl->two_phase ? !pl->bp_in_smem2 : !pl->bp_in_smem;
+    pl->off_bp = o; if (need_bp_global) o = (o + (size_t)N * bp_bytes + 255) / 256 * 256;
+    pl->off_tv = o; if (pl->two_phase) o = (o + (size_t)N * (T > 0 ? T : 1) * beam * 4 + 255) / 256 * 256;
+    pl->off_ti = o; if (pl->two_phase) o = (o + (size_t)N * (T > 0 ? T : 1) * beam * 4 + 255) / 256 * 256;
     pl->total = o;
     return true;
 }
@@ -489,7 +710,48 @@ extern "C" int avctc_beam_search(const float* log_probs, int64_t stride_n, int64
     bp.path_ws = reinterpret_cast<int32_t*>(w + pl.off_path);
     bp.status = reinterpret_cast<int*>(w + pl.off_status);
     bp.row_floats = pl.row_floats; bp.n_enum = pl.n_enum; bp.use_nth = pl.use_nth;
+    bp.tk_val = nullptr; bp.tk_idx = nullptr;
     AVCTC_CUDA_RETURN(cudaMemsetAsync(bp.status, 0, sizeof(int), st));
+    if (pl.two_phase) {
+        if (T == 0) { AVCTC_CUDA_RETURN(cudaMemsetAsync(out_len, 0, sizeof(int32_t) * N, st)); return AVCTC_OK; }
+        bp.tk_val = reinterpret_cast<float*>(w + pl.off_tv);
+        bp.tk_idx = reinterpret_cast<int32_t*>(w + pl.off_ti);
+        bp.bp_global = pl.bp_in_smem2 ? nullptr : reinterpret_cast<uint32_t*>(w + pl.off_bp);
+        const int need = (V + 31) / 32;
+        const long long rows = (long long)N * T;
+        long long blocks = (rows + kTopkWarps - 1) / kTopkWarps;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+#define AVCTC_TOPK(NV)                                                                                              \
+    do {                                                                                                            \
+        static bool cfg = false;                                                                                    \
+        if (!cfg && pl.smem_topk > 48 * 1024) {                                                                     \
+            AVCTC_CUDA_RETURN(cudaFuncSetAttribute(beam_topk_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                   200 * 1024));                                                    \
+            cfg = true;                                                                                             \
+        }                                                                                                           \
+        beam_topk_kernel<NV><<<(unsigned)blocks, kTopkWarps * 32, pl.smem_topk, st>>>(bp);                          \
+    } while (0)
+        if (need <= 4) AVCTC_TOPK(4);
+        else if (need <= 8) AVCTC_TOPK(8);
+        else if (need <= 16) AVCTC_TOPK(16);
+        else if (need <= 25) AVCTC_TOPK(25);
+        else if (need <= 26) AVCTC_TOPK(26);
+        else AVCTC_TOPK(32);
+#undef AVCTC_TOPK
+        AVCTC_CUDA_RETURN(cudaGetLastError());
+        const size_t smem2 = pl.smem_recur_per_warp * kRecurWarps;
+        static bool cfg2 = false;
+        if (!cfg2 && smem2 > 48 * 1024) {
+            AVCTC_CUDA_RETURN(cudaFuncSetAttribute(beam_recur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            cfg2 = true;
+        }
+        beam_recur_kernel<<<(N + kRecurWarps - 1) / kRecurWarps, kRecurWarps * 32, smem2, st>>>(
+            bp, (int)pl.smem_recur_per_warp, pl.bp_in_smem2 ? 1 : 0);
+        return (int)cudaGetLastError();
+    }
     static size_t configured = 0;
     if (pl.smem > 48 * 1024 && pl.smem > configured) {
         AVCTC_CUDA_RETURN(cudaFuncSetAttribute(beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
