@@ -259,23 +259,41 @@ def bench_ctc(device, iters=10, Ts=(250, 1000)):
 
 
 def bench_beam(device, rank, world, iters=5, N=4096, T=150, beam=10):
-    """BASELINE config 5: N utterances sharded contiguously over ranks, no collective."""
+    """BASELINE config 5: N utterances sharded contiguously over ranks, no collective.
+    ms = the two decode kernels through the C ABI (log-probs resident in HBM, ids left on the device);
+    e2e = beam_search_batch() from pinned host log-probs to Python token lists."""
     import multimodal_av_model_b200 as pkg
-    from multimodal_av_model_b200 import ddp
+    from multimodal_av_model_b200 import _lib, ddp
     lo, hi = ddp.shard_range(N, rank, world)
     g = torch.Generator().manual_seed(7 + rank)
     n = hi - lo
     lp_host = (3 * torch.randn(n, T, VOCAB, generator=g)).log_softmax(-1).pin_memory()
     lp = lp_host.to(device)
     flush = l2_flusher(device)
-    t_k, _ = event_time(lambda: pkg.beam_search_batch(lp, beam_width=beam, blank=BLANK), iters, 2, flush, device)
+    L = _lib.lib()
+    st = torch.cuda.current_stream(device).cuda_stream
+    wsb = int(L.avctc_beam_workspace_bytes(n, T, VOCAB, beam))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=device)
+    out = torch.empty((n, T), dtype=torch.int32, device=device)
+    ol = torch.empty(n, dtype=torch.int32, device=device)
+
+    def kernels():
+        _lib.check(L.avctc_beam_search(lp.data_ptr(), lp.stride(0), lp.stride(1), n, T, VOCAB, None, beam, BLANK,
+                                       out.data_ptr(), ol.data_ptr(), None, None, ws.data_ptr(), wsb, st), "beam")
+    t_k, _ = event_time(kernels, iters, 2, flush, device)
+    for _ in range(1):
+        pkg.beam_search_batch(lp_host.to(device, non_blocking=True), beam_width=beam, blank=BLANK)
+    torch.cuda.synchronize(device)
     t0 = time.perf_counter()
     for _ in range(2):
         pkg.beam_search_batch(lp_host.to(device, non_blocking=True), beam_width=beam, blank=BLANK)
     t_e2e = (time.perf_counter() - t0) / 2 * 1e3
     return dict(utterances=N, shard=n, beam=beam, ms=t_k, utt_per_s_shard=n / t_k * 1e3, e2e_ms=t_e2e,
                 e2e_utt_per_s_shard=n / t_e2e * 1e3, gbs=n * T * VOCAB * 4 / t_k / 1e6,
-                note="ms includes the D2H of token ids and Python list construction; e2e adds the H2D of log-probs")
+                hbm_frac=n * T * VOCAB * 4 / t_k / 1e6 / measured_peaks()["hbm"],
+                algorithmic_bytes=n * T * VOCAB * 4,
+                note="ms = decode kernels only (log-probs resident, ids left on device); e2e = H2D of log-probs from pinned "
+                     "memory + kernels + D2H of ids + Python list construction")
 
 
 def bench_fusion(device, peaks, iters=10):
@@ -430,6 +448,11 @@ def main():
         line["fusion"] = fusion
     if args.workload != "train":
         line["metric"] = {"ctc": "ctc_fwd_bwd_gbs", "beam": "beam_decode_utt_per_s", "fusion": "fusion_tensor_frac"}[args.workload]
+        line["unit"] = {"ctc": "GB/s", "beam": "utt/s", "fusion": "fraction of bf16 tensor peak"}[args.workload]
+        line["config"] = {"workload": {"ctc": "config2: CTC fwd+bwd micro-benchmark B=64 T=250/1000 V=801 L in [10,80] fp32",
+                                       "beam": "config5: beam-10 decode of 4096 x [150,800] log-prob utterances",
+                                       "fusion": "config3: fusion projections + cross attention fwd/bwd bf16 B=32 T_v=150 T_a=249"}[args.workload],
+                          "l2": "256 MB write between timed iterations flushes L2"}
         line["value"] = {"ctc": lambda: ctc["T1000"]["gbs"], "beam": lambda: beam["utt_per_s"], "fusion": lambda: fusion["tensor_frac_fwd_bwd"]}[args.workload]()
     if rank == 0 and world == 1 and args.workload == "train" and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

@@ -164,6 +164,30 @@ AVCTC_API int avctc_log_softmax_backward(const void* Y, const void* dY, int dtyp
                                long long ldx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused fusion path — CrossAttentionFusion.forward up to and including fusion_proj, and its backward,
+ *   /root/reference/model/fusion_module.py:40-63 (resample, visual_proj, audio_proj, cross_attn_audio, fusion_proj)
+ * as ONE host call each: the call enqueues the weight casts, the resample, the tcgen05 GEMMs, the softmax and the bias
+ * column sums on `stream`.  Requires fused_dim/num_heads to be a multiple of 64 and Dv, Da multiples of 8.
+ * visual: bf16 [B*T,Dv]; audio: fp32/bf16 [B,Ta,Da]; mask int64 [B,Ta]; weights and biases are the fp32 nn.Module
+ * parameters (w_in/b_in = MultiheadAttention.in_proj_weight/bias [3E,E]/[3E]).  out: fp32 [B*T,E].
+ * `saved` (which=0 bytes) carries the bf16 weights and activations from forward to backward; `scratch` (which=1 for
+ * forward, which=2 for backward) is free after the call's kernels ran.  backward writes fp32 parameter gradients and,
+ * when the pointers are non-NULL, d_visual (bf16 [B*T,Dv]) and d_audio ([B,Ta,Da], fp32 or bf16).
+ * ---------------------------------------------------------------------------------------------- */
+AVCTC_API size_t avctc_fusion_workspace_bytes(int B, int T, int Ta, int Dv, int Da, int E, int H, int which);
+AVCTC_API int avctc_fusion_forward(const void* visual_bf16, const void* audio, int audio_dtype, const int64_t* mask,
+                         const float* w_vp, const float* b_vp, const float* w_ap, const float* b_ap,
+                         const float* w_in, const float* b_in, const float* w_o, const float* b_o,
+                         const float* w_f, const float* b_f, int B, int T, int Ta, int Dv, int Da, int E, int H,
+                         float* out, int64_t* mask_out, int64_t* input_lengths, void* saved, size_t saved_bytes,
+                         void* scratch, size_t scratch_bytes, void* stream);
+AVCTC_API int avctc_fusion_backward(const void* df, int df_dtype, const void* visual_bf16, int B, int T, int Ta, int Dv,
+                          int Da, int E, int H, float* g_wvp, float* g_bvp, float* g_wap, float* g_bap,
+                          float* g_win, float* g_bin, float* g_wo, float* g_bo, float* g_wf, float* g_bf,
+                          void* d_visual_bf16, void* d_audio, int d_audio_dtype, const void* saved,
+                          size_t saved_bytes, void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * InfoNCE — replaces contrastive_loss_with_mask after its optional projection
  *   /root/reference/contrastive.py:13-44 (valid-row select, F.normalize, index sets, sim/TEMPERATURE,
  *   -log_softmax(.).mean() for (weak,strong) * w_pos and (weak,neg) * w_neg), called at model/trainer.py:108-109.

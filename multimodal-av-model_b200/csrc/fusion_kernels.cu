@@ -135,15 +135,26 @@ __global__ void resample_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int 
     } else if (Tp == Tv) {
         t_lo = t_hi = r;
     }
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        float acc = 0.f;
-        for (int t = t_lo; t <= t_hi; ++t) {
+    // the few (frame, weight) pairs that touch padded index r, found once per CTA
+    __shared__ int st_t[8];
+    __shared__ float st_w[8];
+    __shared__ int st_n;
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int t = t_lo; t <= t_hi && n < 8; ++t) {
             const LerpCoef c = lerp_coef(t, Tp, Tv);
             float w = 0.f;
             if (c.i0 == r) w += c.w0;
             if (c.i1 == r && c.w1 != 0.f) w += c.w1;
-            if (w != 0.f) acc += w * __bfloat162float(dout[((size_t)b * Tv + t) * D + d]);
+            if (w != 0.f) { st_t[n] = t; st_w[n] = w; ++n; }
         }
+        st_n = n;
+    }
+    __syncthreads();
+    const int n = st_n;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.f;
+        for (int i = 0; i < n; ++i) acc += st_w[i] * __bfloat162float(dout[((size_t)b * Tv + st_t[i]) * D + d]);
         put(drow + d, acc);
     }
 }
@@ -183,23 +194,25 @@ __global__ void softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, const fl
 }
 
 // ------------------------------------------------------------------------------------------ colsum
-// out[n] (+)= sum_m X[m][n]; block = 32 columns x 8 row-lanes
+// out[n] (+)= sum_m X[m][n]; block = 32 columns x 8 row-lanes over one of gridDim.y row chunks; chunk sums are
+// added with fp32 atomics into an `out` the host zeroed (the sum order of the <= 64 chunk totals is not fixed).
 template <typename TIn>
-__global__ void colsum_kernel(const TIn* __restrict__ X, long long M, int N, long long ld, float* __restrict__ out,
-                              int accumulate) {
+__global__ void colsum_kernel(const TIn* __restrict__ X, long long M, int N, long long ld, float* __restrict__ out) {
     __shared__ float part[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + tx;
+    const long long per = (M + gridDim.y - 1) / gridDim.y;
+    const long long m0 = (long long)blockIdx.y * per, m1 = (m0 + per < M) ? m0 + per : M;
     float acc = 0.f;
     if (n < N)
-        for (long long m = ty; m < M; m += 8) acc += to_float(X[m * ld + n]);
+        for (long long m = m0 + ty; m < m1; m += 8) acc += to_float(X[m * ld + n]);
     part[ty][tx] = acc;
     __syncthreads();
     if (ty == 0 && n < N) {
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += part[i][tx];
-        out[n] = accumulate ? out[n] + s : s;
+        atomicAdd(out + n, s);
     }
 }
 
@@ -312,10 +325,13 @@ extern "C" int avctc_colsum(const void* X, int dtype, long long M, int N, long l
                             void* stream) {
     if (!X || !out || M <= 0 || N <= 0) return AVCTC_ERR_BAD_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const unsigned grid = (N + 31) / 32;
-    if (dtype == AVCTC_F32) colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(X), M, N, ld, out, accumulate);
+    int chunks = (int)((M + 127) / 128);
+    if (chunks > 64) chunks = 64;
+    const dim3 grid((N + 31) / 32, chunks);
+    if (!accumulate) AVCTC_CUDA_RETURN(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st));
+    if (dtype == AVCTC_F32) colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(X), M, N, ld, out);
     else if (dtype == AVCTC_BF16)
-        colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(X), M, N, ld, out, accumulate);
+        colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(X), M, N, ld, out);
     else return AVCTC_ERR_BAD_ARG;
     return (int)cudaGetLastError();
 }

@@ -20,10 +20,11 @@
 
 namespace avctc {
 
-constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 4, kUmmaK = 16;
+constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 3, kUmmaK = 16;   // 3 stages = 96 KiB: two CTAs per SM
 constexpr int kGemmThreads = 192;
 constexpr int kTileBytes = kBM * kBK * 2;           // 16 KiB per operand per stage
 constexpr int kTmemCols = 128;
+constexpr int kStgLd = kBN + 4;                     // fp32 staging tile row stride (bank-conflict-free float4 rows)
 
 struct OperandSpec {      // where batch z's slice starts, in elements of the TMA tensor
     int k_outer, k_inner;   // offset along the reduction dim
@@ -39,7 +40,17 @@ struct GemmParams {
     const float* bias; int bias_mode;   // 0 none, 1 per output column (N), 2 per output row (M)
     float alpha;
     int accumulate;                      // C += result (fp32 output only)
+    int splits;                          // split-K: blockIdx.z = z * splits + s; partial sums go to C with red.add.f32
+    int dbg;                             // record phase timestamps of CTA (0,0,0) into g_gemm_dbg
 };
+
+__device__ long long g_gemm_dbg[16];
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define GEMM_DBG(slot) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_gemm_dbg[slot] = gtime(); } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -99,7 +110,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int mn_major) {
            (2ull << 61);
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -109,15 +120,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t sA = base, sB = base + kStages * kTileBytes;
     const uint32_t bars = base + 2 * kStages * kTileBytes;     // full[kStages], empty[kStages], tmem_full
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + 2 * kStages * kTileBytes + (2 * kStages + 1) * 8);
+    float* bias_s = reinterpret_cast<float*>(gen + ((2 * kStages * kTileBytes + (2 * kStages + 1) * 8 + 16 + 15) & ~15));   // [kBN]
     auto full = [&](int s) { return bars + 8u * s; };
     auto empty = [&](int s) { return bars + 8u * (kStages + s); };
     const uint32_t tmem_full = bars + 8u * 2 * kStages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN, z = blockIdx.z;
+    if (threadIdx.x == 0) GEMM_DBG(0);
+    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
+    const int z = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
     const int zo = z / p.inner_count, zi = z % p.inner_count;
-    const int num_kb = (p.K + kBK - 1) / kBK;
+    const int total_kb = (p.K + kBK - 1) / kBK;
+    const int kb_per = (total_kb + p.splits - 1) / p.splits;
+    const int kb0 = split * kb_per;
+    const int num_kb = max(0, min(total_kb, kb0 + kb_per) - kb0);   // this CTA's share of the reduction
 
+    if (threadIdx.x >= 64) {      // per-column bias of this N tile (zero when absent / not the leading split)
+        const int i = threadIdx.x - 64;
+        bias_s[i] = (split == 0 && p.bias_mode == 1 && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
         mbar_init(tmem_full, 1);
@@ -133,6 +154,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    if (threadIdx.x == 0) GEMM_DBG(1);
 
     if (warp == 0) {
         if (lane == 0) {   // ===== TMA producer =====
@@ -145,17 +167,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 mbar_wait(empty(s), ((kb / kStages) & 1) ^ 1);
                 mbar_expect_tx(full(s), 2 * kTileBytes);
                 const uint32_t da = sA + s * kTileBytes, db = sB + s * kTileBytes;
+                const int ko = (kb0 + kb) * kBK;
                 if (p.a.mn_major) {   // tensor dims {rows, K, z}: two 64-wide row blocks of 64 k-rows each
-                    tma_load_3d(da, &map_a, full(s), ar, ak + kb * kBK, az);
-                    tma_load_3d(da + kTileBytes / 2, &map_a, full(s), ar + 64, ak + kb * kBK, az);
+                    tma_load_3d(da, &map_a, full(s), ar, ak + ko, az);
+                    tma_load_3d(da + kTileBytes / 2, &map_a, full(s), ar + 64, ak + ko, az);
                 } else {              // tensor dims {K, rows, z}
-                    tma_load_3d(da, &map_a, full(s), ak + kb * kBK, ar, az);
+                    tma_load_3d(da, &map_a, full(s), ak + ko, ar, az);
                 }
                 if (p.b.mn_major) {
-                    tma_load_3d(db, &map_b, full(s), br, bk + kb * kBK, bz);
-                    tma_load_3d(db + kTileBytes / 2, &map_b, full(s), br + 64, bk + kb * kBK, bz);
+                    tma_load_3d(db, &map_b, full(s), br, bk + ko, bz);
+                    tma_load_3d(db + kTileBytes / 2, &map_b, full(s), br + 64, bk + ko, bz);
                 } else {
-                    tma_load_3d(db, &map_b, full(s), bk + kb * kBK, br, bz);
+                    tma_load_3d(db, &map_b, full(s), bk + ko, br, bz);
                 }
             }
         }
@@ -171,6 +194,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kStages;
                 mbar_wait(full(s), (kb / kStages) & 1);
+                if (kb == 0) GEMM_DBG(2);
+                if (kb == num_kb - 1) GEMM_DBG(3);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t adesc = make_desc(sA + s * kTileBytes, p.a.mn_major);
                 const uint64_t bdesc = make_desc(sB + s * kTileBytes, p.b.mn_major);
@@ -183,57 +208,96 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             umma_commit(tmem_full);               // accumulator complete
         }
         __syncwarp();
-    } else {               // ===== epilogue: TMEM -> registers -> global =====
+    } else {               // ===== epilogue: TMEM -> registers -> shared staging -> coalesced global =====
         mbar_wait(tmem_full, 0);
+        if (threadIdx.x == 64) GEMM_DBG(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                   // a warp may only touch TMEM lanes [32q, 32q+32)
-        const int row = m0 + q * 32 + lane;
+        const int r_loc = q * 32 + lane;
+        const int row = m0 + r_loc;
         const long long coff = (long long)zo * p.c_outer + (long long)zi * p.c_inner;
-        const float rb = (p.bias_mode == 2 && row < p.M) ? p.bias[row] : 0.f;
+        const bool lead = (split == 0);           // only one split adds the bias
+        const float rb = (lead && p.bias_mode == 2 && row < p.M) ? p.bias[row] : 0.f;
+        // every MMA has retired (tmem_full), so the operand stages are free: reuse them as a [128][kStgLd] fp32 tile
+        float* stg = reinterpret_cast<float*>(gen);
+        if (num_kb > 0) {
 #pragma unroll 1
-        for (int c = 0; c < kBN / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int col0 = n0 + c * 32;
-            if (row < p.M && col0 < p.N) {
-                float f[32];
+            for (int c = 0; c < kBN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float* srow = stg + r_loc * kStgLd + c * 32;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]) * p.alpha + rb;
-                    if (p.bias_mode == 1 && col0 + j < p.N) x += p.bias[col0 + j];
-                    f[j] = x;
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
+                    float4 o;
+                    o.x = fmaf(__uint_as_float(v[j]), p.alpha, rb + b4.x);
+                    o.y = fmaf(__uint_as_float(v[j + 1]), p.alpha, rb + b4.y);
+                    o.z = fmaf(__uint_as_float(v[j + 2]), p.alpha, rb + b4.z);
+                    o.w = fmaf(__uint_as_float(v[j + 3]), p.alpha, rb + b4.w);
+                    *reinterpret_cast<float4*>(srow + j) = o;
                 }
-                const bool fullchunk = (col0 + 32 <= p.N);
-                if (p.out_dtype == AVCTC_F32) {
-                    float* dst = reinterpret_cast<float*>(p.C) + coff + (long long)row * p.ldc + col0;
-                    if (fullchunk && !p.accumulate && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    } else {
-                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = p.accumulate ? dst[j] + f[j] : f[j];
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
+        if (num_kb > 0) {
+            const int te = threadIdx.x - 64;                   // 0..127
+            const int rows_valid = min(kBM, p.M - m0), cols_valid = min(kBN, p.N - n0);
+            const size_t esz = (p.out_dtype == AVCTC_F32) ? 4 : 2;
+            const long long tile_off = coff + (long long)m0 * p.ldc + n0;
+            const bool vec_ok = (cols_valid == kBN) && ((p.ldc * (long long)esz) % 16 == 0) &&
+                                (((reinterpret_cast<uintptr_t>(p.C) + (uintptr_t)tile_off * esz) & 15) == 0);
+            if (vec_ok && p.out_dtype == AVCTC_BF16) {
+                __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C) + tile_off;
+#pragma unroll 4
+                for (int i = 0; i < 16; ++i) {                 // 16 threads cover one 256-byte output row
+                    const int idx = te + 128 * i, r = idx >> 4, c8 = (idx & 15) * 8;
+                    if (r < rows_valid) {
+                        const float4 x = *reinterpret_cast<const float4*>(stg + r * kStgLd + c8);
+                        const float4 y = *reinterpret_cast<const float4*>(stg + r * kStgLd + c8 + 4);
+                        uint4 pk;
+                        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+                        h[0] = __floats2bfloat162_rn(x.x, x.y); h[1] = __floats2bfloat162_rn(x.z, x.w);
+                        h[2] = __floats2bfloat162_rn(y.x, y.y); h[3] = __floats2bfloat162_rn(y.z, y.w);
+                        *reinterpret_cast<uint4*>(Cb + (long long)r * p.ldc + c8) = pk;
                     }
-                } else {
-                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + coff + (long long)row * p.ldc + col0;
-                    if (fullchunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 pk;
-                            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-                            h[0] = __floats2bfloat162_rn(f[j], f[j + 1]); h[1] = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                            h[2] = __floats2bfloat162_rn(f[j + 4], f[j + 5]); h[3] = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                            *reinterpret_cast<uint4*>(dst + j) = pk;
+                }
+            } else if (vec_ok) {
+                float* Cf = reinterpret_cast<float*>(p.C) + tile_off;
+#pragma unroll 4
+                for (int i = 0; i < 32; ++i) {                 // one warp covers one 512-byte output row
+                    const int idx = te + 128 * i, r = idx >> 5, c4 = (idx & 31) * 4;
+                    if (r < rows_valid) {
+                        float4 x = *reinterpret_cast<const float4*>(stg + r * kStgLd + c4);
+                        float4* dst = reinterpret_cast<float4*>(Cf + (long long)r * p.ldc + c4);
+                        if (p.splits > 1) atomicAdd(dst, x);   // split-K partial sum: C was zeroed by the host
+                        else {
+                            if (p.accumulate) { const float4 o = *dst; x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w; }
+                            *dst = x;
                         }
+                    }
+                }
+            } else {                                           // ragged tile / unaligned C: element-wise
+                for (int idx = te; idx < kBM * kBN; idx += 128) {
+                    const int r = idx / kBN, c = idx % kBN;
+                    if (r >= rows_valid || c >= cols_valid) continue;
+                    const float x = stg[r * kStgLd + c];
+                    const long long off = tile_off + (long long)r * p.ldc + c;
+                    if (p.out_dtype == AVCTC_F32) {
+                        float* dst = reinterpret_cast<float*>(p.C) + off;
+                        if (p.splits > 1) atomicAdd(dst, x);
+                        else *dst = p.accumulate ? *dst + x : x;
                     } else {
-                        for (int j = 0; j < 32 && col0 + j < p.N; ++j) dst[j] = __float2bfloat16(f[j]);
+                        reinterpret_cast<__nv_bfloat16*>(p.C)[off] = __float2bfloat16(x);
                     }
                 }
             }
         }
     }
+    if (threadIdx.x == 64) GEMM_DBG(5);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) GEMM_DBG(6);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
     }
@@ -275,11 +339,29 @@ static int make_map(CUtensorMap* m, const void* ptr, long long dim0, long long d
 
 using namespace avctc;
 
+// Internal launcher shared with fusion_path.cu.  splits > 1: split-K over blockIdx.z with fp32 red.add into a C that
+// this function zeroes first (fp32 output, no accumulate, batch C slices must be disjoint).
+int avctc_gemm_launch(const avctc_gemm_operand* a, const avctc_gemm_operand* b, int M, int N, int K, int batch,
+                      int inner_count, void* C, int out_dtype, long long ldc, long long c_outer, long long c_inner,
+                      const float* bias, int bias_mode, float alpha, int accumulate, int splits, void* stream);
+
+// debug only (not part of the public header): phase timestamps (ns) of CTA (0,0,0) of the last launch with gemm_dbg=1
+extern "C" __attribute__((visibility("default"))) int avctc_debug_gemm_timestamps(long long* host_out16) {
+    return (int)cudaMemcpyFromSymbol(host_out16, g_gemm_dbg, sizeof(long long) * 16);
+}
+
 // See include/avctc_b200.h for the argument contract.
 extern "C" int avctc_gemm_bf16(const avctc_gemm_operand* a, const avctc_gemm_operand* b, int M, int N, int K, int batch,
                                int inner_count, void* C, int out_dtype, long long ldc, long long c_outer,
                                long long c_inner, const float* bias, int bias_mode, float alpha, int accumulate,
                                void* stream) {
+    return avctc_gemm_launch(a, b, M, N, K, batch, inner_count, C, out_dtype, ldc, c_outer, c_inner, bias, bias_mode,
+                             alpha, accumulate, 1, stream);
+}
+
+int avctc_gemm_launch(const avctc_gemm_operand* a, const avctc_gemm_operand* b, int M, int N, int K, int batch,
+                      int inner_count, void* C, int out_dtype, long long ldc, long long c_outer, long long c_inner,
+                      const float* bias, int bias_mode, float alpha, int accumulate, int splits, void* stream) {
     if (!a || !b || !C || M <= 0 || N <= 0 || K <= 0 || batch <= 0 || inner_count <= 0) return AVCTC_ERR_BAD_ARG;
     if (out_dtype != AVCTC_F32 && out_dtype != AVCTC_BF16) return AVCTC_ERR_BAD_ARG;
     if (accumulate && out_dtype != AVCTC_F32) return AVCTC_ERR_BAD_ARG;
@@ -307,13 +389,27 @@ extern "C" int avctc_gemm_bf16(const avctc_gemm_operand* a, const avctc_gemm_ope
     p.M = M; p.N = N; p.K = K; p.batch = batch; p.inner_count = inner_count;
     p.C = C; p.ldc = ldc; p.c_outer = c_outer; p.c_inner = c_inner; p.out_dtype = out_dtype;
     p.bias = bias; p.bias_mode = bias_mode; p.alpha = alpha; p.accumulate = accumulate;
-    const size_t smem = 2 * kStages * kTileBytes + (2 * kStages + 1) * 8 + 16 + 1024;
+    {
+        const int total_kb = (K + kBK - 1) / kBK;
+        if (splits < 1) splits = 1;
+        if (splits > total_kb) splits = total_kb;
+        const int kb_per = (total_kb + splits - 1) / splits;
+        splits = (total_kb + kb_per - 1) / kb_per;            // every split owns at least one k-block
+        if (splits > 1) {
+            if (out_dtype != AVCTC_F32 || accumulate || batch != 1) return AVCTC_ERR_BAD_ARG;
+            AVCTC_CUDA_RETURN(cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M,
+                                                reinterpret_cast<cudaStream_t>(stream)));
+        }
+        p.splits = splits;
+        p.dbg = avctc_tuning_get("gemm_dbg", 0);
+    }
+    const size_t smem = 2 * kStages * kTileBytes + (2 * kStages + 1) * 8 + 32 + kBN * sizeof(float) + 1024;
     static bool configured = false;
     if (!configured) {
         AVCTC_CUDA_RETURN(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid((M + kBM - 1) / kBM, (N + kBN - 1) / kBN, batch);
+    dim3 grid((M + kBM - 1) / kBM, (N + kBN - 1) / kBN, batch * p.splits);
     gemm_bf16_kernel<<<grid, kGemmThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(ma, mb, p);
     return (int)cudaGetLastError();
 }

@@ -63,8 +63,9 @@ def _colsum(x, out=None):
     return out
 
 
-class _FusionCoreFn(torch.autograd.Function):
-    """resample -> visual/audio projections -> cross attention (audio queries, visual keys/values) -> fusion_proj."""
+class _FusionCoreFnPy(torch.autograd.Function):
+    """(per-kernel Python orchestration; used when a head is not a multiple of 64 columns wide)
+    resample -> visual/audio projections -> cross attention (audio queries, visual keys/values) -> fusion_proj."""
 
     @staticmethod
     def forward(ctx, visual, audio, mask, num_heads, w_vp, b_vp, w_ap, b_ap, w_in, b_in, w_o, b_o, w_f, b_f):
@@ -204,6 +205,83 @@ class _FusionCoreFn(torch.autograd.Function):
         return (d_visual, d_audio, None, None, g_wvp, g_bvp, g_wap, g_bap, g_win, g_bin, g_wo, g_bo, g_wf, g_bf)
 
 
+class _FusionCoreFn(torch.autograd.Function):
+    """Same computation through avctc_fusion_forward / avctc_fusion_backward: ONE host call enqueues every kernel of the
+    step (weight casts, resample, 6 projection GEMMs, Q.K^T, softmax, P.V forward; 21 GEMMs + glue backward)."""
+
+    @staticmethod
+    def forward(ctx, visual, audio, mask, num_heads, w_vp, b_vp, w_ap, b_ap, w_in, b_in, w_o, b_o, w_f, b_f):
+        _lib.require_cuda(visual, "visual_feat")
+        _lib.require_cuda(audio, "audio_feat")
+        if mask is None:
+            raise RuntimeError("mask is required (the reference indexes it unconditionally, fusion_module.py:44)")
+        dev = visual.device
+        B, T, Dv = visual.shape
+        _, Ta, Da = audio.shape
+        E = w_f.shape[0]
+        H = int(num_heads)
+        L = _lib.lib()
+        st = _lib.stream_ptr(dev)
+        audio_c = audio.detach()
+        if audio_c.dtype not in (torch.float32, _BF16):
+            audio_c = audio_c.float()
+        audio_c = audio_c.contiguous()
+        mask_c = mask.to(device=dev, dtype=torch.long).contiguous()
+        xv = _bf16(visual.detach().reshape(B * T, Dv)).contiguous()
+        ws = [t.detach().float().contiguous() for t in (w_vp, b_vp, w_ap, b_ap, w_in, b_in, w_o, b_o, w_f, b_f)]
+        saved_bytes = int(L.avctc_fusion_workspace_bytes(B, T, Ta, Dv, Da, E, H, 0))
+        scratch_bytes = int(L.avctc_fusion_workspace_bytes(B, T, Ta, Dv, Da, E, H, 1))
+        if saved_bytes == 0:
+            raise RuntimeError("fusion dims not supported by the fused path")
+        saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+        out = torch.empty((B, T, E), dtype=torch.float32, device=dev)
+        mask_out = torch.empty((B, T), dtype=torch.long, device=dev)
+        input_lengths = torch.empty(B, dtype=torch.long, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.avctc_fusion_forward(xv.data_ptr(), audio_c.data_ptr(), _lib.dtype_enum(audio_c), mask_c.data_ptr(),
+                                              *[t.data_ptr() for t in ws], B, T, Ta, Dv, Da, E, H, out.data_ptr(),
+                                              mask_out.data_ptr(), input_lengths.data_ptr(), saved.data_ptr(), saved_bytes,
+                                              scratch.data_ptr(), scratch_bytes, st), "avctc_fusion_forward")
+        ctx.save_for_backward(xv, saved)
+        ctx.dims = (B, T, Ta, Dv, Da, E, H, saved_bytes, audio.dtype, visual.dtype)
+        ctx.mark_non_differentiable(mask_out, input_lengths)
+        return out, mask_out, input_lengths
+
+    @staticmethod
+    def backward(ctx, df, _dm, _dl):
+        xv, saved = ctx.saved_tensors
+        B, T, Ta, Dv, Da, E, H, saved_bytes, audio_dtype, visual_dtype = ctx.dims
+        dev = df.device
+        L = _lib.lib()
+        dfc = df.detach()
+        if dfc.dtype not in (torch.float32, _BF16):
+            dfc = dfc.float()
+        dfc = dfc.contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        g = [torch.empty(shape, **f32) for shape in ((E, Dv), (E,), (E, Da), (E,), (3 * E, E), (3 * E,), (E, E), (E,), (E, E), (E,))]
+        scratch_bytes = int(L.avctc_fusion_workspace_bytes(B, T, Ta, Dv, Da, E, H, 2))
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+        d_visual = torch.empty((B, T, Dv), dtype=_BF16, device=dev) if ctx.needs_input_grad[0] else None
+        d_audio = None
+        if ctx.needs_input_grad[1]:
+            d_audio = torch.empty((B, Ta, Da), dtype=audio_dtype if audio_dtype in (torch.float32, _BF16) else torch.float32,
+                                  device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.avctc_fusion_backward(dfc.data_ptr(), _lib.dtype_enum(dfc), xv.data_ptr(), B, T, Ta, Dv, Da, E, H,
+                                               *[t.data_ptr() for t in g],
+                                               d_visual.data_ptr() if d_visual is not None else None,
+                                               d_audio.data_ptr() if d_audio is not None else None,
+                                               _lib.dtype_enum(d_audio) if d_audio is not None else 0,
+                                               saved.data_ptr(), saved_bytes, scratch.data_ptr(), scratch_bytes,
+                                               _lib.stream_ptr(dev)), "avctc_fusion_backward")
+        if d_visual is not None:
+            d_visual = d_visual.to(visual_dtype)
+        if d_audio is not None:
+            d_audio = d_audio.to(audio_dtype)
+        return (d_visual, d_audio, None, None, *g)
+
+
 class CrossAttentionFusion(nn.Module):
     def __init__(self, visual_dim, audio_dim, fused_dim, num_heads=4):
         super().__init__()
@@ -220,7 +298,11 @@ class CrossAttentionFusion(nn.Module):
     def fused_projection(self, visual_feat, audio_feat, mask):
         """Everything up to and including fusion_proj (fusion_module.py:40-63): (fused[B,T,E] fp32, mask[B,T], lengths)."""
         at = self.cross_attn_audio
-        return _FusionCoreFn.apply(visual_feat, audio_feat, mask, self.num_heads,
+        E = self.fusion_proj.weight.shape[0]
+        fused = (E % self.num_heads == 0 and (E // self.num_heads) % 64 == 0 and visual_feat.shape[-1] % 8 == 0
+                 and audio_feat.shape[-1] % 8 == 0)
+        fn = _FusionCoreFn if fused else _FusionCoreFnPy
+        return fn.apply(visual_feat, audio_feat, mask, self.num_heads,
                                    self.visual_proj.weight, self.visual_proj.bias,
                                    self.audio_proj.weight, self.audio_proj.bias,
                                    at.in_proj_weight, at.in_proj_bias, at.out_proj.weight, at.out_proj.bias,
