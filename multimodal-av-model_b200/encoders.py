@@ -123,6 +123,13 @@ class AudioEncoder(nn.Module):
             self.model.requires_grad_(False)
 
     def forward(self, x, attention_mask=None):
+        # HF marks the conv feature extractor's output as requiring grad in train mode (a gradient-checkpointing
+        # aid) unless freeze_feature_encoder() was called; the reference only sets requires_grad=False on the
+        # parameters (main.py:26-31), so autograd back-propagates through seven frozen conv layers for nothing.
+        # With every parameter frozen the flag changes no gradient that is ever used.
+        fe = getattr(self.model, "feature_extractor", None)
+        if fe is not None and getattr(fe, "_requires_grad", False) and not any(p.requires_grad for p in fe.parameters()):
+            fe._requires_grad = False
         if attention_mask is not None:
             attention_mask = attention_mask.long()
         out = self.model(input_values=x, attention_mask=attention_mask, return_dict=True)
