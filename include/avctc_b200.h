@@ -188,6 +188,25 @@ AVCTC_API int avctc_fusion_backward(const void* df, int df_dtype, const void* vi
                           size_t saved_bytes, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * temporal_model — nn.LSTM(E, E, num_layers=2, batch_first=True, bidirectional=True), zero initial state,
+ *   /root/reference/model/fusion_module.py:21-27, called at :64 over all padded frames
+ * as persistent cooperative kernels (csrc/lstm.cu).  H in {256, 512}, B <= 32, In % 8 == 0.
+ * x: bf16 [B,T,In]; params / grads: HOST arrays of 16 DEVICE fp32 pointers in nn.LSTM's flat parameter order
+ * (weight_ih_l0 [4H,In], weight_hh_l0 [4H,H], bias_ih_l0 [4H], bias_hh_l0 [4H], the same four "_reverse", then the
+ * four + four of layer 1 with In = 2H); gate order i,f,g,o.  y: bf16 [B,T,2H].  `saved` (which=0) carries weights in
+ * bf16, gates and cell states from forward to backward (written only when need_grad); scratch which=1 forward,
+ * which=2 backward.  backward: dy bf16 [B,T,2H] -> 16 parameter gradients and, if non-NULL, dx bf16 [B,T,In].
+ * The kernels use a cooperative launch (2*H/16 CTAs must be co-resident).
+ * ---------------------------------------------------------------------------------------------- */
+AVCTC_API size_t avctc_bilstm_workspace_bytes(int B, int T, int In, int H, int which);
+AVCTC_API int avctc_bilstm_forward(const void* x_bf16, int B, int T, int In, int H, const float* const* params,
+                         void* y_bf16, void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes,
+                         int need_grad, void* stream);
+AVCTC_API int avctc_bilstm_backward(const void* dy_bf16, const void* x_bf16, int B, int T, int In, int H,
+                          float* const* grads, void* dx_bf16, const void* saved, size_t saved_bytes,
+                          void* scratch, size_t scratch_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * InfoNCE — replaces contrastive_loss_with_mask after its optional projection
  *   /root/reference/contrastive.py:13-44 (valid-row select, F.normalize, index sets, sim/TEMPERATURE,
  *   -log_softmax(.).mean() for (weak,strong) * w_pos and (weak,neg) * w_neg), called at model/trainer.py:108-109.

@@ -44,6 +44,9 @@ SIGNATURES = {
     "avctc_fusion_workspace_bytes": (_sz, [_i] * 8),
     "avctc_fusion_forward": (_i, [_vp, _vp, _i, _vp] + [_vp] * 10 + [_i] * 7 + [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "avctc_fusion_backward": (_i, [_vp, _i, _vp] + [_i] * 7 + [_vp] * 10 + [_vp, _vp, _i, _vp, _sz, _vp, _sz, _vp]),
+    "avctc_bilstm_workspace_bytes": (_sz, [_i] * 5),
+    "avctc_bilstm_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp, _sz, _i, _vp]),
+    "avctc_bilstm_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "avctc_infonce_workspace_bytes": (_sz, [_i, _i]),
     "avctc_infonce_forward": (_i, [_vp, _i, ctypes.c_longlong, _vp, _i, _i, ctypes.c_float, ctypes.c_float,
                                    ctypes.c_float, _vp, _vp, _sz, _vp]),
@@ -65,7 +68,8 @@ KERNELS = {"avctc_ctc_forward": 1, "avctc_ctc_reduce": 1, "avctc_ctc_backward": 
            "avctc_gemm_bf16": 1, "avctc_resample_forward": 2, "avctc_resample_backward": 1, "avctc_softmax_forward": 1,
            "avctc_softmax_backward": 1, "avctc_colsum": 1, "avctc_log_softmax_forward": 1,
            "avctc_log_softmax_backward": 1, "avctc_infonce_forward": 4, "avctc_infonce_backward": 2,
-           "avctc_fusion_forward": 12, "avctc_fusion_backward": 29}
+           "avctc_fusion_forward": 12, "avctc_fusion_backward": 29,
+           "avctc_bilstm_forward": 7, "avctc_bilstm_backward": 20}
 launch_count = 0
 
 
@@ -129,6 +133,18 @@ def require_cuda(t, name: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor: the AV-CTC hot path has no CPU implementation "
                            "(the CPU restatement under oracle/ is test infrastructure only)")
+
+
+_PY_TUNING = {"lstm_custom": 1}
+
+
+def tuning_enabled(key: str) -> bool:
+    """Host-side switches of the Python layer (e.g. lstm_custom=0 routes temporal_model to nn.LSTM / cuDNN)."""
+    return bool(_PY_TUNING.get(key, 1))
+
+
+def set_py_tuning(key: str, value: int) -> None:
+    _PY_TUNING[key] = int(value)
 
 
 def set_tuning(key: str, value: int) -> None:

@@ -18,6 +18,8 @@ What runs where:
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 import torch.nn as nn
 
@@ -282,6 +284,58 @@ class _FusionCoreFn(torch.autograd.Function):
         return (d_visual, d_audio, None, None, *g)
 
 
+class _BiLSTMFn(torch.autograd.Function):
+    """temporal_model (2-layer bidirectional LSTM, zero initial state, all padded frames — fusion_module.py:21-27,64)
+    on the persistent sm_100a kernels of csrc/lstm.cu.  `weights` are nn.LSTM's 16 flat parameters in their own order."""
+
+    @staticmethod
+    def forward(ctx, x, *weights):
+        _lib.require_cuda(x, "lstm input")
+        dev = x.device
+        B, T, In = x.shape
+        H = weights[1].shape[1]
+        L = _lib.lib()
+        xb = _bf16(x.detach()).contiguous()
+        ws = [w.detach().float().contiguous() for w in weights]
+        need_grad = any(ctx.needs_input_grad)
+        saved_bytes = int(L.avctc_bilstm_workspace_bytes(B, T, In, H, 0))
+        scratch_bytes = int(L.avctc_bilstm_workspace_bytes(B, T, In, H, 1))
+        if saved_bytes == 0:
+            raise RuntimeError("LSTM shape not supported by the sm_100a kernels")
+        saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+        y = torch.empty((B, T, 2 * H), dtype=_BF16, device=dev)
+        ptrs = (ctypes.c_void_p * 16)(*[w.data_ptr() for w in ws])
+        with torch.cuda.device(dev):
+            _lib.check(L.avctc_bilstm_forward(xb.data_ptr(), B, T, In, H, ptrs, y.data_ptr(), saved.data_ptr(), saved_bytes,
+                                              scratch.data_ptr(), scratch_bytes, int(need_grad), _lib.stream_ptr(dev)),
+                       "avctc_bilstm_forward")
+        ctx.save_for_backward(xb, saved)
+        ctx.meta = (B, T, In, H, saved_bytes, x.dtype, [tuple(w.shape) for w in weights])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, saved = ctx.saved_tensors
+        B, T, In, H, saved_bytes, xdtype, shapes = ctx.meta
+        dev = dy.device
+        L = _lib.lib()
+        dyb = _bf16(dy.detach()).contiguous()
+        grads = [torch.empty(shp, dtype=torch.float32, device=dev) for shp in shapes]
+        scratch_bytes = int(L.avctc_bilstm_workspace_bytes(B, T, In, H, 2))
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+        dx = torch.empty((B, T, In), dtype=_BF16, device=dev) if ctx.needs_input_grad[0] else None
+        ptrs = (ctypes.c_void_p * 16)(*[g.data_ptr() for g in grads])
+        with torch.cuda.device(dev):
+            _lib.check(L.avctc_bilstm_backward(dyb.data_ptr(), xb.data_ptr(), B, T, In, H, ptrs,
+                                               dx.data_ptr() if dx is not None else None, saved.data_ptr(), saved_bytes,
+                                               scratch.data_ptr(), scratch_bytes, _lib.stream_ptr(dev)),
+                       "avctc_bilstm_backward")
+        if dx is not None:
+            dx = dx.to(xdtype)
+        return (dx, *grads)
+
+
 class CrossAttentionFusion(nn.Module):
     def __init__(self, visual_dim, audio_dim, fused_dim, num_heads=4):
         super().__init__()
@@ -310,5 +364,18 @@ class CrossAttentionFusion(nn.Module):
 
     def forward(self, visual_feat, audio_feat, mask=None):
         fused, _mask_rs, input_lengths = self.fused_projection(visual_feat, audio_feat, mask)
-        fused_seq, _ = self.temporal_model(fused)          # cuDNN BiLSTM over all padded frames (fusion_module.py:64)
-        return fused_seq, input_lengths
+        return self.temporal(fused), input_lengths
+
+    def temporal(self, fused):
+        """temporal_model over all padded frames (fusion_module.py:64).  The reference's configuration (hidden 512,
+        also 256; batch <= 32) runs on the persistent kernels of csrc/lstm.cu; other shapes use nn.LSTM (cuDNN)."""
+        lstm = self.temporal_model
+        B, _, In = fused.shape
+        if (fused.is_cuda and lstm.hidden_size in (256, 512) and B <= 32 and In % 8 == 0 and lstm.num_layers == 2
+                and lstm.bidirectional and _lib.tuning_enabled("lstm_custom")):
+            y = _BiLSTMFn.apply(fused, *lstm._flat_weights)
+            if fused.dtype == torch.float32 and not torch.is_autocast_enabled():
+                y = y.float()
+            return y
+        fused_seq, _ = lstm(fused)
+        return fused_seq
