@@ -454,25 +454,28 @@ __global__ void __launch_bounds__(kTopkWarps * 32) beam_topk_kernel(const BeamPa
     int* ti = reinterpret_cast<int*>(tv + kBeamMax + 1);
     float* srow = reinterpret_cast<float*>(ti + kBeamMax + 1);
     int* qi = reinterpret_cast<int*>(srow + p.row_floats);
-    const long long rows = (long long)p.N * p.T;
-    for (long long r = (long long)blockIdx.x * kTopkWarps + warp; r < rows; r += (long long)gridDim.x * kTopkWarps) {
-        const int n = (int)(r / p.T), t = (int)(r % p.T);
+    const unsigned rows = (unsigned)p.N * (unsigned)p.T;       // host guarantees N*T < 2^31
+    const unsigned uT = (unsigned)p.T;
+    const bool can_fast = p.fast && (k + 1 <= 32) && (p.V >= k + 1);
+    const int full_slots = p.V / 32;
+    for (unsigned r = blockIdx.x * kTopkWarps + warp; r < rows; r += gridDim.x * kTopkWarps) {
+        const unsigned n = r / uT, t = r - n * uT;
         if (p.lengths) {
             const long long fl = p.lengths[n];
-            if (t >= fl) continue;
+            if ((long long)t >= fl) continue;
         }
-        const float* row = p.lp + (int64_t)n * p.stride_n + (int64_t)t * p.stride_t;
+        const float* row = p.lp + (int64_t)n * p.stride_n + (int64_t)t * p.stride_t + lane;
         float x[NV];
-        bool bad = false;
         float ml = AVCTC_NEG_INF;
+        unsigned nanbits = 0;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            const int c = lane + 32 * j;
-            x[j] = (c < p.V) ? __ldcs(row + c) : AVCTC_NEG_INF;
-            bad |= (x[j] != x[j]);
+            if (j < full_slots || lane + 32 * j < p.V) x[j] = __ldcs(row + 32 * j);      // ragged / empty tail slots
+            else x[j] = AVCTC_NEG_INF;
+            nanbits = max(nanbits, __float_as_uint(x[j]) & 0x7fffffffu);
             ml = fmaxf(ml, x[j]);
         }
-        bool ok = p.fast && (k + 1 <= 32) && (p.V >= k + 1) && !__any_sync(kFullMask, bad);
+        bool ok = can_fast && !__any_sync(kFullMask, nanbits > 0x7f800000u);
         if (ok) {
             // (k+1)-th largest lane maximum = lower bound of the (k+1)-th largest element
             unsigned key = f2key(ml), m = 0;
@@ -481,11 +484,12 @@ __global__ void __launch_bounds__(kTopkWarps * 32) beam_topk_kernel(const BeamPa
                 const unsigned who = __ballot_sync(kFullMask, key == m);
                 if (lane == __ffs(who) - 1) key = 0u;
             }
+            const float tau = __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);   // inverse of f2key
             // everything >= tau, in (slot, lane) order
             int count = 0;
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
-                const bool take = (lane + 32 * j < p.V) && (f2key(x[j]) >= m);
+                const bool take = (x[j] >= tau) && (j < full_slots || lane + 32 * j < p.V);
                 const unsigned bm = __ballot_sync(kFullMask, take);
                 if (bm) {
                     const int pos = count + __popc(bm & ((1u << lane) - 1));
@@ -712,6 +716,7 @@ extern "C" int avctc_beam_search(const float* log_probs, int64_t stride_n, int64
     bp.row_floats = pl.row_floats; bp.n_enum = pl.n_enum; bp.use_nth = pl.use_nth;
     bp.tk_val = nullptr; bp.tk_idx = nullptr;
     AVCTC_CUDA_RETURN(cudaMemsetAsync(bp.status, 0, sizeof(int), st));
+    if (pl.two_phase && (long long)N * T >= (1ll << 31)) return AVCTC_ERR_UNSUPPORTED;
     if (pl.two_phase) {
         if (T == 0) { AVCTC_CUDA_RETURN(cudaMemsetAsync(out_len, 0, sizeof(int32_t) * N, st)); return AVCTC_OK; }
         bp.tk_val = reinterpret_cast<float*>(w + pl.off_tv);
