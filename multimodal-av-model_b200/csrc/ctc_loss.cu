@@ -1340,7 +1340,7 @@ __device__ __forceinline__ void grad_stream_row(const TIn* __restrict__ lrow, TI
 }
 
 template <int K, typename TIn>
-__global__ void __launch_bounds__(256) ctc_grad_lin_kernel(const GradParams p) {
+__global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(const GradParams p) {
     constexpr int KL = K / 2;
     constexpr int kVec = VecTraits<TIn>::kVec;
     extern __shared__ __align__(16) float smem[];

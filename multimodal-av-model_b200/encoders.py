@@ -130,11 +130,38 @@ class AudioEncoder(nn.Module):
         fe = getattr(self.model, "feature_extractor", None)
         if fe is not None and getattr(fe, "_requires_grad", False) and not any(p.requires_grad for p in fe.parameters()):
             fe._requires_grad = False
+        if fe is not None and not hasattr(fe, "_avctc_cached"):
+            _install_feature_cache(fe)
         if attention_mask is not None:
             attention_mask = attention_mask.long()
         out = self.model(input_values=x, attention_mask=attention_mask, return_dict=True)
         middle = torch.stack(out.hidden_states[6:10], dim=0).mean(dim=0)
         return out.last_hidden_state, middle
+
+
+def _install_feature_cache(fe):
+    """The trainer runs the audio encoder twice per step on the SAME waveform tensor (once per speaker mask,
+    trainer.py:94-95).  The conv feature extractor is deterministic (no dropout) and frozen, so its output for an
+    unchanged input tensor is reused instead of recomputed: identical values, one conv stack pass per step instead of
+    two.  Installed as an instance-level forward wrapper, so module structure and state_dict keys do not change."""
+    inner = fe.forward
+    state = {"key": None, "out": None}
+
+    def cached_forward(input_values):
+        frozen = not any(p.requires_grad for p in fe.parameters()) and not getattr(fe, "_requires_grad", False)
+        if not frozen or torch.is_grad_enabled() and input_values.requires_grad:
+            state["key"] = None
+            return inner(input_values)
+        key = (input_values.data_ptr(), input_values._version, tuple(input_values.shape), input_values.dtype,
+               torch.is_autocast_enabled(), fe.training)
+        if state["key"] != key:
+            with torch.no_grad():
+                state["out"] = inner(input_values)
+            state["key"] = key
+        return state["out"]
+
+    fe.forward = cached_forward
+    fe._avctc_cached = True
 
 
 def unfreeze_middle_layers(model):
