@@ -891,7 +891,7 @@ __device__ __forceinline__ void ws_bulk_g2s(uint32_t dst, const void* src, uint3
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int K, typename TIn>
+template <int K, typename TIn, bool STORE>
 __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, const int row_stride_bytes) {
     constexpr int KL = K / 2;
     constexpr int G = kWsGroup, NG = kWsGroups;
@@ -934,7 +934,7 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
 
     const int g = lane;
     const int nvalid = min(max(S - g * K, 0), K);
-    const bool do_store = p.store != 0;
+    constexpr bool do_store = STORE;
     const TIn* row0 = reinterpret_cast<const TIn*>(p.lp) + (int64_t)b * p.stride_b +
                       (int64_t)(dir ? Tb - 1 : 0) * p.stride_t;
     const long long fstep = dir ? -p.stride_t : p.stride_t;
@@ -1161,12 +1161,12 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
     // one frame of the chain; RENORM frames bring the lane maximum back into [1,2) (exact power of two), the frames
     // in between only accumulate the emission exponent — two frames cannot move a lane by more than fp32's range
     // unless a class the mass sits on is > e^-40 below the best class of its lane twice in a row.
-    auto frame = [&](const int tau, const int owner, const bool renorm) {
+    auto frame = [&](const int tau, const int slot, const int owner, const bool renorm) {   // slot = tau & (RD-1), static
         const float up_a = __shfl_up_sync(kFullMask, a[K - 1], 1);
         const int up_C = __shfl_up_sync(kFullMask, C, 1);
         if (availP[owner] <= tau) availP[owner] = ws_wait_ge(&prog[owner * 32 + lane], tau + 1);
         if (do_store && tau - doneW >= RD) doneW = ws_wait_ge(&prog[96 + lane], tau - RD + 1);
-        const int roff = (tau & (RD - 1)) * 32 * PW;
+        const int roff = slot * 32 * PW;
         float pr[PW];
         {
             const float4* src = reinterpret_cast<const float4*>(pmine + roff);
@@ -1226,13 +1226,16 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
         asm volatile("" ::: "memory");
         st_volatile_shared_s32(&prog[64 + lane], tau + 1);
     };
+    int base = 1;
 #pragma unroll 1
-    for (int base = 1; base < Tb; base += 2 * G) {
+    for (; base + 2 * G <= Tb; base += 2 * G) {          // full groups: no bounds checks on the chain
 #pragma unroll
-        for (int u = 0; u < 2 * G; ++u) {
-            const int tau = base + u;
-            if (tau < Tb) frame(tau, (u / G) & 1, (u & 1) == 1);
-        }
+        for (int u = 0; u < 2 * G; ++u) frame(base + u, (1 + u) & (RD - 1), (u / G) & 1, (u & 1) == 1);
+    }
+#pragma unroll
+    for (int u = 0; u < 2 * G; ++u) {
+        const int tau = base + u;
+        if (tau < Tb) frame(tau, (1 + u) & (RD - 1), (u / G) & 1, (u & 1) == 1);
     }
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -1552,11 +1555,14 @@ static int launch_scan_ws(const ScanParams& sp, int ndir, cudaStream_t st) {
     if (smem > 200 * 1024) return -1000;     // rows too long for the shared-memory ring: caller falls back
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        AVCTC_CUDA_RETURN(cudaFuncSetAttribute(ctc_scan_ws_kernel<K, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        AVCTC_CUDA_RETURN(cudaFuncSetAttribute(ctc_scan_ws_kernel<K, TIn, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               200 * 1024));
+        AVCTC_CUDA_RETURN(cudaFuncSetAttribute(ctc_scan_ws_kernel<K, TIn, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                200 * 1024));
         configured = 200 * 1024;
     }
-    ctc_scan_ws_kernel<K, TIn><<<grid, block, smem, st>>>(sp, row_stride);
+    if (sp.store) ctc_scan_ws_kernel<K, TIn, true><<<grid, block, smem, st>>>(sp, row_stride);
+    else ctc_scan_ws_kernel<K, TIn, false><<<grid, block, smem, st>>>(sp, row_stride);
     return (int)cudaGetLastError();
 }
 template <typename TIn>
