@@ -80,19 +80,44 @@ class VisualEncoder(nn.Module):
         (measured: 20.4 -> 10.8 ms per [8,1,150,96,96] call); values are unchanged up to bf16 rounding."""
         if not getattr(self, "_cl_done", False):
             self.trunk.to(memory_format=torch.channels_last)
-            self.frontend3D.to(memory_format=torch.channels_last_3d)
             self._cl_done = True
 
+    def _frontend_as_2d(self, x):
+        """frontend3D (encoder.py:57-62) evaluated frame-wise with 2-D kernels, same parameters and same arithmetic:
+        a (5,7,7) Conv3d over ONE input channel with stride (1,2,2) is a 7x7 Conv2d whose 5 input channels are the
+        temporal taps t-2..t+2 (zero padded); BatchNorm3d over (B,T,H,W) equals BatchNorm2d over (B*T,H,W);
+        MaxPool3d((1,3,3)) is MaxPool2d(3) per frame.  cuDNN has bf16 tensor-core kernels for the 2-D form (the 3-D
+        form falls back to a TF32 kernel plus layout conversions) and the [B,64,T,H,W] -> [B*T,64,H,W] transpose copy
+        disappears.  Returns [B*T,64,H',W'] channels-last."""
+        import torch.nn.functional as F
+        conv, bn, act, pool = self.frontend3D[0], self.frontend3D[1], self.frontend3D[2], self.frontend3D[3]
+        b, _, t, h, w = x.shape
+        kt = conv.kernel_size[0]
+        pt = conv.padding[0]
+        xp = F.pad(x[:, 0], (0, 0, 0, 0, pt, pt))                                   # [B, T+2pt, H, W]
+        taps = xp.unfold(1, kt, 1)                                                    # [B, T, H, W, kt] (view)
+        taps = taps.permute(0, 1, 4, 2, 3).reshape(b * t, kt, h, w)                   # temporal taps as channels
+        taps = taps.contiguous(memory_format=torch.channels_last)
+        w2 = conv.weight[:, 0]                                                        # [64, kt, 7, 7]
+        y = F.conv2d(taps, w2, None, stride=conv.stride[1:], padding=conv.padding[1:])
+        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias,
+                         bn.training or not bn.track_running_stats, bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+        y = act(y)
+        return F.max_pool2d(y, pool.kernel_size[1:], pool.stride[1:], pool.padding[1:])
+
     def forward(self, x):
-        b = x.shape[0]
-        if x.is_cuda:
+        b, t = x.shape[0], x.shape[2]
+        conv = self.frontend3D[0]
+        if (x.is_cuda and x.shape[1] == 1 and conv.stride[0] == 1 and conv.dilation == (1, 1, 1)
+                and isinstance(self.frontend3D[1], nn.BatchNorm3d) and self.frontend3D[1].momentum is not None):
             self._channels_last()
-            x = x.contiguous(memory_format=torch.channels_last_3d)
+            y = self._frontend_as_2d(x)
+            return self.trunk(y).view(b, t, 512)
         y = self.frontend3D(x)                                   # [B,64,T,H',W']
         t, h, w = y.shape[2:]
         y = y.transpose(1, 2).reshape(b * t, 64, h, w)
-        if x.is_cuda:
-            y = y.contiguous(memory_format=torch.channels_last)
         return self.trunk(y).view(b, t, 512)
 
 
