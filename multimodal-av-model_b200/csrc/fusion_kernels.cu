@@ -81,6 +81,28 @@ __device__ __forceinline__ int batch_max(const int* cnt, int B) {
     return m;
 }
 
+// 8 consecutive elements of a row (nullptr -> zeros) as floats; the row start is 16-byte aligned when D % 8 == 0
+__device__ __forceinline__ void load8(const float* r, int d, float (&x)[8]) {
+    if (!r) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = 0.f;
+        return;
+    }
+    const float4 a = *reinterpret_cast<const float4*>(r + d), b = *reinterpret_cast<const float4*>(r + d + 4);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* r, int d, float (&x)[8]) {
+    if (!r) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = 0.f;
+        return;
+    }
+    const uint4 raw = *reinterpret_cast<const uint4*>(r + d);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); x[2 * k] = f.x; x[2 * k + 1] = f.y; }
+}
+
 template <typename TIn>
 __global__ void resample_apply_kernel(const TIn* __restrict__ audio, const int64_t* __restrict__ mask, int B, int Ta,
                                       int D, int Tv, const int* __restrict__ src, const int* __restrict__ cnt,
@@ -98,10 +120,24 @@ __global__ void resample_apply_kernel(const TIn* __restrict__ audio, const int64
     const LerpCoef c = lerp_coef(t, Tp, Tv);
     const TIn* r0 = (c.i0 < nb) ? audio + ((size_t)b * Ta + src[(size_t)b * Ta + c.i0]) * D : nullptr;
     const TIn* r1 = (c.i1 < nb && c.w1 != 0.f) ? audio + ((size_t)b * Ta + src[(size_t)b * Ta + c.i1]) * D : nullptr;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        const float x0 = r0 ? to_float(r0[d]) : 0.f;
-        const float x1 = r1 ? to_float(r1[d]) : 0.f;
-        orow[d] = __float2bfloat16(c.w0 * x0 + c.w1 * x1);
+    if ((D & 7) == 0) {          // 8 elements per thread: 16-byte (bf16) / 2 x 16-byte (fp32) loads, 16-byte stores
+        for (int d = threadIdx.x * 8; d < D; d += blockDim.x * 8) {
+            float x0[8], x1[8];
+            load8(r0, d, x0);
+            load8(r1, d, x1);
+            uint4 pk;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                h[k] = __floats2bfloat162_rn(c.w0 * x0[2 * k] + c.w1 * x1[2 * k], c.w0 * x0[2 * k + 1] + c.w1 * x1[2 * k + 1]);
+            *reinterpret_cast<uint4*>(orow + d) = pk;
+        }
+    } else {
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            const float x0 = r0 ? to_float(r0[d]) : 0.f;
+            const float x1 = r1 ? to_float(r1[d]) : 0.f;
+            orow[d] = __float2bfloat16(c.w0 * x0 + c.w1 * x1);
+        }
     }
     if (threadIdx.x == 0) {
         const int s = nearest_src(t, Tp, Tv);
@@ -123,7 +159,18 @@ __global__ void resample_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int 
         if constexpr (sizeof(TOut) == 4) *p = v; else *p = __float2bfloat16(v);
     };
     if (r < 0 || Tp == 0) {
-        for (int d = threadIdx.x; d < D; d += blockDim.x) put(drow + d, 0.f);
+        if ((D & 7) == 0) {
+            for (int d = threadIdx.x * 8; d < D; d += blockDim.x * 8) {
+                if constexpr (sizeof(TOut) == 4) {
+                    *reinterpret_cast<float4*>(drow + d) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(drow + d + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    *reinterpret_cast<uint4*>(drow + d) = make_uint4(0, 0, 0, 0);
+                }
+            }
+        } else {
+            for (int d = threadIdx.x; d < D; d += blockDim.x) put(drow + d, 0.f);
+        }
         return;
     }
     // output frames whose stencil can touch padded index r
@@ -152,6 +199,30 @@ __global__ void resample_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int 
     }
     __syncthreads();
     const int n = st_n;
+    if ((D & 7) == 0) {
+        for (int d = threadIdx.x * 8; d < D; d += blockDim.x * 8) {
+            float acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+            for (int i = 0; i < n; ++i) {
+                float x[8];
+                load8(dout + ((size_t)b * Tv + st_t[i]) * D, d, x);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += st_w[i] * x[k];
+            }
+            if constexpr (sizeof(TOut) == 4) {
+                *reinterpret_cast<float4*>(drow + d) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                *reinterpret_cast<float4*>(drow + d + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            } else {
+                uint4 pk;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
+                *reinterpret_cast<uint4*>(drow + d) = pk;
+            }
+        }
+        return;
+    }
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         float acc = 0.f;
         for (int i = 0; i < n; ++i) acc += st_w[i] * __bfloat162float(dout[((size_t)b * Tv + st_t[i]) * D + d]);
@@ -268,6 +339,8 @@ extern "C" int avctc_resample_forward(const void* audio, int dtype, const int64_
     if (B <= 0 || Ta <= 0 || D <= 0 || Tv <= 0) return AVCTC_ERR_BAD_ARG;
     if (!audio || !mask || !out_bf16 || !mask_out || !input_lengths || !workspace) return AVCTC_ERR_BAD_ARG;
     if (workspace_bytes < avctc_resample_workspace_bytes(B, Ta)) return AVCTC_ERR_WORKSPACE;
+    if ((D & 7) == 0 && ((reinterpret_cast<uintptr_t>(audio) | reinterpret_cast<uintptr_t>(out_bf16)) & 15))
+        return AVCTC_ERR_ALIGNMENT;      // the 8-wide path uses 16-byte accesses
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int* rank = reinterpret_cast<int*>(workspace);
     int* src = rank + (size_t)B * Ta;
@@ -276,11 +349,11 @@ extern "C" int avctc_resample_forward(const void* audio, int dtype, const int64_
     resample_index_kernel<<<B, 256, 0, st>>>(mask, B, Ta, rank, src, cnt);
     dim3 grid(Tv, B);
     if (dtype == AVCTC_F32)
-        resample_apply_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(audio), mask, B, Ta, D, Tv, src,
+        resample_apply_kernel<float><<<grid, 128, 0, st>>>(reinterpret_cast<const float*>(audio), mask, B, Ta, D, Tv, src,
                                                           cnt, reinterpret_cast<__nv_bfloat16*>(out_bf16), mask_out,
                                                           input_lengths);
     else if (dtype == AVCTC_BF16)
-        resample_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(audio), mask, B,
+        resample_apply_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(audio), mask, B,
                                                                   Ta, D, Tv, src, cnt,
                                                                   reinterpret_cast<__nv_bfloat16*>(out_bf16), mask_out,
                                                                   input_lengths);
@@ -291,15 +364,17 @@ extern "C" int avctc_resample_forward(const void* audio, int dtype, const int64_
 extern "C" int avctc_resample_backward(const void* dout_bf16, int B, int Ta, int D, int Tv, const void* workspace,
                                        void* daudio, int dtype, void* stream) {
     if (B <= 0 || Ta <= 0 || D <= 0 || Tv <= 0 || !dout_bf16 || !workspace || !daudio) return AVCTC_ERR_BAD_ARG;
+    if ((D & 7) == 0 && ((reinterpret_cast<uintptr_t>(dout_bf16) | reinterpret_cast<uintptr_t>(daudio)) & 15))
+        return AVCTC_ERR_ALIGNMENT;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int* rank = reinterpret_cast<const int*>(workspace);
     const int* cnt = rank + (size_t)2 * B * Ta;
     dim3 grid(Ta, B);
     const __nv_bfloat16* d = reinterpret_cast<const __nv_bfloat16*>(dout_bf16);
     if (dtype == AVCTC_F32)
-        resample_bwd_kernel<float><<<grid, 256, 0, st>>>(d, B, Ta, D, Tv, rank, cnt, reinterpret_cast<float*>(daudio));
+        resample_bwd_kernel<float><<<grid, 128, 0, st>>>(d, B, Ta, D, Tv, rank, cnt, reinterpret_cast<float*>(daudio));
     else if (dtype == AVCTC_BF16)
-        resample_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(d, B, Ta, D, Tv, rank, cnt,
+        resample_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(d, B, Ta, D, Tv, rank, cnt,
                                                                 reinterpret_cast<__nv_bfloat16*>(daudio));
     else return AVCTC_ERR_BAD_ARG;
     return (int)cudaGetLastError();

@@ -17,20 +17,24 @@ namespace avctc {
 struct CastJob { const float* src; __nv_bfloat16* dst; long long n; };
 struct CastJobs { CastJob j[8]; int count; };
 
-// fp32 -> bf16 for up to 8 tensors in one launch (weights of the five linears, or the incoming gradient)
+// fp32 -> bf16 for up to 8 tensors in one launch: one flat index space over all tensors (4 elements per step)
 __global__ void multi_cast_kernel(const CastJobs jobs) {
-    for (int t = 0; t < jobs.count; ++t) {
+    long long total4 = 0;
+    for (int t = 0; t < jobs.count; ++t) total4 += (jobs.j[t].n + 3) >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        int t = 0;
+        while (r >= ((jobs.j[t].n + 3) >> 2)) { r -= (jobs.j[t].n + 3) >> 2; ++t; }
         const CastJob jb = jobs.j[t];
-        const long long n4 = jb.n >> 2;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-            const float4 v = reinterpret_cast<const float4*>(jb.src)[i];
-            __nv_bfloat162* d = reinterpret_cast<__nv_bfloat162*>(jb.dst) + 2 * i;
+        const long long e = r << 2;
+        if (e + 4 <= jb.n && ((reinterpret_cast<uintptr_t>(jb.src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(jb.dst) & 7) == 0)) {
+            const float4 v = *reinterpret_cast<const float4*>(jb.src + e);
+            __nv_bfloat162* d = reinterpret_cast<__nv_bfloat162*>(jb.dst + e);
             d[0] = __floats2bfloat162_rn(v.x, v.y);
             d[1] = __floats2bfloat162_rn(v.z, v.w);
+        } else {
+            for (long long k = e; k < jb.n && k < e + 4; ++k) jb.dst[k] = __float2bfloat16(jb.src[k]);
         }
-        for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < jb.n;
-             i += (long long)gridDim.x * blockDim.x)
-            jb.dst[i] = __float2bfloat16(jb.src[i]);
     }
 }
 
@@ -160,7 +164,7 @@ extern "C" int avctc_fusion_forward(const void* visual_bf16, const void* audio, 
     cj.count = 5;
     cj.j[0] = {w_vp, s.w_vp, (long long)Eh * Dv}; cj.j[1] = {w_ap, s.w_ap, (long long)Eh * Da};
     cj.j[2] = {w_in, s.w_in, 3ll * Eh * Eh}; cj.j[3] = {w_o, s.w_o, (long long)Eh * Eh}; cj.j[4] = {w_f, s.w_f, (long long)Eh * Eh};
-    multi_cast_kernel<<<148, 256, 0, st>>>(cj);
+    multi_cast_kernel<<<592, 256, 0, st>>>(cj);
     AVCTC_CUDA_RETURN(cudaGetLastError());
     AVCTC_TRY(avctc_resample_forward(audio, audio_dtype, mask, B, Ta, Da, T, s.xa, mask_out, input_lengths, s.rs_ws,
                                      s.rs_bytes, stream));

@@ -45,6 +45,7 @@ struct GemmParams {
 };
 
 __device__ long long g_gemm_dbg[16];
+__device__ long long g_gemm_dbg2[2 * 2048 + 2];   // per-CTA start/end timestamps (debug)
 __device__ __forceinline__ long long gtime() {
     long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -127,6 +128,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) GEMM_DBG(0);
+    const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (p.dbg && threadIdx.x == 0 && cta_lin < 2048) g_gemm_dbg2[2 * cta_lin] = gtime();
     const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
     const int z = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
     const int zo = z / p.inner_count, zi = z % p.inner_count;
@@ -298,6 +301,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) GEMM_DBG(6);
+    if (p.dbg && threadIdx.x == 0 && cta_lin < 2048) g_gemm_dbg2[2 * cta_lin + 1] = gtime();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
     }
@@ -348,6 +352,9 @@ int avctc_gemm_launch(const avctc_gemm_operand* a, const avctc_gemm_operand* b, 
 // debug only (not part of the public header): phase timestamps (ns) of CTA (0,0,0) of the last launch with gemm_dbg=1
 extern "C" __attribute__((visibility("default"))) int avctc_debug_gemm_timestamps(long long* host_out16) {
     return (int)cudaMemcpyFromSymbol(host_out16, g_gemm_dbg, sizeof(long long) * 16);
+}
+extern "C" __attribute__((visibility("default"))) int avctc_debug_gemm_cta_times(long long* host_out, int n_ctas) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_gemm_dbg2, sizeof(long long) * 2 * (n_ctas < 2048 ? n_ctas : 2048));
 }
 
 // See include/avctc_b200.h for the argument contract.
