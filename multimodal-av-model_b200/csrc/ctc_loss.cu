@@ -19,6 +19,8 @@
 //                   alpha/beta into per-class posteriors (deterministic chains for repeated labels),
 //                   writes (exp(lp) - posterior) * g as aligned 16-byte stores.  HBM-bound:
 //                   algorithmic bytes = one read of log_probs + one write of grad.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace avctc {
@@ -29,10 +31,15 @@ constexpr int kRing = 32;          // handoff ring slots between neighbouring wa
 constexpr int kMaxWarps = 16;
 constexpr int kChainNone = 0x3fffffff;
 constexpr int kChainFirst = 0x40000000;
+// Largest spread (natural-log units) between the emissions of one lane's classes in one frame for which the
+// probability-domain scan is used: p = exp(lp - max) >= e^-40 = 2^-58, so two frames between renormalisations stay
+// inside fp32's exponent range.  Beyond it the batch is recomputed by the log-domain kernels (device-side flag).
+constexpr float kLinSafeRange = 40.f;
 
 struct CtcPlan {
     int K, W, S_pad, Lpad, linear;
-    size_t off_alpha, off_beta, off_coff_a, off_coff_b, off_nll2, off_chain, total;
+    int Klog, Wlog, CW;          // log-domain plan of the same problem (fallback of the linear path); coff row stride
+    size_t off_alpha, off_beta, off_coff_a, off_coff_b, off_nll2, off_chain, off_flag, total;
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -49,29 +56,36 @@ static bool make_plan(int T, int B, int Lmax, CtcPlan* pl) {
         W = 1;
         pl->linear = 1;
     }
-    const int forced = pl->linear ? 0 : avctc_tuning_get("ctc_k", 0);
+    const int forced = avctc_tuning_get("ctc_k", 0);
+    int Kl = 0, Wl = 0;
     if (forced == 2 || forced == 4 || forced == 8 || forced == 16) {
         int w = (S + 32 * forced - 1) / (32 * forced);
-        if (w <= kMaxWarps) { K = forced; W = w; }
+        if (w <= kMaxWarps) { Kl = forced; Wl = w; }
     }
-    if (K == 0) {
-        if (S <= 64) { K = 2; W = 1; }
-        else if (S <= 128) { K = 4; W = 1; }
-        else if (S <= 512) { K = 2; W = (S + 63) / 64; }
-        else if (S <= 2048) { K = 4; W = (S + 127) / 128; }
-        else if (S <= 4096) { K = 8; W = (S + 255) / 256; }
-        else if (S <= 8192) { K = 16; W = (S + 511) / 512; }
+    if (Kl == 0) {
+        if (S <= 64) { Kl = 2; Wl = 1; }
+        else if (S <= 128) { Kl = 4; Wl = 1; }
+        else if (S <= 512) { Kl = 2; Wl = (S + 63) / 64; }
+        else if (S <= 2048) { Kl = 4; Wl = (S + 127) / 128; }
+        else if (S <= 4096) { Kl = 8; Wl = (S + 255) / 256; }
+        else if (S <= 8192) { Kl = 16; Wl = (S + 511) / 512; }
         else return false;
     }
-    pl->K = K; pl->W = W; pl->S_pad = W * 32 * K; pl->Lpad = Lmax > 0 ? Lmax : 1;
+    pl->Klog = Kl; pl->Wlog = Wl;
+    if (!pl->linear) { K = Kl; W = Wl; }
+    pl->K = K; pl->W = W; pl->Lpad = Lmax > 0 ? Lmax : 1;
+    // one set of buffers serves both layouts: rows are as long as the longer of the two, one exponent per lane
+    pl->S_pad = std::max(W * 32 * K, Wl * 32 * Kl);
+    pl->CW = 32 * std::max(W, Wl);
     const size_t TB = (size_t)(T > 0 ? T : 1) * (size_t)B;
     size_t o = 0;
     pl->off_alpha = o; o = align_up(o + TB * pl->S_pad * sizeof(float), 256);
     pl->off_beta = o; o = align_up(o + TB * pl->S_pad * sizeof(float), 256);
-    pl->off_coff_a = o; o = align_up(o + TB * W * 32 * sizeof(int), 256);   // one offset per LANE
-    pl->off_coff_b = o; o = align_up(o + TB * W * 32 * sizeof(int), 256);
+    pl->off_coff_a = o; o = align_up(o + TB * pl->CW * sizeof(int), 256);
+    pl->off_coff_b = o; o = align_up(o + TB * pl->CW * sizeof(int), 256);
     pl->off_nll2 = o; o = align_up(o + (size_t)B * sizeof(double), 256);
     pl->off_chain = o; o = align_up(o + (size_t)B * pl->Lpad * sizeof(int), 256);
+    pl->off_flag = o; o = align_up(o + 256, 256);
     pl->total = o;
     return true;
 }
@@ -85,6 +99,10 @@ struct ScanParams {
     float* nll;
     float* alpha; float* beta; int* coff_a; int* coff_b; double* nll2; int* chain;
     int W, S_pad, Lpad;
+    int cw;            // coff row stride (ints)
+    int* flag;         // device int: set to 1 by the probability-domain scan when an emission ratio is out of its safe
+                       // range; the log-domain kernels run only when run_if == *flag (flag == nullptr: always)
+    int run_if;
 };
 
 template <int K>
@@ -103,6 +121,7 @@ __global__ void __launch_bounds__(32 * kMaxWarps) ctc_scan_kernel(const ScanPara
     constexpr int KL = K / 2;
     constexpr int D = (K >= 16) ? kScanPrefetch / 4 : (K >= 8) ? kScanPrefetch / 2 : kScanPrefetch;
     constexpr int RN = (D < kRenorm) ? D : kRenorm;
+    if (p.flag && *reinterpret_cast<volatile int*>(p.flag) != p.run_if) return;   // fallback launch, not needed
     const int b = blockIdx.x;
     const int dir = blockIdx.y;  // 0: alpha (forward in time), 1: beta (mirrored problem)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -186,9 +205,9 @@ __global__ void __launch_bounds__(32 * kMaxWarps) ctc_scan_kernel(const ScanPara
         int cons = 0;
         const size_t rowi0 = (size_t)b * p.T + (dir ? Tb - 1 : 0);
         float* wsp = (dir ? p.beta : p.alpha) + (p.store ? rowi0 * p.S_pad + (size_t)g * K : 0);
-        int* cfp = (dir ? p.coff_b : p.coff_a) + (p.store ? rowi0 * (p.W * 32) + g : 0);
+        int* cfp = (dir ? p.coff_b : p.coff_a) + (p.store ? rowi0 * p.cw + g : 0);
         long long wstep = dir ? -(long long)p.S_pad : (long long)p.S_pad;
-        long long cstep = dir ? -(long long)p.W * 32 : (long long)p.W * 32;
+        long long cstep = dir ? -(long long)p.cw : (long long)p.cw;
         asm volatile("" : "+l"(wstep), "+l"(cstep));   // keep the steps in registers (no per-frame recompute)
         const bool do_store = p.store != 0;
         const bool is_lane0 = (lane == 0);
@@ -453,12 +472,13 @@ __global__ void __launch_bounds__(32) ctc_scan_lin_kernel(const ScanParams p) {
         a[1] = ex2_approx(xl - Ef);
         C = (int)Ef;
         has_mass = fmaxf(a[0], a[1]) > 0.f;
+        if (L > 0 && p.flag && fabsf(xb - xl) > kLinSafeRange * AVCTC_LOG2E) *p.flag = 1;
     }
     const size_t rowi0 = (size_t)b * p.T + (dir ? Tb - 1 : 0);
     float* wsp = (dir ? p.beta : p.alpha) + (p.store ? rowi0 * p.S_pad + (size_t)g * K : 0);
-    int* cfp = (dir ? p.coff_b : p.coff_a) + (p.store ? rowi0 * 32 + g : 0);
+    int* cfp = (dir ? p.coff_b : p.coff_a) + (p.store ? rowi0 * p.cw + g : 0);
     long long wstep = dir ? -(long long)p.S_pad : (long long)p.S_pad;
-    long long cstep = dir ? -32ll : 32ll;
+    long long cstep = dir ? -(long long)p.cw : (long long)p.cw;
     asm volatile("" : "+l"(wstep), "+l"(cstep));
     const bool do_store = p.store != 0;
     auto publish = [&]() {
@@ -536,12 +556,14 @@ __global__ void __launch_bounds__(32) ctc_scan_lin_kernel(const ScanParams p) {
         --live_left;
         slot = (slot + 1) & (D - 1);
         xb = (nvalid > 0) ? xb * AVCTC_LOG2E : AVCTC_NEG_INF;
-        float mx = xb;
+        float mx = xb, mn = (nvalid > 0) ? xb : CUDART_INF_F;
 #pragma unroll
         for (int i = 0; i < KL; ++i) {
             xl[i] = (2 * i + 1 < nvalid) ? xl[i] * AVCTC_LOG2E : AVCTC_NEG_INF;
             mx = fmaxf(mx, xl[i]);
+            mn = fminf(mn, (2 * i + 1 < nvalid) ? xl[i] : CUDART_INF_F);
         }
+        if (mx - mn > kLinSafeRange * AVCTC_LOG2E && p.flag) *p.flag = 1;   // batch is redone by the log-domain kernels
         const float Ef = (mx > -1.0e29f) ? floorf(mx) : 0.f;
         E = (int)Ef;
         const float pblank = ex2_approx(xb - Ef);
@@ -638,6 +660,7 @@ struct GradParams {
     const float* alpha; const float* beta; const int* coff_a; const int* coff_b;
     const double* nll2; const int* chain;
     int K, W, S_pad, Lpad, linear;
+    int cw; const int* flag; int run_if;
     int row_floats;   // per-warp smem floats for one staged row (>= V + 8, multiple of 4)
     int w_floats;     // per-warp smem floats for state weights (>= 2*Lmax+1, multiple of 4)
 };
@@ -719,6 +742,7 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const GradParams p) {
     extern __shared__ __align__(16) float smem[];
     constexpr int kVec = VecTraits<TIn>::kVec;
     constexpr int NS = 6;   // states per lane whose alpha/beta loads are issued before the row lands
+    if (p.flag && *p.flag != p.run_if) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     float* rowbuf = smem + (size_t)warp * (2 * p.row_floats + p.w_floats);
     float* outbuf = rowbuf + p.row_floats;
@@ -749,8 +773,8 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const GradParams p) {
         const size_t rowi = (size_t)b * p.T + t;
         const float* arow = p.alpha + rowi * p.S_pad;
         const float* brow = p.beta + rowi * p.S_pad;
-        const int* ca = p.coff_a + rowi * (p.W * 32);
-        const int* cb = p.coff_b + rowi * (p.W * 32);
+        const int* ca = p.coff_a + rowi * p.cw;
+        const int* cb = p.coff_b + rowi * p.cw;
         const double nll2 = p.nll2[b];
         const int perw = p.K;   // states per lane (offsets are per lane)
 
@@ -854,6 +878,7 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const GradParams p) {
 // Per-lane 4-byte gathers straight from HBM (ctc_scan_lin_kernel) are bound by DRAM random-access efficiency
 // (measured ~1 TB/s of 32-byte sectors); full rows stream at HBM speed and are also what the hardware prefetches.
 constexpr int kWsRing = 8;   // frames per ring (power of two)
+
 constexpr int kWsGroup = 4;  // frames per TMA mbarrier phase
 constexpr int kWsGroups = 4; // groups in flight per producer warp
 
@@ -1031,6 +1056,7 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
         int cons = 1;
         int sl = 0;
         uint32_t par = 0;
+        bool risky = false;
         uintptr_t src_c = reinterpret_cast<uintptr_t>(row0) + (uintptr_t)(fstep_b * (1 + pw * G));
         int f = 1 + pw * G;
 #pragma unroll 1
@@ -1043,9 +1069,15 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
                     const uint32_t rb = rbase + (uint32_t)(src_c & 15);
                     float xb = lds_val(rb + off_b) + ninf_b;
                     float xl[KL];
-                    float mx = xb;
+                    float mx = xb, mn = (nvalid > 0) ? xb : CUDART_INF_F;
 #pragma unroll
-                    for (int i = 0; i < KL; ++i) { xl[i] = lds_val(rb + off_l[i]) + ninf_l[i]; mx = fmaxf(mx, xl[i]); }
+                    for (int i = 0; i < KL; ++i) {
+                        const float raw = lds_val(rb + off_l[i]);
+                        xl[i] = raw + ninf_l[i];
+                        mx = fmaxf(mx, xl[i]);
+                        mn = fminf(mn, raw - ninf_l[i]);          // invalid states contribute +inf
+                    }
+                    risky |= (mx - mn > kLinSafeRange);            // p of some class would leave fp32's safe range
                     const float ms = mx * AVCTC_LOG2E;
                     const float Ef = (ms > -1.0e29f) ? floorf(ms) : 0.f;
                     const float pblank = ex2_approx(fmaf(xb, AVCTC_LOG2E, -Ef));
@@ -1075,6 +1107,7 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
             if (k + NG < mygroups) arm(sl);
             if (++sl == NG) { sl = 0; par ^= 1u; }
         }
+        if (risky && p.flag) *p.flag = 1;     // the host's conditional log-domain launches redo this batch
         return;
     }
 
@@ -1083,9 +1116,9 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
         if (!do_store || Tb < 2) return;
         const size_t rowi1 = (size_t)b * p.T + (dir ? Tb - 2 : 1);       // scan frame 1
         float* wsp = (dir ? p.beta : p.alpha) + rowi1 * p.S_pad + (size_t)g * K;
-        int* cfp = (dir ? p.coff_b : p.coff_a) + rowi1 * 32 + g;
+        int* cfp = (dir ? p.coff_b : p.coff_a) + rowi1 * p.cw + g;
         long long wstep = dir ? -(long long)p.S_pad : (long long)p.S_pad;
-        long long cstep = dir ? -32ll : 32ll;
+        long long cstep = dir ? -(long long)p.cw : (long long)p.cw;
         asm volatile("" : "+l"(wstep), "+l"(cstep));
         int avail = 1;
 #pragma unroll 1
@@ -1147,13 +1180,14 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
         a[1] = ex2_approx(xl - Ef);
         C = (int)Ef;
         has_mass = fmaxf(a[0], a[1]) > 0.f;
+        if (L > 0 && p.flag && fabsf(xb - xl) > kLinSafeRange * AVCTC_LOG2E) *p.flag = 1;
     }
     if (do_store) {     // frame 0 goes straight to the workspace
         const size_t rowi0 = (size_t)b * p.T + (dir ? Tb - 1 : 0);
         float* w0 = (dir ? p.beta : p.alpha) + rowi0 * p.S_pad + (size_t)g * K;
 #pragma unroll
         for (int j = 0; j < K; ++j) w0[j] = a[j];
-        ((dir ? p.coff_b : p.coff_a) + rowi0 * 32)[g] = C;
+        ((dir ? p.coff_b : p.coff_a) + rowi0 * p.cw)[g] = C;
     }
     const bool not_lane0 = lane > 0;
     int availP[2] = {1, 1};
@@ -1348,6 +1382,7 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
     constexpr int kVec = VecTraits<TIn>::kVec;
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    if (p.flag && *p.flag != p.run_if) return;
     float* delta = smem + (size_t)warp * (p.row_floats + p.w_floats);   // class posteriors; all-zero between rows
     float* wbuf = delta + p.row_floats;                                  // label-state weights of the current row
     for (int i = lane; i < p.row_floats; i += 32) delta[i] = 0.f;
@@ -1414,8 +1449,8 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
             const size_t rowi = (size_t)b * p.T + t;
             const float* arow = p.alpha + rowi * p.S_pad + s0;
             const float* brow = p.beta + rowi * p.S_pad;
-            const int* cbp = p.coff_b + rowi * 32;
-            const int caL = p.coff_a[rowi * 32 + lane];
+            const int* cbp = p.coff_b + rowi * p.cw;
+            const int caL = p.coff_a[rowi * p.cw + lane];
             float av[K], bv[K];
             int cbv[K];
 #pragma unroll
@@ -1701,14 +1736,25 @@ extern "C" int avctc_ctc_forward(const void* log_probs, int dtype, int64_t strid
     sp.nll2 = need_grad ? reinterpret_cast<double*>(w + pl.off_nll2) : nullptr;
     sp.chain = need_grad ? reinterpret_cast<int*>(w + pl.off_chain) : nullptr;
     sp.W = pl.W; sp.S_pad = pl.S_pad; sp.Lpad = pl.Lpad;
+    sp.cw = pl.CW; sp.flag = nullptr; sp.run_if = 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int ndir = need_grad ? 2 : 1;
-    if (pl.linear) {
-        if (dtype == AVCTC_F32) return dispatch_scan_lin<float>(sp, pl.K, ndir, st);
-        return dispatch_scan_lin<__nv_bfloat16>(sp, pl.K, ndir, st);
+    // The probability-domain scan needs the device flag of the workspace for its range guard; a forward-only call
+    // without workspace (evaluation) goes straight to the log-domain kernel.
+    if (pl.linear && need_grad) {
+        sp.flag = reinterpret_cast<int*>(w + pl.off_flag);
+        AVCTC_CUDA_RETURN(cudaMemsetAsync(sp.flag, 0, sizeof(int), st));
+        int rc = (dtype == AVCTC_F32) ? dispatch_scan_lin<float>(sp, pl.K, ndir, st)
+                                      : dispatch_scan_lin<__nv_bfloat16>(sp, pl.K, ndir, st);
+        if (rc) return rc;
+        ScanParams sl = sp;                       // conditional fallback: runs only if the guard tripped
+        sl.W = pl.Wlog; sl.run_if = 1;
+        if (dtype == AVCTC_F32) return dispatch_scan<float>(sl, pl.Klog, ndir, st);
+        return dispatch_scan<__nv_bfloat16>(sl, pl.Klog, ndir, st);
     }
-    if (dtype == AVCTC_F32) return dispatch_scan<float>(sp, pl.K, ndir, st);
-    return dispatch_scan<__nv_bfloat16>(sp, pl.K, ndir, st);
+    sp.W = pl.Wlog;
+    if (dtype == AVCTC_F32) return dispatch_scan<float>(sp, pl.Klog, ndir, st);
+    return dispatch_scan<__nv_bfloat16>(sp, pl.Klog, ndir, st);
 }
 
 extern "C" int avctc_ctc_reduce(const float* nll, const int64_t* target_lengths, int B, int reduction,
@@ -1752,13 +1798,21 @@ extern "C" int avctc_ctc_backward(const void* log_probs, int dtype, int64_t stri
     gp.nll2 = reinterpret_cast<const double*>(w + pl.off_nll2);
     gp.chain = reinterpret_cast<const int*>(w + pl.off_chain);
     gp.K = pl.K; gp.W = pl.W; gp.S_pad = pl.S_pad; gp.Lpad = pl.Lpad; gp.linear = pl.linear;
+    gp.cw = pl.CW; gp.flag = nullptr; gp.run_if = 0;
     gp.row_floats = (V + 8 + 3) & ~3;
     gp.w_floats = (2 * max_target_len + 1 + 3) & ~3;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (pl.linear) {
-        if (dtype == AVCTC_F32) return dispatch_grad_lin<float>(gp, st);
-        return dispatch_grad_lin<__nv_bfloat16>(gp, st);
+        gp.flag = reinterpret_cast<const int*>(w + pl.off_flag);
+        gp.run_if = 0;                            // guard not tripped: probability-domain workspaces
+        int rc = (dtype == AVCTC_F32) ? dispatch_grad_lin<float>(gp, st) : dispatch_grad_lin<__nv_bfloat16>(gp, st);
+        if (rc) return rc;
+        GradParams gl = gp;                       // guard tripped: the log-domain scan rewrote the workspaces
+        gl.K = pl.Klog; gl.W = pl.Wlog; gl.linear = 0; gl.run_if = 1;
+        if (dtype == AVCTC_F32) return launch_grad<float>(gl, st);
+        return launch_grad<__nv_bfloat16>(gl, st);
     }
+    gp.K = pl.Klog; gp.W = pl.Wlog;
     if (dtype == AVCTC_F32) return launch_grad<float>(gp, st);
     return launch_grad<__nv_bfloat16>(gp, st);
 }

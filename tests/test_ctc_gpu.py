@@ -138,3 +138,29 @@ def test_ctc_forward_only_and_one_d_targets():
         a = pkg.ctc_loss(lp.cuda(), torch.from_numpy(flat).cuda(), torch.from_numpy(il).cuda(),
                          torch.from_numpy(tl).cuda(), blank=3, reduction="none")
     assert np.allclose(a.cpu().numpy(), ref["nll"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("scale,gtol", [(20.0, 1e-4), (60.0, 1e-3)])
+def test_ctc_peaked_inputs_take_the_log_domain_route(scale, gtol):
+    """Log-probs whose classes differ by more than e^40 within a frame trip the range guard of the probability-domain
+    scan; the batch is then recomputed by the log-domain kernels on the device (no host sync).  Results must be as
+    accurate as forcing the log-domain route, and finite."""
+    pkg = _pkg()
+    lp, tg, il, tl = make_case(200, 8, 800, 3, 20, 58, seed=int(scale), scale=scale)
+    assert lp.min().item() < -100
+    ref = oracle.ctc_loss(lp.numpy(), tg, il, tl, blank=3, reduction="mean", zero_infinity=True)
+    out = {}
+    for lin in (1, 0):
+        pkg._lib.set_tuning("ctc_lin", lin)
+        try:
+            x = lp.cuda().requires_grad_()
+            loss = pkg.ctc_loss(x, torch.from_numpy(tg).cuda(), torch.from_numpy(il).cuda(), torch.from_numpy(tl).cuda(),
+                                blank=3, reduction="mean", zero_infinity=True)
+            loss.backward()
+            out[lin] = (loss.item(), x.grad.cpu().numpy())
+        finally:
+            pkg._lib.set_tuning("ctc_lin", 1)
+    assert np.isfinite(out[1][1]).all()
+    assert abs(out[1][0] - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    assert rel(out[1][1], ref["grad"]) < gtol
+    assert out[1][0] == out[0][0] and np.array_equal(out[1][1], out[0][1])      # same kernels ran
