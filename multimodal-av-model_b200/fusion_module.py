@@ -33,6 +33,23 @@ def _bf16(t):
     return t if t.dtype == _BF16 else t.to(_BF16)
 
 
+def _f32c(t):
+    """fp32 contiguous view of a parameter without touching the dispatcher when it already is one."""
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+_WS_BYTES = {}
+
+
+def _ws_bytes(fn_name, *dims):
+    key = (fn_name,) + dims
+    v = _WS_BYTES.get(key)
+    if v is None:
+        v = _WS_BYTES[key] = int(getattr(_lib.lib(), fn_name)(*dims))
+    return v
+
+
 def _linear(x, w, b, out_dtype=_BF16):
     M, K = x.shape
     N = w.shape[0]
@@ -230,9 +247,9 @@ class _FusionCoreFn(torch.autograd.Function):
         audio_c = audio_c.contiguous()
         mask_c = mask.to(device=dev, dtype=torch.long).contiguous()
         xv = _bf16(visual.detach().reshape(B * T, Dv)).contiguous()
-        ws = [t.detach().float().contiguous() for t in (w_vp, b_vp, w_ap, b_ap, w_in, b_in, w_o, b_o, w_f, b_f)]
-        saved_bytes = int(L.avctc_fusion_workspace_bytes(B, T, Ta, Dv, Da, E, H, 0))
-        scratch_bytes = int(L.avctc_fusion_workspace_bytes(B, T, Ta, Dv, Da, E, H, 1))
+        ws = [_f32c(t) for t in (w_vp, b_vp, w_ap, b_ap, w_in, b_in, w_o, b_o, w_f, b_f)]
+        saved_bytes = _ws_bytes("avctc_fusion_workspace_bytes", B, T, Ta, Dv, Da, E, H, 0)
+        scratch_bytes = _ws_bytes("avctc_fusion_workspace_bytes", B, T, Ta, Dv, Da, E, H, 1)
         if saved_bytes == 0:
             raise RuntimeError("fusion dims not supported by the fused path")
         saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
@@ -262,7 +279,7 @@ class _FusionCoreFn(torch.autograd.Function):
         dfc = dfc.contiguous()
         f32 = dict(dtype=torch.float32, device=dev)
         g = [torch.empty(shape, **f32) for shape in ((E, Dv), (E,), (E, Da), (E,), (3 * E, E), (3 * E,), (E, E), (E,), (E, E), (E,))]
-        scratch_bytes = int(L.avctc_fusion_workspace_bytes(B, T, Ta, Dv, Da, E, H, 2))
+        scratch_bytes = _ws_bytes("avctc_fusion_workspace_bytes", B, T, Ta, Dv, Da, E, H, 2)
         scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
         d_visual = torch.empty((B, T, Dv), dtype=_BF16, device=dev) if ctx.needs_input_grad[0] else None
         d_audio = None
@@ -296,10 +313,10 @@ class _BiLSTMFn(torch.autograd.Function):
         H = weights[1].shape[1]
         L = _lib.lib()
         xb = _bf16(x.detach()).contiguous()
-        ws = [w.detach().float().contiguous() for w in weights]
+        ws = [_f32c(w) for w in weights]
         need_grad = any(ctx.needs_input_grad)
-        saved_bytes = int(L.avctc_bilstm_workspace_bytes(B, T, In, H, 0))
-        scratch_bytes = int(L.avctc_bilstm_workspace_bytes(B, T, In, H, 1))
+        saved_bytes = _ws_bytes("avctc_bilstm_workspace_bytes", B, T, In, H, 0)
+        scratch_bytes = _ws_bytes("avctc_bilstm_workspace_bytes", B, T, In, H, 1)
         if saved_bytes == 0:
             raise RuntimeError("LSTM shape not supported by the sm_100a kernels")
         saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
@@ -322,7 +339,7 @@ class _BiLSTMFn(torch.autograd.Function):
         L = _lib.lib()
         dyb = _bf16(dy.detach()).contiguous()
         grads = [torch.empty(shp, dtype=torch.float32, device=dev) for shp in shapes]
-        scratch_bytes = int(L.avctc_bilstm_workspace_bytes(B, T, In, H, 2))
+        scratch_bytes = _ws_bytes("avctc_bilstm_workspace_bytes", B, T, In, H, 2)
         scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
         dx = torch.empty((B, T, In), dtype=_BF16, device=dev) if ctx.needs_input_grad[0] else None
         ptrs = (ctypes.c_void_p * 16)(*[g.data_ptr() for g in grads])

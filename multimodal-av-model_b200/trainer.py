@@ -193,9 +193,16 @@ class MultimodalTrainer:
                 d = self._to_dev(batch)
                 with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=str(self.device).startswith("cuda")):
                     lps, losses = [], []
+                    # collate_fn pads mask1 and mask2 with 3 at the same positions (dataset/collate_fn.py:39-44), so both
+                    # speakers see the same attention mask and, in eval mode, bit-identical audio features
+                    # (trainer.py:206-207,215-216 computes them twice): one encoder pass serves both when the masks agree
+                    att = [d["masks"][0] != 3, d["masks"][1] != 3]
+                    shared = None
+                    if torch.equal(att[0], att[1]):
+                        shared, _ = self.audio_encoder(d["audio"], attention_mask=att[0])
                     for s in range(2):
                         vis = self.visual_encoder(d["lips"][s])
-                        aud, _ = self.audio_encoder(d["audio"], attention_mask=(d["masks"][s] != 3))
+                        aud = shared if shared is not None else self.audio_encoder(d["audio"], attention_mask=att[s])[0]
                         t_enc = aud.shape[1]
                         mask_ds = F.interpolate(d["masks"][s].unsqueeze(1).float(), size=t_enc, mode="nearest").squeeze(1).long()
                         fused, il = self.fusion_module(vis, aud, mask_ds)
