@@ -13,7 +13,8 @@
 // or "MN-major" (row-major K x rows, i.e. the transposed view) so that forward, dX = dY.W and
 // dW = dY^T.X all run WITHOUT materialising a transpose; batched problems (attention heads) address their
 // slices through TMA coordinates (z -> (outer, inner) -> element offsets), never through copies.
-// Warp roles: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..5 epilogue.
+// Warp roles: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..9 epilogue (two warps per TMEM lane
+// quarter, each taking half of the columns: a lone warp per SM sub-partition issues too slowly to drain the tile).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -21,7 +22,8 @@
 namespace avctc {
 
 constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 3, kUmmaK = 16;   // 3 stages = 96 KiB: two CTAs per SM
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;                  // TMA warp, MMA warp, eight epilogue warps
+constexpr int kEpiThreads = kGemmThreads - 64;
 constexpr int kTileBytes = kBM * kBK * 2;           // 16 KiB per operand per stage
 constexpr int kTmemCols = 128;
 constexpr int kStgLd = kBN + 4;                     // fp32 staging tile row stride (bank-conflict-free float4 rows)
@@ -138,7 +140,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int kb0 = split * kb_per;
     const int num_kb = max(0, min(total_kb, kb0 + kb_per) - kb0);   // this CTA's share of the reduction
 
-    if (threadIdx.x >= 64) {      // per-column bias of this N tile (zero when absent / not the leading split)
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + kBN) {      // per-column bias of this N tile (zero when absent / not the leading split)
         const int i = threadIdx.x - 64;
         bias_s[i] = (split == 0 && p.bias_mode == 1 && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
     }
@@ -216,6 +218,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (threadIdx.x == 64) GEMM_DBG(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                   // a warp may only touch TMEM lanes [32q, 32q+32)
+        const int chalf = (warp - 2) >> 2;        // which half of the tile's columns this warp drains
         const int r_loc = q * 32 + lane;
         const int row = m0 + r_loc;
         const long long coff = (long long)zo * p.c_outer + (long long)zi * p.c_inner;
@@ -225,7 +228,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         float* stg = reinterpret_cast<float*>(gen);
         if (num_kb > 0) {
 #pragma unroll 1
-            for (int c = 0; c < kBN / 32; ++c) {
+            for (int c = chalf * (kBN / 64); c < (chalf + 1) * (kBN / 64); ++c) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -242,9 +245,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
             }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
+        if (threadIdx.x == 64) GEMM_DBG(7);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");       // the epilogue warps only
+        if (threadIdx.x == 64) GEMM_DBG(8);
         if (num_kb > 0) {
-            const int te = threadIdx.x - 64;                   // 0..127
+            const int te = threadIdx.x - 64;                   // 0..kEpiThreads-1
             const int rows_valid = min(kBM, p.M - m0), cols_valid = min(kBN, p.N - n0);
             const size_t esz = (p.out_dtype == AVCTC_F32) ? 4 : 2;
             const long long tile_off = coff + (long long)m0 * p.ldc + n0;
@@ -253,8 +258,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (vec_ok && p.out_dtype == AVCTC_BF16) {
                 __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C) + tile_off;
 #pragma unroll 4
-                for (int i = 0; i < 16; ++i) {                 // 16 threads cover one 256-byte output row
-                    const int idx = te + 128 * i, r = idx >> 4, c8 = (idx & 15) * 8;
+                for (int i = 0; i < (kBM * kBN / 8) / kEpiThreads; ++i) {   // 16 threads cover one 256-byte output row
+                    const int idx = te + kEpiThreads * i, r = idx >> 4, c8 = (idx & 15) * 8;
                     if (r < rows_valid) {
                         const float4 x = *reinterpret_cast<const float4*>(stg + r * kStgLd + c8);
                         const float4 y = *reinterpret_cast<const float4*>(stg + r * kStgLd + c8 + 4);
@@ -268,8 +273,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             } else if (vec_ok) {
                 float* Cf = reinterpret_cast<float*>(p.C) + tile_off;
 #pragma unroll 4
-                for (int i = 0; i < 32; ++i) {                 // one warp covers one 512-byte output row
-                    const int idx = te + 128 * i, r = idx >> 5, c4 = (idx & 31) * 4;
+                for (int i = 0; i < (kBM * kBN / 4) / kEpiThreads; ++i) {   // one warp covers one 512-byte output row
+                    const int idx = te + kEpiThreads * i, r = idx >> 5, c4 = (idx & 31) * 4;
                     if (r < rows_valid) {
                         float4 x = *reinterpret_cast<const float4*>(stg + r * kStgLd + c4);
                         float4* dst = reinterpret_cast<float4*>(Cf + (long long)r * p.ldc + c4);
@@ -281,7 +286,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                 }
             } else {                                           // ragged tile / unaligned C: element-wise
-                for (int idx = te; idx < kBM * kBN; idx += 128) {
+                for (int idx = te; idx < kBM * kBN; idx += kEpiThreads) {
                     const int r = idx / kBN, c = idx % kBN;
                     if (r >= rows_valid || c >= cols_valid) continue;
                     const float x = stg[r * kStgLd + c];

@@ -22,7 +22,7 @@ def run(M, N, K, reps=20, out_dtype=torch.bfloat16):
     ts = (ctypes.c_longlong * 16)()
     L._cdll.avctc_debug_gemm_timestamps(ts)
     t0 = ts[0]
-    names = ["start", "setup done", "first full", "last full", "acc ready", "epi done", "exit sync"]
+    names = ["start", "setup done", "first full", "last full", "acc ready", "epi done", "exit sync", "staged", "bar"]
     n_ctas = ((M + 127) // 128) * ((N + 127) // 128)
     if n_ctas <= 2048:
         buf = (ctypes.c_longlong * (2 * n_ctas))()
