@@ -172,7 +172,9 @@ AVCTC_API int avctc_log_softmax_backward(const void* Y, const void* dY, int dtyp
  * parameters (w_in/b_in = MultiheadAttention.in_proj_weight/bias [3E,E]/[3E]).  out: fp32 [B*T,E].
  * `saved` (which=0 bytes) carries the bf16 weights and activations from forward to backward; `scratch` (which=1 for
  * forward, which=2 for backward) is free after the call's kernels ran.  backward writes fp32 parameter gradients and,
- * when the pointers are non-NULL, d_visual (bf16 [B*T,Dv]) and d_audio ([B,Ta,Da], fp32 or bf16).
+ * when the pointers are non-NULL, d_visual (bf16 [B*T,Dv]) and d_audio ([B,Ta,Da], fp32 or bf16).  grads_zeroed != 0
+ * promises that all ten gradient tensors were zeroed by the caller (e.g. views of one zero-filled buffer): the library
+ * then skips its own per-tensor memsets.
  * ---------------------------------------------------------------------------------------------- */
 AVCTC_API size_t avctc_fusion_workspace_bytes(int B, int T, int Ta, int Dv, int Da, int E, int H, int which);
 AVCTC_API int avctc_fusion_forward(const void* visual_bf16, const void* audio, int audio_dtype, const int64_t* mask,
@@ -185,7 +187,7 @@ AVCTC_API int avctc_fusion_backward(const void* df, int df_dtype, const void* vi
                           int Da, int E, int H, float* g_wvp, float* g_bvp, float* g_wap, float* g_bap,
                           float* g_win, float* g_bin, float* g_wo, float* g_bo, float* g_wf, float* g_bf,
                           void* d_visual_bf16, void* d_audio, int d_audio_dtype, const void* saved,
-                          size_t saved_bytes, void* scratch, size_t scratch_bytes, void* stream);
+                          size_t saved_bytes, void* scratch, size_t scratch_bytes, int grads_zeroed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * temporal_model — nn.LSTM(E, E, num_layers=2, batch_first=True, bidirectional=True), zero initial state,

@@ -43,7 +43,7 @@ SIGNATURES = {
     "avctc_log_softmax_backward": (_i, [_vp, _vp, _i, _vp, ctypes.c_longlong, _i, ctypes.c_longlong, _vp]),
     "avctc_fusion_workspace_bytes": (_sz, [_i] * 8),
     "avctc_fusion_forward": (_i, [_vp, _vp, _i, _vp] + [_vp] * 10 + [_i] * 7 + [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
-    "avctc_fusion_backward": (_i, [_vp, _i, _vp] + [_i] * 7 + [_vp] * 10 + [_vp, _vp, _i, _vp, _sz, _vp, _sz, _vp]),
+    "avctc_fusion_backward": (_i, [_vp, _i, _vp] + [_i] * 7 + [_vp] * 10 + [_vp, _vp, _i, _vp, _sz, _vp, _sz, _i, _vp]),
     "avctc_bilstm_workspace_bytes": (_sz, [_i] * 5),
     "avctc_bilstm_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp, _sz, _i, _vp]),
     "avctc_bilstm_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
@@ -68,7 +68,7 @@ KERNELS = {"avctc_ctc_forward": 1, "avctc_ctc_reduce": 1, "avctc_ctc_backward": 
            "avctc_gemm_bf16": 1, "avctc_resample_forward": 2, "avctc_resample_backward": 1, "avctc_softmax_forward": 1,
            "avctc_softmax_backward": 1, "avctc_colsum": 1, "avctc_log_softmax_forward": 1,
            "avctc_log_softmax_backward": 1, "avctc_infonce_forward": 4, "avctc_infonce_backward": 2,
-           "avctc_fusion_forward": 12, "avctc_fusion_backward": 29,
+           "avctc_fusion_forward": 12, "avctc_fusion_backward": 24,
            "avctc_bilstm_forward": 7, "avctc_bilstm_backward": 20}
 launch_count = 0
 

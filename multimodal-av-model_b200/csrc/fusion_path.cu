@@ -38,6 +38,31 @@ __global__ void multi_cast_kernel(const CastJobs jobs) {
     }
 }
 
+struct ColsumJob { const __nv_bfloat16* x; long long M; int N; long long ld; float* out; };
+struct ColsumJobs { ColsumJob j[6]; int count; };
+// bias gradients of every linear in one launch: out[n] += sum_m x[m][n] (outs zeroed by the caller); grid (N/32, row
+// chunks, jobs), fp32 atomics across row chunks
+__global__ void multi_colsum_kernel(const ColsumJobs jobs) {
+    __shared__ float part[8][33];
+    const ColsumJob jb = jobs.j[blockIdx.z];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    if (blockIdx.x * 32 >= jb.N) return;
+    const long long per = (jb.M + gridDim.y - 1) / gridDim.y;
+    const long long m0 = (long long)blockIdx.y * per, m1 = (m0 + per < jb.M) ? m0 + per : jb.M;
+    float acc = 0.f;
+    if (n < jb.N)
+        for (long long m = m0 + ty; m < m1; m += 8) acc += __bfloat162float(jb.x[m * jb.ld + n]);
+    part[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && n < jb.N) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += part[i][tx];
+        atomicAdd(jb.out + n, s);
+    }
+}
+
 struct FusionDims { int B, T, Ta, Dv, Da, E, H, hd, Tp; long long M, BH; };
 
 static bool make_dims(int B, int T, int Ta, int Dv, int Da, int E, int H, FusionDims* d) {
@@ -123,12 +148,13 @@ static int dgrad(const __nv_bfloat16* dy, long long ldy, const __nv_bfloat16* w,
 }
 // g[N,K] (fp32) = dy[M,N]^T . x[M,K], split-K over M
 static int wgrad(const __nv_bfloat16* dy, long long ldy, const __nv_bfloat16* x, long long ldx, long long M, int N, int K,
-                 float* g, long long ldg, void* st) {
+                 float* g, long long ldg, void* st, bool prezeroed = false) {
     const avctc_gemm_operand A = opnd(dy, N, M, ldy, true), Bo = opnd(x, K, M, ldx, true);
     const int tiles = ((N + 127) / 128) * ((K + 127) / 128);
     int splits = tiles >= 74 ? 1 : (148 + tiles - 1) / tiles;     // ~one CTA per SM, 16-byte vector red.add epilogue
     if (splits > 8) splits = 8;
-    return avctc_gemm_launch(&A, &Bo, N, K, (int)M, 1, 1, g, AVCTC_F32, ldg, 0, 0, nullptr, 0, 1.f, 0, splits, st);
+    return avctc_gemm_launch(&A, &Bo, N, K, (int)M, 1, 1, g, AVCTC_F32, ldg, 0, 0, nullptr, 0, 1.f, 0,
+                             prezeroed ? -splits : splits, st);
 }
 
 }  // namespace avctc
@@ -199,7 +225,8 @@ extern "C" int avctc_fusion_backward(const void* df, int df_dtype, const void* v
                                      int Da, int E, int H, float* g_wvp, float* g_bvp, float* g_wap, float* g_bap,
                                      float* g_win, float* g_bin, float* g_wo, float* g_bo, float* g_wf, float* g_bf,
                                      void* d_visual_bf16, void* d_audio, int d_audio_dtype, const void* saved,
-                                     size_t saved_bytes, void* scratch, size_t scratch_bytes, void* stream) {
+                                     size_t saved_bytes, void* scratch, size_t scratch_bytes, int grads_zeroed,
+                                     void* stream) {
     FusionDims d;
     if (!make_dims(B, T, Ta, Dv, Da, E, H, &d)) return AVCTC_ERR_UNSUPPORTED;
     if (!df || !visual_bf16 || !g_wvp || !g_bvp || !g_wap || !g_bap || !g_win || !g_bin || !g_wo || !g_bo || !g_wf || !g_bf ||
@@ -223,13 +250,12 @@ extern "C" int avctc_fusion_backward(const void* df, int df_dtype, const void* v
         dfb = w.dfb;
     }
     const __nv_bfloat16* xv = reinterpret_cast<const __nv_bfloat16*>(visual_bf16);
+    const bool pz = grads_zeroed != 0;     // all ten gradient tensors are views of one buffer the caller zeroed once
     // fusion_proj
-    AVCTC_TRY(wgrad(dfb, Eh, s.ao, Eh, M, Eh, Eh, g_wf, Eh, stream));
-    AVCTC_TRY(avctc_colsum(dfb, AVCTC_BF16, M, Eh, Eh, g_bf, 0, stream));
+    AVCTC_TRY(wgrad(dfb, Eh, s.ao, Eh, M, Eh, Eh, g_wf, Eh, stream, pz));
     AVCTC_TRY(dgrad(dfb, Eh, s.w_f, M, Eh, Eh, w.dao, stream));
     // out_proj
-    AVCTC_TRY(wgrad(w.dao, Eh, s.o, Eh, M, Eh, Eh, g_wo, Eh, stream));
-    AVCTC_TRY(avctc_colsum(w.dao, AVCTC_BF16, M, Eh, Eh, g_bo, 0, stream));
+    AVCTC_TRY(wgrad(w.dao, Eh, s.o, Eh, M, Eh, Eh, g_wo, Eh, stream, pz));
     AVCTC_TRY(dgrad(w.dao, Eh, s.w_o, M, Eh, Eh, w.dout, stream));
     // attention core: dP = do_h . v_h^T ; dS = P * (dP - sum(dP*P)) ; dq = alpha dS.k ; dk = alpha dS^T.q ; dv = P^T.do
     const __nv_bfloat16* kk = s.kv;
@@ -266,17 +292,34 @@ extern "C" int avctc_fusion_backward(const void* df, int df_dtype, const void* v
                                     nullptr, 0, 1.f, 0, 1, stream));
     }
     // in_proj: rows [0,E) = query projection of a; rows [E,3E) = key|value projections of v
-    AVCTC_TRY(wgrad(w.dq, Eh, s.a, Eh, M, Eh, Eh, g_win, Eh, stream));
-    AVCTC_TRY(avctc_colsum(w.dq, AVCTC_BF16, M, Eh, Eh, g_bin, 0, stream));
-    AVCTC_TRY(wgrad(w.dkv, 2 * Eh, s.v, Eh, M, 2 * Eh, Eh, g_win + (size_t)Eh * Eh, Eh, stream));
-    AVCTC_TRY(avctc_colsum(w.dkv, AVCTC_BF16, M, 2 * Eh, 2 * Eh, g_bin + Eh, 0, stream));
+    AVCTC_TRY(wgrad(w.dq, Eh, s.a, Eh, M, Eh, Eh, g_win, Eh, stream, pz));
+    AVCTC_TRY(wgrad(w.dkv, 2 * Eh, s.v, Eh, M, 2 * Eh, Eh, g_win + (size_t)Eh * Eh, Eh, stream, pz));
     AVCTC_TRY(dgrad(w.dq, Eh, s.w_in, M, Eh, Eh, w.da, stream));
     AVCTC_TRY(dgrad(w.dkv, 2 * Eh, s.w_in + (size_t)Eh * Eh, M, 2 * Eh, Eh, w.dv, stream));
     // audio_proj / visual_proj
-    AVCTC_TRY(wgrad(w.da, Eh, s.xa, Da, M, Eh, Da, g_wap, Da, stream));
-    AVCTC_TRY(avctc_colsum(w.da, AVCTC_BF16, M, Eh, Eh, g_bap, 0, stream));
-    AVCTC_TRY(wgrad(w.dv, Eh, xv, Dv, M, Eh, Dv, g_wvp, Dv, stream));
-    AVCTC_TRY(avctc_colsum(w.dv, AVCTC_BF16, M, Eh, Eh, g_bvp, 0, stream));
+    AVCTC_TRY(wgrad(w.da, Eh, s.xa, Da, M, Eh, Da, g_wap, Da, stream, pz));
+    AVCTC_TRY(wgrad(w.dv, Eh, xv, Dv, M, Eh, Dv, g_wvp, Dv, stream, pz));
+    {   // the six bias gradients (column sums of the six dY tensors) in one launch
+        if (!pz) {
+            AVCTC_CUDA_RETURN(cudaMemsetAsync(g_bf, 0, sizeof(float) * Eh, st));
+            AVCTC_CUDA_RETURN(cudaMemsetAsync(g_bo, 0, sizeof(float) * Eh, st));
+            AVCTC_CUDA_RETURN(cudaMemsetAsync(g_bin, 0, sizeof(float) * 3 * Eh, st));
+            AVCTC_CUDA_RETURN(cudaMemsetAsync(g_bap, 0, sizeof(float) * Eh, st));
+            AVCTC_CUDA_RETURN(cudaMemsetAsync(g_bvp, 0, sizeof(float) * Eh, st));
+        }
+        ColsumJobs cj;
+        cj.count = 6;
+        cj.j[0] = {dfb, M, Eh, Eh, g_bf};
+        cj.j[1] = {w.dao, M, Eh, Eh, g_bo};
+        cj.j[2] = {w.dq, M, Eh, Eh, g_bin};
+        cj.j[3] = {w.dkv, M, 2 * Eh, 2 * Eh, g_bin + Eh};
+        cj.j[4] = {w.da, M, Eh, Eh, g_bap};
+        cj.j[5] = {w.dv, M, Eh, Eh, g_bvp};
+        int chunks = (int)((M + 127) / 128);
+        if (chunks > 32) chunks = 32;
+        multi_colsum_kernel<<<dim3((2 * Eh + 31) / 32, chunks, 6), 256, 0, st>>>(cj);
+        AVCTC_CUDA_RETURN(cudaGetLastError());
+    }
     if (d_visual_bf16) AVCTC_TRY(dgrad(w.dv, Eh, s.w_vp, M, Eh, Dv, reinterpret_cast<__nv_bfloat16*>(d_visual_bf16), stream));
     if (d_audio) {
         AVCTC_TRY(dgrad(w.da, Eh, s.w_ap, M, Eh, Da, w.dxa, stream));

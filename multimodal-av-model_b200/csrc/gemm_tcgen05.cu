@@ -403,13 +403,15 @@ int avctc_gemm_launch(const avctc_gemm_operand* a, const avctc_gemm_operand* b, 
     p.bias = bias; p.bias_mode = bias_mode; p.alpha = alpha; p.accumulate = accumulate;
     {
         const int total_kb = (K + kBK - 1) / kBK;
+        const bool prezeroed = splits < 0;      // negative: |splits|-way split-K into a C the caller already zeroed
+        if (prezeroed) splits = -splits;
         if (splits < 1) splits = 1;
         if (splits > total_kb) splits = total_kb;
         const int kb_per = (total_kb + splits - 1) / splits;
         splits = (total_kb + kb_per - 1) / kb_per;            // every split owns at least one k-block
         if (splits > 1) {
             if (out_dtype != AVCTC_F32 || accumulate || batch != 1) return AVCTC_ERR_BAD_ARG;
-            AVCTC_CUDA_RETURN(cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M,
+            if (!prezeroed) AVCTC_CUDA_RETURN(cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M,
                                                 reinterpret_cast<cudaStream_t>(stream)));
         }
         p.splits = splits;

@@ -277,8 +277,13 @@ class _FusionCoreFn(torch.autograd.Function):
         if dfc.dtype not in (torch.float32, _BF16):
             dfc = dfc.float()
         dfc = dfc.contiguous()
-        f32 = dict(dtype=torch.float32, device=dev)
-        g = [torch.empty(shape, **f32) for shape in ((E, Dv), (E,), (E, Da), (E,), (3 * E, E), (3 * E,), (E, E), (E,), (E, E), (E,))]
+        shapes = ((E, Dv), (E,), (E, Da), (E,), (3 * E, E), (3 * E,), (E, E), (E,), (E, E), (E,))
+        sizes = [(int(torch.Size(shp).numel()) + 63) // 64 * 64 for shp in shapes]       # 256-byte aligned views
+        gbuf = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)                   # ONE fill for all ten gradients
+        g, off = [], 0
+        for shp, n in zip(shapes, sizes):
+            g.append(gbuf[off:off + int(torch.Size(shp).numel())].view(shp))
+            off += n
         scratch_bytes = _ws_bytes("avctc_fusion_workspace_bytes", B, T, Ta, Dv, Da, E, H, 2)
         scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
         d_visual = torch.empty((B, T, Dv), dtype=_BF16, device=dev) if ctx.needs_input_grad[0] else None
@@ -292,7 +297,7 @@ class _FusionCoreFn(torch.autograd.Function):
                                                d_visual.data_ptr() if d_visual is not None else None,
                                                d_audio.data_ptr() if d_audio is not None else None,
                                                _lib.dtype_enum(d_audio) if d_audio is not None else 0,
-                                               saved.data_ptr(), saved_bytes, scratch.data_ptr(), scratch_bytes,
+                                               saved.data_ptr(), saved_bytes, scratch.data_ptr(), scratch_bytes, 1,
                                                _lib.stream_ptr(dev)), "avctc_fusion_backward")
         if d_visual is not None:
             d_visual = d_visual.to(visual_dtype)
