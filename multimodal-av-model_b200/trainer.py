@@ -112,11 +112,40 @@ class MultimodalTrainer:
         return out
 
     def _to_dev(self, batch):
+        """Host -> device.  Pinned host tensors are copied on a side stream (small tensors first, the two 44 MB lip
+        clips last); `lips` entries are zero-argument callables that make the main stream wait for exactly the clip it
+        is about to consume, so the audio encoder runs while the lip frames are still in flight."""
         dev = self.device
-        g = lambda k: batch[k].to(dev, non_blocking=True)
-        lips = [g("lip1").permute(0, 2, 1, 3, 4).contiguous(), g("lip2").permute(0, 2, 1, 3, 4).contiguous()]
-        return dict(lips=lips, audio=g("audio"), masks=[g("mask1"), g("mask2")], texts=[g("text1"), g("text2")],
-                    lens=[g("text1_lengths"), g("text2_lengths")])
+        on_gpu = str(dev).startswith("cuda")
+        any_host = on_gpu and any(torch.is_tensor(v) and not v.is_cuda for v in batch.values())
+        if not any_host:
+            g = lambda k: batch[k].to(dev, non_blocking=True)
+            lips = [g("lip1").permute(0, 2, 1, 3, 4).contiguous(), g("lip2").permute(0, 2, 1, 3, 4).contiguous()]
+            return dict(lips=[(lambda t=t: t) for t in lips], audio=g("audio"), masks=[g("mask1"), g("mask2")],
+                        texts=[g("text1"), g("text2")], lens=[g("text1_lengths"), g("text2_lengths")])
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cs = self._copy_stream            # (the caching allocator orders cross-stream reuse through record_stream)
+        out, events = {}, {}
+        with torch.cuda.stream(cs):
+            for k in ("audio", "mask1", "mask2", "text1", "text2", "text1_lengths", "text2_lengths"):
+                out[k] = batch[k].to(dev, non_blocking=True)
+            events["small"] = cs.record_event()
+            for k in ("lip1", "lip2"):
+                out[k] = batch[k].to(dev, non_blocking=True).permute(0, 2, 1, 3, 4).contiguous()
+                events[k] = cs.record_event()
+        for t in out.values():
+            t.record_stream(main)
+        main.wait_event(events["small"])
+
+        def lip(k):
+            def get():
+                torch.cuda.current_stream(dev).wait_event(events[k])
+                return out[k]
+            return get
+        return dict(lips=[lip("lip1"), lip("lip2")], audio=out["audio"], masks=[out["mask1"], out["mask2"]],
+                    texts=[out["text1"], out["text2"]], lens=[out["text1_lengths"], out["text2_lengths"]])
 
     def _ensure_projection(self, D):
         if self.projection_layer is None:           # trainer.py:105-106: created lazily, once per epoch
@@ -146,11 +175,11 @@ class MultimodalTrainer:
         self.optimizer.zero_grad()
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=str(self.device).startswith("cuda")):
             d = self._to_dev(batch)
-            vis = [self.visual_encoder(d["lips"][0]), self.visual_encoder(d["lips"][1])]
             aud, mid = [], []
             for s in range(2):
                 a, m = self.audio_encoder(d["audio"], attention_mask=(d["masks"][s] != 3))
                 aud.append(a); mid.append(m)
+            vis = [self.visual_encoder(d["lips"][0]()), self.visual_encoder(d["lips"][1]())]
             total, c1, c2, k1, k2 = self.hot_path_loss(vis, aud, mid, d["masks"], d["texts"], d["lens"])
         total.backward()
         if self._reducer is not None:
@@ -201,7 +230,7 @@ class MultimodalTrainer:
                     if torch.equal(att[0], att[1]):
                         shared, _ = self.audio_encoder(d["audio"], attention_mask=att[0])
                     for s in range(2):
-                        vis = self.visual_encoder(d["lips"][s])
+                        vis = self.visual_encoder(d["lips"][s]())
                         aud = shared if shared is not None else self.audio_encoder(d["audio"], attention_mask=att[s])[0]
                         t_enc = aud.shape[1]
                         mask_ds = F.interpolate(d["masks"][s].unsqueeze(1).float(), size=t_enc, mode="nearest").squeeze(1).long()
