@@ -80,7 +80,8 @@ class MultimodalTrainer:
             {"params": self.visual_encoder.parameters(), "lr": learning_rate},
             {"params": self.audio_encoder.parameters(), "lr": 2e-5},
             {"params": self.fusion_module.parameters(), "lr": learning_rate},
-            {"params": self.decoder1.parameters(), "lr": learning_rate}])
+            {"params": self.decoder1.parameters(), "lr": learning_rate}],
+            **({"fused": True} if str(device).startswith("cuda") else {}))   # same update rule, one kernel per group
         self.autocast_dtype = torch.bfloat16
         self.projection_layer = None
         self.verbose = True
