@@ -129,3 +129,37 @@ def test_decoder_loss_branch_and_state_dict_keys():
     fus = pkg.CrossAttentionFusion(512, 1024, 512)
     want = tp.FusionPort(512, 1024, 512).state_dict()
     assert {k: tuple(v.shape) for k, v in fus.state_dict().items()} == {k: tuple(v.shape) for k, v in want.items()}
+
+
+@pytest.mark.parametrize("B,Tv,Ta,E,H", [(3, 37, 51, 256, 4), (1, 5, 9, 128, 2), (5, 130, 77, 512, 4), (2, 257, 300, 256, 2)])
+def test_fused_path_odd_shapes_full_module_vs_torch_port(B, Tv, Ta, E, H):
+    """The one-call C++ path (head width a multiple of 64) and the persistent BiLSTM at ragged shapes: T not a multiple
+    of 8 or of the 128-row tile, T_a < T_v (up-sampling), B = 1, more than one key tile (T > 256), per-sample padding."""
+    pkg = _pkg()
+    torch.manual_seed(B * 100 + Tv)
+    ref = tp.FusionPort(64, 96, E, num_heads=H)
+    ours = pkg.CrossAttentionFusion(64, 96, E, num_heads=H)
+    ours.load_state_dict(ref.state_dict())
+    ours.cuda()
+    vis, aud = torch.randn(B, Tv, 64), torch.randn(B, Ta, 96)
+    mask = torch.ones(B, Ta, dtype=torch.long)
+    for b in range(B):
+        mask[b, Ta - 2 * b - 1:] = 3
+        mask[b, 2:4 + b] = 2
+        mask[b, Ta // 2:Ta // 2 + b] = 0
+    v1, a1 = vis.clone().requires_grad_(), aud.clone().requires_grad_()
+    y_ref, il_ref = ref(v1, a1, mask)
+    r = torch.randn_like(y_ref)
+    (y_ref * r).sum().backward()
+    v2, a2 = vis.cuda().requires_grad_(), aud.cuda().requires_grad_()
+    y, il = ours(v2, a2, mask=mask.cuda())
+    (y * r.cuda()).sum().backward()
+    assert il.cpu().tolist() == il_ref.tolist()
+    assert relerr(y, y_ref) < 3e-2
+    assert relerr(a2.grad, a1.grad) < 6e-2
+    assert relerr(v2.grad, v1.grad) < 6e-2
+    for (k, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+        if q.grad is None:
+            assert p.grad is None, k
+        else:
+            assert relerr(p.grad, q.grad) < 6e-2, k
