@@ -64,7 +64,6 @@ struct LstmFwdParams {
     float* cst;                  // [2][T][B][H] cell state, or nullptr
     unsigned* bar;               // [2] step counters, zeroed by the host
     int B, T;
-    int dbg;
 };
 
 // NB = batch tiles of 8 (B <= 8*NB)
@@ -355,352 +354,11 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(const LstmBwd
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Cluster variants (default when they fit): one thread-block cluster of 16 CTAs per direction.  h_t (forward) and the
-// gate gradients (backward) are broadcast straight into every CTA's shared memory (DSMEM, st.shared::cluster) and a
-// hardware cluster barrier replaces the atomic + poll in L2: ~1 us per step instead of ~2.5-3 us.
-constexpr int kClusterSize = 16;
-constexpr int kClThreads = 512;
-__device__ long long g_lstm_dbg[8];      // debug: accumulated cycles per phase of CTA 0 (lstm_dbg tuning knob)
-#define LSTM_DBG_MARK(k) do { if (dbg) { const long long now_ = clock64(); g_lstm_dbg[k] += now_ - tmark; tmark = now_; } } while (0)
-
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ unsigned cluster_rank() {
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t dsmem_addr(const void* local, unsigned rank) {
-    uint32_t la = (uint32_t)__cvta_generic_to_shared(local), ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
-    return ra;
-}
-__device__ __forceinline__ void dsmem_st16(uint32_t raddr, uint4 v) {
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-template <int H, int NB>
-__global__ void __launch_bounds__(kClThreads, 1) lstm_fwd_cluster_kernel(const LstmFwdParams p) {
-    constexpr int UN = H / kClusterSize;             // hidden units per CTA
-    constexpr int MT = UN / 16;                      // m16 tiles per gate
-    constexpr int KSPLIT = 16 / (4 * MT);            // warps sharing one (gate, m-tile), split over K
-    constexpr int KS = H / 16 / KSPLIT;              // k-steps per warp
-    constexpr int HS = H + 8;
-    constexpr int BP = 8 * NB;
-    constexpr int PP = (UN * BP + kClThreads - 1) / kClThreads;
-    constexpr int SEG = UN * 2 / 16;                 // 16-byte chunks of one batch row of my h slice
-    extern __shared__ __align__(16) unsigned char lstm_smem[];
-    __nv_bfloat16* hs = reinterpret_cast<__nv_bfloat16*>(lstm_smem);                          // [2][BP][HS]
-    float* red = reinterpret_cast<float*>(lstm_smem + (size_t)2 * BP * HS * 2);                // [KSPLIT][4][UN][BP]
-    __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(red + (size_t)KSPLIT * 4 * UN * BP);   // [BP][UN]
-    const int d = blockIdx.x / kClusterSize;
-    const unsigned rank = cluster_rank();
-    const int u0 = rank * UN;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gid = lane >> 2, tig = lane & 3;
-    const int gate = warp & 3, mt = (warp >> 2) % MT, ksp = warp / (4 * MT);
-    const int B = p.B, T = p.T;
-
-    uint32_t afrag[KS][4];
-    {
-        const __nv_bfloat16* W = p.whh + ((size_t)d * 4 * H + (size_t)gate * H + u0 + mt * 16) * H;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            const int k0 = (ksp * KS + ks) * 16 + tig * 2;
-            afrag[ks][0] = *reinterpret_cast<const uint32_t*>(W + (size_t)gid * H + k0);
-            afrag[ks][1] = *reinterpret_cast<const uint32_t*>(W + (size_t)(gid + 8) * H + k0);
-            afrag[ks][2] = *reinterpret_cast<const uint32_t*>(W + (size_t)gid * H + k0 + 8);
-            afrag[ks][3] = *reinterpret_cast<const uint32_t*>(W + (size_t)(gid + 8) * H + k0 + 8);
-        }
-    }
-    float creg[PP];
-#pragma unroll
-    for (int i = 0; i < PP; ++i) creg[i] = 0.f;
-    for (int i = tid; i < 2 * BP * HS; i += kClThreads) hs[i] = __float2bfloat16(0.f);
-    for (int i = tid; i < BP * UN; i += kClThreads) stage[i] = __float2bfloat16(0.f);
-    __syncthreads();
-    cluster_arrive();        // nobody writes into a peer's hs before that peer has zeroed it
-    cluster_wait();
-    const uint32_t hs_remote = dsmem_addr(hs, (unsigned)warp);      // warp w serves destination CTA w
-    const bool dbg = (p.dbg != 0) && blockIdx.x == 0 && tid == 0;
-    long long tmark = clock64();
-    if (dbg) for (int k = 0; k < 8; ++k) g_lstm_dbg[k] = 0;
-
-    float xnext[PP][4];                              // input projections, fetched one step ahead
-    auto load_x = [&](int step) {
-        const int tt = d ? (T - 1 - step) : step;
-#pragma unroll
-        for (int i = 0; i < PP; ++i) {
-            const int e = tid + kClThreads * i, u = e % UN, b = e / UN;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-                xnext[i][g] = (b < B && step < T) ? __ldg(p.xproj + ((size_t)b * T + tt) * 8 * H + (size_t)d * 4 * H + g * H + u0 + u) : 0.f;
-        }
-    };
-    load_x(0);
-    for (int s = 0; s < T; ++s) {
-        const int t = d ? (T - 1 - s) : s;
-        const __nv_bfloat16* hcur = hs + (size_t)(s & 1) * BP * HS;
-        float xg[PP][4], sv[PP][4];
-        __nv_bfloat16 hpv[PP];
-#pragma unroll
-        for (int i = 0; i < PP; ++i)
-#pragma unroll
-            for (int g = 0; g < 4; ++g) xg[i][g] = xnext[i][g];
-        load_x(s + 1);
-        LSTM_DBG_MARK(0);
-        if (s > 0) cluster_wait();                   // every CTA's h_{t-1} slice has landed in hs[s & 1]
-        LSTM_DBG_MARK(1);
-        float accp[4][NB][4];          // four independent accumulator chains (mma.sync latency), summed below
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4)
-#pragma unroll
-            for (int n = 0; n < NB; ++n)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) accp[c4][n][j] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            const int k0 = (ksp * KS + ks) * 16 + tig * 2;
-#pragma unroll
-            for (int n = 0; n < NB; ++n) {
-                const __nv_bfloat16* hb = hcur + (n * 8 + gid) * HS + k0;
-                mma_bf16_16816(accp[ks & 3][n], afrag[ks], *reinterpret_cast<const uint32_t*>(hb),
-                               *reinterpret_cast<const uint32_t*>(hb + 8));
-            }
-        }
-        float acc[NB][4];
-#pragma unroll
-        for (int n = 0; n < NB; ++n)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[n][j] = (accp[0][n][j] + accp[1][n][j]) + (accp[2][n][j] + accp[3][n][j]);
-        {
-            float* r = red + ((size_t)(ksp * 4 + gate) * UN + mt * 16) * BP;
-#pragma unroll
-            for (int n = 0; n < NB; ++n) {
-                const int bc = n * 8 + tig * 2;
-                r[gid * BP + bc] = acc[n][0]; r[gid * BP + bc + 1] = acc[n][1];
-                r[(gid + 8) * BP + bc] = acc[n][2]; r[(gid + 8) * BP + bc + 1] = acc[n][3];
-            }
-        }
-        __syncthreads();
-        LSTM_DBG_MARK(2);
-#pragma unroll
-        for (int i = 0; i < PP; ++i) {
-            const int e = tid + kClThreads * i, u = e % UN, b = e / UN;
-            if (b < B) {
-                float pre[4];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float v = xg[i][g];
-#pragma unroll
-                    for (int k = 0; k < KSPLIT; ++k) v += red[((size_t)(k * 4 + g) * UN + u) * BP + b];
-                    pre[g] = v;
-                }
-                const float ig = sigmoidf_(pre[0]), fg = sigmoidf_(pre[1]), gg = tanh_fast(pre[2]), og = sigmoidf_(pre[3]);
-                const float c = fg * creg[i] + ig * gg;
-                creg[i] = c;
-                const __nv_bfloat16 hb = __float2bfloat16(og * tanh_fast(c));
-                stage[b * UN + u] = hb;
-                sv[i][0] = ig; sv[i][1] = fg; sv[i][2] = gg; sv[i][3] = og;
-                hpv[i] = hcur[b * HS + u0 + u];      // read now: peers may overwrite this buffer right after the arrive
-            }
-        }
-        __syncthreads();
-        LSTM_DBG_MARK(3);
-        {   // my h_t slice -> hs[(s+1) & 1] of CTA `warp`
-            const uint32_t dst = hs_remote + (uint32_t)(((s + 1) & 1) * BP * HS * 2);
-            for (int e = lane; e < B * SEG; e += 32) {
-                const int b = e / SEG, q = e % SEG;
-                const uint4 v = *reinterpret_cast<const uint4*>(stage + b * UN + q * 8);
-                dsmem_st16(dst + (uint32_t)((b * HS + u0 + q * 8) * 2), v);
-            }
-        }
-        LSTM_DBG_MARK(4);
-        cluster_arrive();
-        LSTM_DBG_MARK(5);
-        // global stores (output and what backward needs) go out AFTER the arrive: its release must not wait for them
-#pragma unroll
-        for (int i = 0; i < PP; ++i) {
-            const int e = tid + kClThreads * i, u = e % UN, b = e / UN;
-            if (b < B) {
-                p.y[((size_t)b * T + t) * 2 * H + (size_t)d * H + u0 + u] = stage[b * UN + u];
-                if (p.gates) {
-                    float* gp = p.gates + (((size_t)d * T + t) * B + b) * 4 * H + u0 + u;
-                    gp[0] = sv[i][0]; gp[H] = sv[i][1]; gp[2 * H] = sv[i][2]; gp[3 * H] = sv[i][3];
-                    p.cst[(((size_t)d * T + t) * B + b) * H + u0 + u] = creg[i];
-                    p.hprev[((size_t)b * T + t) * 2 * H + (size_t)d * H + u0 + u] = hpv[i];
-                }
-            }
-        }
-        LSTM_DBG_MARK(6);
-    }
-    cluster_wait();          // no CTA leaves while peers may still write into its shared memory
-}
-
-template <int H, int NB>
-__global__ void __launch_bounds__(kClThreads, 1) lstm_bwd_cluster_kernel(const LstmBwdParams p) {
-    constexpr int UN = H / kClusterSize;
-    constexpr int MT = UN / 16;
-    constexpr int KSPLIT = 16 / MT;                  // warps splitting K = 4H for one m-tile
-    constexpr int KS = 4 * H / 16 / KSPLIT;
-    constexpr int GS = 4 * H + 8;
-    constexpr int BP = 8 * NB;
-    constexpr int PP = (UN * BP + kClThreads - 1) / kClThreads;
-    constexpr int SEG = UN * 2 / 16;                 // 16-byte chunks of one (batch, gate) segment of my slice
-    extern __shared__ __align__(16) unsigned char lstm_smem[];
-    __nv_bfloat16* dgs = reinterpret_cast<__nv_bfloat16*>(lstm_smem);                         // [2][BP][GS]
-    float* red = reinterpret_cast<float*>(lstm_smem + (size_t)2 * BP * GS * 2);                // [KSPLIT][UN][BP]
-    __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(red + (size_t)KSPLIT * UN * BP);   // [BP][4][UN]
-    const int d = blockIdx.x / kClusterSize;
-    const unsigned rank = cluster_rank();
-    const int u0 = rank * UN;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gid = lane >> 2, tig = lane & 3;
-    const int mt = warp % MT, ksp = warp / MT;
-    const int B = p.B, T = p.T;
-
-    uint32_t afrag[KS][4];
-    {
-        const __nv_bfloat16* W = p.whh + (size_t)d * 4 * H * H;         // W[k][u]
-        const int ub = u0 + mt * 16;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            const int k0 = (ksp * KS + ks) * 16 + tig * 2;
-            afrag[ks][0] = pack_bf16(W[(size_t)k0 * H + ub + gid], W[(size_t)(k0 + 1) * H + ub + gid]);
-            afrag[ks][1] = pack_bf16(W[(size_t)k0 * H + ub + gid + 8], W[(size_t)(k0 + 1) * H + ub + gid + 8]);
-            afrag[ks][2] = pack_bf16(W[(size_t)(k0 + 8) * H + ub + gid], W[(size_t)(k0 + 9) * H + ub + gid]);
-            afrag[ks][3] = pack_bf16(W[(size_t)(k0 + 8) * H + ub + gid + 8], W[(size_t)(k0 + 9) * H + ub + gid + 8]);
-        }
-    }
-    float dh_rec[PP], dc_carry[PP];
-#pragma unroll
-    for (int i = 0; i < PP; ++i) { dh_rec[i] = 0.f; dc_carry[i] = 0.f; }
-    for (int i = tid; i < 2 * BP * GS; i += kClThreads) dgs[i] = __float2bfloat16(0.f);
-    for (int i = tid; i < BP * 4 * UN; i += kClThreads) stage[i] = __float2bfloat16(0.f);
-    __syncthreads();
-    cluster_arrive();
-    cluster_wait();
-    const uint32_t dgs_remote = dsmem_addr(dgs, (unsigned)warp);
-
-    float nx[PP][7];                                 // saved gates / cell states / dy, fetched one step ahead
-    auto load_step = [&](int step) {
-        const int tt = d ? step : (T - 1 - step);
-        const int tp = d ? tt + 1 : tt - 1;
-#pragma unroll
-        for (int i = 0; i < PP; ++i) {
-            const int e = tid + kClThreads * i, u = e % UN, b = e / UN;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) nx[i][k] = 0.f;
-            if (b < B && step < T) {
-                const size_t gi = (((size_t)d * T + tt) * B + b) * 4 * H + u0 + u;
-                nx[i][0] = p.gates[gi]; nx[i][1] = p.gates[gi + H]; nx[i][2] = p.gates[gi + 2 * H]; nx[i][3] = p.gates[gi + 3 * H];
-                nx[i][4] = p.cst[(((size_t)d * T + tt) * B + b) * H + u0 + u];
-                nx[i][5] = (tp >= 0 && tp < T) ? p.cst[(((size_t)d * T + tp) * B + b) * H + u0 + u] : 0.f;
-                nx[i][6] = __bfloat162float(p.dy[((size_t)b * T + tt) * 2 * H + (size_t)d * H + u0 + u]);
-            }
-        }
-    };
-    load_step(0);
-    for (int s = 0; s < T; ++s) {
-        const int t = d ? s : (T - 1 - s);
-        float cur[PP][7];
-#pragma unroll
-        for (int i = 0; i < PP; ++i)
-#pragma unroll
-            for (int k = 0; k < 7; ++k) cur[i][k] = nx[i][k];
-        load_step(s + 1);
-#pragma unroll
-        for (int i = 0; i < PP; ++i) {
-            const int e = tid + kClThreads * i, u = e % UN, b = e / UN;
-            if (b < B) {
-                const float ig = cur[i][0], fg = cur[i][1], gg = cur[i][2], og = cur[i][3];
-                const float c = cur[i][4];
-                const float cp = cur[i][5];
-                const float dh = cur[i][6] + dh_rec[i];
-                const float tc = tanh_fast(c);
-                const float dc = dc_carry[i] + dh * og * (1.f - tc * tc);
-                const __nv_bfloat16 d_i = __float2bfloat16(dc * gg * ig * (1.f - ig));
-                const __nv_bfloat16 d_f = __float2bfloat16(dc * cp * fg * (1.f - fg));
-                const __nv_bfloat16 d_g = __float2bfloat16(dc * ig * (1.f - gg * gg));
-                const __nv_bfloat16 d_o = __float2bfloat16(dh * tc * og * (1.f - og));
-                dc_carry[i] = dc * fg;
-                __nv_bfloat16* so = stage + (size_t)b * 4 * UN + u;
-                so[0] = d_i; so[UN] = d_f; so[2 * UN] = d_g; so[3 * UN] = d_o;
-            }
-        }
-        auto flush_dG = [&]() {     // gate gradients of this step to HBM (for the weight-gradient GEMMs)
-#pragma unroll
-            for (int i = 0; i < PP; ++i) {
-                const int e = tid + kClThreads * i, u = e % UN, b = e / UN;
-                if (b < B) {
-                    __nv_bfloat16* go = p.dG + ((size_t)b * T + t) * 8 * H + (size_t)d * 4 * H + u0 + u;
-                    const __nv_bfloat16* so = stage + (size_t)b * 4 * UN + u;
-                    go[0] = so[0]; go[H] = so[UN]; go[2 * H] = so[2 * UN]; go[3 * H] = so[3 * UN];
-                }
-            }
-        };
-        if (s == T - 1) { flush_dG(); break; }       // uniform: every CTA leaves at the same step
-        __syncthreads();
-        {   // my gate-gradient slice of step t -> dgs[s & 1] of CTA `warp`
-            const uint32_t dst = dgs_remote + (uint32_t)((s & 1) * BP * GS * 2);
-            for (int e = lane; e < B * 4 * SEG; e += 32) {
-                const int b = e / (4 * SEG), g = (e / SEG) & 3, q = e % SEG;
-                const uint4 v = *reinterpret_cast<const uint4*>(stage + (size_t)b * 4 * UN + g * UN + q * 8);
-                dsmem_st16(dst + (uint32_t)((b * GS + g * H + u0 + q * 8) * 2), v);
-            }
-        }
-        cluster_arrive();
-        flush_dG();                                  // after the arrive: its release must not wait for these stores
-        cluster_wait();
-        const __nv_bfloat16* dcur = dgs + (size_t)(s & 1) * BP * GS;
-        float accp[4][NB][4];          // four independent accumulator chains (mma.sync latency), summed below
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4)
-#pragma unroll
-            for (int n = 0; n < NB; ++n)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) accp[c4][n][j] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            const int k0 = (ksp * KS + ks) * 16 + tig * 2;
-#pragma unroll
-            for (int n = 0; n < NB; ++n) {
-                const __nv_bfloat16* gb = dcur + (n * 8 + gid) * GS + k0;
-                mma_bf16_16816(accp[ks & 3][n], afrag[ks], *reinterpret_cast<const uint32_t*>(gb),
-                               *reinterpret_cast<const uint32_t*>(gb + 8));
-            }
-        }
-        float acc[NB][4];
-#pragma unroll
-        for (int n = 0; n < NB; ++n)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[n][j] = (accp[0][n][j] + accp[1][n][j]) + (accp[2][n][j] + accp[3][n][j]);
-        {
-            float* r = red + ((size_t)ksp * UN + mt * 16) * BP;
-#pragma unroll
-            for (int n = 0; n < NB; ++n) {
-                const int bc = n * 8 + tig * 2;
-                r[gid * BP + bc] = acc[n][0]; r[gid * BP + bc + 1] = acc[n][1];
-                r[(gid + 8) * BP + bc] = acc[n][2]; r[(gid + 8) * BP + bc + 1] = acc[n][3];
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < PP; ++i) {
-            const int e = tid + kClThreads * i, u = e % UN, b = e / UN;
-            float v = 0.f;
-            if (b < B) {
-#pragma unroll
-                for (int k = 0; k < KSPLIT; ++k) v += red[((size_t)k * UN + u) * BP + b];
-            }
-            dh_rec[i] = v;
-        }
-        __syncthreads();
-    }
-    cluster_arrive();        // pairs with the wait below: nobody exits while a peer may still address its shared memory
-    cluster_wait();
-}
+// (A thread-block-cluster variant — 16 CTAs per direction, h_t / gate gradients broadcast through DSMEM with
+// st.shared::cluster and barrier.cluster arrive/wait instead of the L2 atomic + poll — was built and measured in round 1:
+// 655 us vs 656 us forward and 1140 us vs 956 us backward per 2-layer call at B=8, T=150.  The release of
+// barrier.cluster.arrive waits ~1300 cycles for the DSMEM stores, as long as the L2 round trips it replaces, so the
+// cooperative kernels above are the only path; see git history for the variant.)
 
 // ---- small helpers
 struct LCastJob { const float* src; __nv_bfloat16* dst; long long n; };
@@ -806,73 +464,11 @@ static int launch_bwd(const LstmBwdParams& p, cudaStream_t st) {
     return (int)cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_bwd_kernel<H, NB>), dim3(2 * H / kLstmUnits),
                                             dim3(kLstmThreads), args, smem, st);
 }
-template <int H, int NB>
-static int launch_fwd_cluster(const LstmFwdParams& p, cudaStream_t st) {
-    constexpr int UN = H / kClusterSize, MT = UN / 16, KSPLIT = 16 / (4 * MT), BP = 8 * NB;
-    const size_t smem = (size_t)2 * BP * (H + 8) * 2 + (size_t)KSPLIT * 4 * UN * BP * 4 + (size_t)BP * UN * 2;
-    static int state = 0;          // 0 unknown, 1 usable, -1 not usable on this device / configuration
-    if (state < 0) return -1000;
-    if (state == 0) {
-        if (cudaFuncSetAttribute(lstm_fwd_cluster_kernel<H, NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
-            cudaFuncSetAttribute(lstm_fwd_cluster_kernel<H, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            state = -1;
-            return -1000;
-        }
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * kClusterSize); cfg.blockDim = dim3(kClThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = kClusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_fwd_cluster_kernel<H, NB>, p);
-    if (e != cudaSuccess) { cudaGetLastError(); if (state == 0) state = -1; return -1000; }
-    state = 1;
-    return 0;
-}
-template <int H, int NB>
-static int launch_bwd_cluster(const LstmBwdParams& p, cudaStream_t st) {
-    constexpr int UN = H / kClusterSize, MT = UN / 16, KSPLIT = 16 / MT, BP = 8 * NB;
-    const size_t smem = (size_t)2 * BP * (4 * H + 8) * 2 + (size_t)KSPLIT * UN * BP * 4 + (size_t)BP * 4 * UN * 2;
-    static int state = 0;
-    if (state < 0 || smem > 200 * 1024) return -1000;
-    if (state == 0) {
-        if (cudaFuncSetAttribute(lstm_bwd_cluster_kernel<H, NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
-            cudaFuncSetAttribute(lstm_bwd_cluster_kernel<H, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            state = -1;
-            return -1000;
-        }
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * kClusterSize); cfg.blockDim = dim3(kClThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = kClusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_bwd_cluster_kernel<H, NB>, p);
-    if (e != cudaSuccess) { cudaGetLastError(); if (state == 0) state = -1; return -1000; }
-    state = 1;
-    return 0;
-}
 static int dispatch_fwd(int H, int NB, const LstmFwdParams& p, cudaStream_t st) {
-    if (avctc_tuning_get("lstm_cluster", 1) != 0 && NB <= 2) {       // DSMEM variant; falls through if it cannot launch
-        int rc = -1000;
-        if (H == 512) rc = (NB == 1) ? launch_fwd_cluster<512, 1>(p, st) : launch_fwd_cluster<512, 2>(p, st);
-        else rc = (NB == 1) ? launch_fwd_cluster<256, 1>(p, st) : launch_fwd_cluster<256, 2>(p, st);
-        if (rc != -1000) return rc;
-    }
     if (H == 512) { if (NB == 1) return launch_fwd<512, 1>(p, st); if (NB == 2) return launch_fwd<512, 2>(p, st); return launch_fwd<512, 4>(p, st); }
     if (NB == 1) return launch_fwd<256, 1>(p, st); if (NB == 2) return launch_fwd<256, 2>(p, st); return launch_fwd<256, 4>(p, st);
 }
 static int dispatch_bwd(int H, int NB, const LstmBwdParams& p, cudaStream_t st) {
-    if (avctc_tuning_get("lstm_cluster", 1) != 0 && NB <= 2) {
-        int rc = -1000;
-        if (H == 512) rc = (NB == 1) ? launch_bwd_cluster<512, 1>(p, st) : launch_bwd_cluster<512, 2>(p, st);
-        else rc = (NB == 1) ? launch_bwd_cluster<256, 1>(p, st) : launch_bwd_cluster<256, 2>(p, st);
-        if (rc != -1000) return rc;
-    }
     if (H == 512) { if (NB == 1) return launch_bwd<512, 1>(p, st); if (NB == 2) return launch_bwd<512, 2>(p, st); return launch_bwd<512, 4>(p, st); }
     if (NB == 1) return launch_bwd<256, 1>(p, st); if (NB == 2) return launch_bwd<256, 2>(p, st); return launch_bwd<256, 4>(p, st);
 }
@@ -882,10 +478,6 @@ static int dispatch_bwd(int H, int NB, const LstmBwdParams& p, cudaStream_t st) 
 }  // namespace avctc
 
 using namespace avctc;
-
-extern "C" __attribute__((visibility("default"))) int avctc_debug_lstm_phases(long long* host_out8) {
-    return (int)cudaMemcpyFromSymbol(host_out8, g_lstm_dbg, sizeof(long long) * 8);
-}
 
 // params / grads: 16 pointers in nn.LSTM's flat order
 //   l0: weight_ih, weight_hh, bias_ih, bias_hh, then the same four with suffix _reverse; then l1 likewise.
@@ -939,7 +531,7 @@ extern "C" int avctc_bilstm_forward(const void* x_bf16, int B, int T, int In, in
         fp.hprev = need_grad ? s.l[l].hprev : nullptr;
         fp.gates = need_grad ? s.l[l].gates : nullptr;
         fp.cst = need_grad ? s.l[l].cst : nullptr;
-        fp.bar = w.bar; fp.B = B; fp.T = T; fp.dbg = avctc_tuning_get("lstm_dbg", 0);
+        fp.bar = w.bar; fp.B = B; fp.T = T;
         LSTM_TRY(dispatch_fwd(H, d.NB, fp, st));
         xin = fp.y;
     }
