@@ -169,20 +169,24 @@ def _install_feature_cache(fe):
     trainer.py:94-95).  The conv feature extractor is deterministic (no dropout) and frozen, so its output for an
     unchanged input tensor is reused instead of recomputed: identical values, one conv stack pass per step instead of
     two.  Installed as an instance-level forward wrapper, so module structure and state_dict keys do not change."""
+    import weakref
     inner = fe.forward
-    state = {"key": None, "out": None}
+    state = {"ref": None, "key": None, "out": None}
 
     def cached_forward(input_values):
         frozen = not any(p.requires_grad for p in fe.parameters()) and not getattr(fe, "_requires_grad", False)
         if not frozen or torch.is_grad_enabled() and input_values.requires_grad:
-            state["key"] = None
+            state["ref"] = None
             return inner(input_values)
-        key = (input_values.data_ptr(), input_values._version, tuple(input_values.shape), input_values.dtype,
-               torch.is_autocast_enabled(), fe.training)
-        if state["key"] != key:
+        # identity of the live tensor OBJECT (a weak reference) + its version counter: a later batch that happens to be
+        # allocated at the same address is a different object, and in-place edits bump the version
+        key = (input_values._version, tuple(input_values.shape), input_values.dtype, torch.is_autocast_enabled(),
+               fe.training)
+        same = state["ref"] is not None and state["ref"]() is input_values and state["key"] == key
+        if not same:
             with torch.no_grad():
                 state["out"] = inner(input_values)
-            state["key"] = key
+            state["ref"], state["key"] = weakref.ref(input_values), key
         return state["out"]
 
     fe.forward = cached_forward

@@ -59,3 +59,17 @@ def test_audio_feature_cache_and_no_grad_through_frozen_extractor():
     (out.sum() + mid.sum()).backward()
     grads = {n for n, p in aud.named_parameters() if p.grad is not None}
     assert grads and all("encoder.layers." in n for n in grads)
+
+
+def test_audio_feature_cache_is_keyed_on_object_identity_not_address():
+    """A new batch is often allocated at the address of the freed previous one with the same version counter (0):
+    the cache must still recompute."""
+    aud = _tiny_audio()
+    aud.eval()
+    m = torch.ones(1, 4000, dtype=torch.bool)
+    outs = []
+    for seed in (1, 2, 3):
+        x = torch.randn(1, 4000, generator=torch.Generator().manual_seed(seed)) * 0.1      # same shape, often same address
+        outs.append(aud(x, attention_mask=m)[0].clone())
+        del x
+    assert not torch.allclose(outs[0], outs[1]) and not torch.allclose(outs[1], outs[2])
