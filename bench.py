@@ -341,6 +341,16 @@ def bench_fusion(device, peaks, iters=10):
             fwd()
         t_g, _ = event_time(g.replay, iters, 3, flush, device)
         out.update(graph_fwd_ms=t_g, graph_tensor_frac_fwd=flop_f / t_g / 1e9 / peaks["tf_burst"])
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fwd_bwd()
+        torch.cuda.current_stream(device).wait_stream(side)
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2):
+            fwd_bwd()
+        t_g2, _ = event_time(g2.replay, iters, 3, flush, device)
+        out.update(graph_fwd_bwd_ms=t_g2, graph_tensor_frac_fwd_bwd=3 * flop_f / t_g2 / 1e9 / peaks["tf_burst"])
     except Exception as e:          # capture is a measurement aid, never a requirement
         out.update(graph_fwd_ms=None, graph_error=str(e)[:120])
     return out

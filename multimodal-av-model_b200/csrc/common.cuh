@@ -97,6 +97,13 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor grid has
+// completed and its memory is visible, pdl_launch_dependents() lets the successor be scheduled early.  Both are no-ops
+// for a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ int ld_volatile_shared_s32(const int* p) {
     int v;
     unsigned s = (unsigned)__cvta_generic_to_shared(p);
@@ -136,6 +143,20 @@ __device__ __forceinline__ int stage_row(const float* grow, int V, float* buf, i
 }
 
 }  // namespace avctc
+
+// host: launch with the PDL attribute (falls back to a plain launch when the knob "pdl" is 0)
+int avctc_tuning_get(const char* key, int dflt);
+template <typename... KArgs, typename... Args>
+static inline cudaError_t avctc_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                           Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = avctc_tuning_get("pdl", 1) ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // process-global tuning knobs (c_api.cu)
 int avctc_tuning_get(const char* key, int dflt);

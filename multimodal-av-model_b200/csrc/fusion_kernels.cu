@@ -234,6 +234,8 @@ __global__ void resample_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int 
 // one warp per row; S fp32 [rows][Tp] (first T valid) -> P bf16 [rows][Tp], pad columns written as 0
 __global__ void softmax_fwd_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, long long rows, int T,
                                    int Tp) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -251,6 +253,8 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ S, __nv_bfloat16* _
 // dS = P * (dP - sum_k dP*P)
 __global__ void softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, const float* __restrict__ dP,
                                    __nv_bfloat16* __restrict__ dS, long long rows, int T, int Tp) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -383,17 +387,16 @@ extern "C" int avctc_resample_backward(const void* dout_bf16, int B, int Ta, int
 extern "C" int avctc_softmax_forward(const float* S, void* P_bf16, long long rows, int T, int Tp, void* stream) {
     if (!S || !P_bf16 || rows <= 0 || T <= 0 || Tp < T) return AVCTC_ERR_BAD_ARG;
     const int wpb = 8;
-    softmax_fwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        S, reinterpret_cast<__nv_bfloat16*>(P_bf16), rows, T, Tp);
-    return (int)cudaGetLastError();
+    return (int)avctc_launch_pdl(softmax_fwd_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0,
+                                 reinterpret_cast<cudaStream_t>(stream), S, reinterpret_cast<__nv_bfloat16*>(P_bf16), rows, T, Tp);
 }
 extern "C" int avctc_softmax_backward(const void* P_bf16, const float* dP, void* dS_bf16, long long rows, int T, int Tp,
                                       void* stream) {
     if (!P_bf16 || !dP || !dS_bf16 || rows <= 0 || T <= 0 || Tp < T) return AVCTC_ERR_BAD_ARG;
     const int wpb = 8;
-    softmax_bwd_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(P_bf16), dP, reinterpret_cast<__nv_bfloat16*>(dS_bf16), rows, T, Tp);
-    return (int)cudaGetLastError();
+    return (int)avctc_launch_pdl(softmax_bwd_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0,
+                                 reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(P_bf16), dP,
+                                 reinterpret_cast<__nv_bfloat16*>(dS_bf16), rows, T, Tp);
 }
 
 extern "C" int avctc_colsum(const void* X, int dtype, long long M, int N, long long ld, float* out, int accumulate,

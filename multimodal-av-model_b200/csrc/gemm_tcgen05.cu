@@ -140,10 +140,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int kb0 = split * kb_per;
     const int num_kb = max(0, min(total_kb, kb0 + kb_per) - kb0);   // this CTA's share of the reduction
 
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + kBN) {      // per-column bias of this N tile (zero when absent / not the leading split)
-        const int i = threadIdx.x - 64;
-        bias_s[i] = (split == 0 && p.bias_mode == 1 && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
-    }
+    pdl_launch_dependents();          // the next kernel of the stream may be scheduled; it waits for this grid itself
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
         mbar_init(tmem_full, 1);
@@ -160,6 +157,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     if (threadIdx.x == 0) GEMM_DBG(1);
+    pdl_wait();                       // everything above overlapped the predecessor; global memory is touched from here on
 
     if (warp == 0) {
         if (lane == 0) {   // ===== TMA producer =====
@@ -214,6 +212,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         __syncwarp();
     } else {               // ===== epilogue: TMEM -> registers -> shared staging -> coalesced global =====
+        if (threadIdx.x < 64 + kBN) {         // per-column bias of this N tile (zero when absent / not the leading split)
+            const int i = threadIdx.x - 64;
+            bias_s[i] = (split == 0 && p.bias_mode == 1 && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         mbar_wait(tmem_full, 0);
         if (threadIdx.x == 64) GEMM_DBG(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -424,6 +427,5 @@ int avctc_gemm_launch(const avctc_gemm_operand* a, const avctc_gemm_operand* b, 
         configured = true;
     }
     dim3 grid((M + kBM - 1) / kBM, (N + kBN - 1) / kBN, batch * p.splits);
-    gemm_bf16_kernel<<<grid, kGemmThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(ma, mb, p);
-    return (int)cudaGetLastError();
+    return (int)avctc_launch_pdl(gemm_bf16_kernel, grid, dim3(kGemmThreads), smem, reinterpret_cast<cudaStream_t>(stream), ma, mb, p);
 }

@@ -98,7 +98,13 @@ class VisualEncoder(nn.Module):
         taps = xp.unfold(1, kt, 1)                                                    # [B, T, H, W, kt] (view)
         taps = taps.permute(0, 1, 4, 2, 3).reshape(b * t, kt, h, w)                   # temporal taps as channels
         taps = taps.contiguous(memory_format=torch.channels_last)
-        w2 = conv.weight[:, 0]                                                        # [64, kt, 7, 7]
+        w2 = conv.weight
+        if not w2.requires_grad and torch.is_autocast_enabled(w2.device.type) and w2.dtype == torch.float32:
+            key = (w2._version, w2.data_ptr(), torch.get_autocast_dtype(w2.device.type))
+            if getattr(self, "_front_w", (None,))[0] != key:                          # frozen: cast once, not per step
+                self._front_w = (key, w2.detach().to(key[2]))
+            w2 = self._front_w[1]
+        w2 = w2[:, 0]                                                                 # [64, kt, 7, 7]
         y = F.conv2d(taps, w2, None, stride=conv.stride[1:], padding=conv.padding[1:])
         if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
@@ -147,7 +153,7 @@ class AudioEncoder(nn.Module):
         if freeze:
             self.model.requires_grad_(False)
 
-    def forward(self, x, attention_mask=None):
+    def forward(self, x, attention_mask=None, host_lengths=None):
         # HF marks the conv feature extractor's output as requiring grad in train mode (a gradient-checkpointing
         # aid) unless freeze_feature_encoder() was called; the reference only sets requires_grad=False on the
         # parameters (main.py:26-31), so autograd back-propagates through seven frozen conv layers for nothing.
@@ -159,9 +165,105 @@ class AudioEncoder(nn.Module):
             _install_feature_cache(fe)
         if attention_mask is not None:
             attention_mask = attention_mask.long()
-        out = self.model(input_values=x, attention_mask=attention_mask, return_dict=True)
-        middle = torch.stack(out.hidden_states[6:10], dim=0).mean(dim=0)
-        return out.last_hidden_state, middle
+        if self.sync_free and self._sync_free_supported():
+            last, hidden_states = self._forward_sync_free(x, attention_mask, host_lengths)
+        else:
+            out = self.model(input_values=x, attention_mask=attention_mask, return_dict=True)
+            last, hidden_states = out.last_hidden_state, out.hidden_states
+        middle = torch.stack(hidden_states[6:10], dim=0).mean(dim=0)
+        return last, middle
+
+    # -------------------------------------------------------------------------------------- sync-free forward
+    # Wav2Vec2Model.forward blocks the host on the GPU up to three times per call in train mode with an attention
+    # mask: SpecAugment reads the utterance lengths back (`attention_mask.sum(-1).tolist()`), writes the mask
+    # embedding through a boolean index (`nonzero`), and the SDPA mask builder asks `padding_mask.all()`.  Each one
+    # drains the queue, so the host cannot enqueue the 24 (launch-bound) transformer layers while the GPU is still busy
+    # with the convolutional front ends.  `_forward_sync_free` runs the SAME submodules in the SAME order with the same
+    # random draws (numpy for SpecAugment, torch.rand([]) for LayerDrop, the CUDA generator for dropout) but takes the
+    # lengths from the host copy of the mask and applies the masks with where/masked_fill.
+    sync_free = True
+
+    def _sync_free_supported(self):
+        m = self.model
+        cfg = m.config
+        enc = m.encoder
+        return (getattr(cfg, "_attn_implementation", None) == "sdpa" and getattr(m, "adapter", None) is None
+                and not getattr(enc, "gradient_checkpointing", False)
+                and type(enc).__name__ in ("Wav2Vec2Encoder", "Wav2Vec2EncoderStableLayerNorm"))
+
+    def prefetch_features(self, x):
+        """Enqueue the (frozen, cached) convolutional feature extractor for waveform tensor `x` now, so that later
+        forward() calls on the same tensor find its output ready.  No-op when the extractor is trainable."""
+        fe = self.model.feature_extractor
+        if not hasattr(fe, "_avctc_cached"):
+            if getattr(fe, "_requires_grad", False) and not any(p.requires_grad for p in fe.parameters()):
+                fe._requires_grad = False
+            _install_feature_cache(fe)
+        fe(x)
+
+    def _forward_sync_free(self, x, attention_mask, host_lengths):
+        from transformers.models.wav2vec2.modeling_wav2vec2 import _compute_mask_indices
+        m = self.model
+        cfg = m.config
+        extract = m.feature_extractor(x).transpose(1, 2)
+        B, T = extract.shape[0], extract.shape[1]
+        mask2d = None
+        if attention_mask is not None:
+            if host_lengths is None:                               # no host copy of the lengths: one read-back
+                host_lengths = attention_mask.sum(-1).cpu()
+            host_lengths = torch.as_tensor(host_lengths, dtype=torch.long).cpu()
+            # upstream drops the attention mask when nothing is padded (`padding_mask.all()`, a GPU read-back, in
+            # masking_utils); the host lengths answer the same question
+            padded = bool((host_lengths < attention_mask.shape[1]).any())
+            mask2d = m._get_feature_vector_attention_mask(T, attention_mask, add_adapter=False)
+        hidden, extract = m.feature_projection(extract)
+        # ---- SpecAugment (Wav2Vec2Model._mask_hidden_states) ----
+        if getattr(cfg, "apply_spec_augment", True) and m.training:
+            if cfg.mask_time_prob > 0:
+                cpu_mask = None
+                if attention_mask is not None:
+                    lens = m._get_feat_extract_output_lengths(host_lengths)
+                    cpu_mask = (torch.arange(T)[None, :] < lens.to(torch.long)[:, None])
+                idx = _compute_mask_indices((B, T), mask_prob=cfg.mask_time_prob, mask_length=cfg.mask_time_length,
+                                            attention_mask=cpu_mask, min_masks=cfg.mask_time_min_masks)
+                idx = _to_device_async(torch.from_numpy(idx), hidden.device)
+                hidden = torch.where(idx.unsqueeze(-1), m.masked_spec_embed.to(hidden.dtype), hidden)
+            if cfg.mask_feature_prob > 0:
+                idx = _compute_mask_indices((B, hidden.shape[2]), mask_prob=cfg.mask_feature_prob,
+                                            mask_length=cfg.mask_feature_length, min_masks=cfg.mask_feature_min_masks)
+                idx = _to_device_async(torch.from_numpy(idx), hidden.device)
+                hidden = hidden.masked_fill(idx[:, None, :], 0)
+        # ---- Wav2Vec2Encoder(.StableLayerNorm).forward ----
+        enc = m.encoder
+        stable = type(enc).__name__ == "Wav2Vec2EncoderStableLayerNorm"
+        mask4d = None
+        if mask2d is not None:
+            hidden = hidden.masked_fill(~mask2d.unsqueeze(-1), 0)                # padded frames output 0
+            if padded:
+                mask4d = mask2d[:, None, None, :].expand(B, 1, T, T)             # SDPA: True = attend to that key
+        pos = enc.pos_conv_embed(hidden)
+        hidden = hidden + pos
+        if not stable:
+            hidden = enc.layer_norm(hidden)
+        hidden = enc.dropout(hidden)
+        all_hidden = ()
+        for layer in enc.layers:
+            all_hidden = all_hidden + (hidden,)
+            draw = torch.rand([])                                                 # LayerDrop: host draw, as upstream
+            skip = enc.training and bool(draw < cfg.layerdrop)
+            if not skip:
+                hidden = layer(hidden, attention_mask=mask4d, output_attentions=False)[0]
+        if stable:
+            hidden = enc.layer_norm(hidden)
+        all_hidden = all_hidden + (hidden,)
+        return hidden, all_hidden
+
+
+def _to_device_async(t, device):
+    """Small host tensor -> device without a stream synchronise (a pageable source makes the copy blocking)."""
+    if device.type == "cuda":
+        t = t.pin_memory()
+    return t.to(device, non_blocking=True)
 
 
 def _install_feature_cache(fe):
@@ -191,6 +293,58 @@ def _install_feature_cache(fe):
 
     fe.forward = cached_forward
     fe._avctc_cached = True
+
+
+def install_frozen_cast_cache(root):
+    """Under autocast every use of an fp32 weight launches a cast kernel; the autocast weight cache only covers
+    parameters that require grad, so the FROZEN encoders (main.py:100-106: all of the visual encoder, all of wav2vec2
+    but four layers) re-cast ~850 tensors per step, each a launch the host has to build.  For every Linear / Conv /
+    PReLU under `root` whose own parameters are all frozen, keep the lower-precision copy of weight and bias and hand
+    it to the module's forward; autocast then finds the dtype it wants and launches nothing.  The copy is the very
+    rounding autocast applies, keyed on the parameter's version counter and storage so load_state_dict / in-place edits
+    refresh it; a module whose parameters (again) require grad takes the normal path.  Parameters, state_dict and
+    module structure are untouched (instance-level forward wrapper)."""
+    kinds = (nn.Linear, nn.Conv1d, nn.Conv2d, nn.Conv3d, nn.PReLU)
+    count = 0
+    for mod in root.modules():
+        if not isinstance(mod, kinds) or hasattr(mod, "_avctc_cast_cache") or hasattr(mod, "parametrizations"):
+            continue
+        _wrap_cast_cache(mod)
+        count += 1
+    return count
+
+
+def _wrap_cast_cache(mod):
+    inner = mod.forward
+    cache = {}
+
+    def forward(*args, **kwargs):
+        params = mod._parameters
+        w = params.get("weight")
+        if w is None or w.dtype != torch.float32 or not torch.is_autocast_enabled(w.device.type):
+            return inner(*args, **kwargs)
+        b = params.get("bias")
+        if w.requires_grad or (b is not None and b.requires_grad):
+            return inner(*args, **kwargs)
+        dt = torch.get_autocast_dtype(w.device.type)
+        saved = {}
+        for name, p in (("weight", w), ("bias", b)):
+            if p is None or p.dtype != torch.float32:
+                continue
+            key = (p._version, p.data_ptr(), dt)
+            hit = cache.get(name)
+            if hit is None or hit[0] != key:
+                hit = (key, p.detach().to(dt))
+                cache[name] = hit
+            saved[name] = p
+            params[name] = hit[1]
+        try:
+            return inner(*args, **kwargs)
+        finally:
+            params.update(saved)
+
+    mod.forward = forward
+    mod._avctc_cast_cache = cache
 
 
 def unfreeze_middle_layers(model):

@@ -64,6 +64,8 @@ def _log_softmax_again(lp):
 
 
 class MultimodalTrainer:
+    cache_frozen_casts = True       # encoders.install_frozen_cast_cache on the two encoders (frozen weights only)
+
     def __init__(self, visual_encoder, audio_encoder, fusion_module, decoder1, tokenizer, learning_rate=1e-4,
                  device="cuda", lambda_=0.1):
         self.visual_encoder = visual_encoder.to(device)
@@ -83,9 +85,14 @@ class MultimodalTrainer:
             {"params": self.decoder1.parameters(), "lr": learning_rate}],
             **({"fused": True} if str(device).startswith("cuda") else {}))   # same update rule, one kernel per group
         self.autocast_dtype = torch.bfloat16
+        if self.cache_frozen_casts:
+            from .encoders import install_frozen_cast_cache
+            for m in (self.visual_encoder, self.audio_encoder):
+                install_frozen_cast_cache(m)
         self.projection_layer = None
         self.verbose = True
         self.beam_width = 5                       # trainer.py:230,237
+        self.gpu_heavy_first = False              # train_step enqueue order (see there); measured slower on B200, kept as a switch
         self.world_size = dist.get_world_size() if dist.is_initialized() else 1
         self._reducer = None
         if self.world_size > 1:
@@ -148,6 +155,15 @@ class MultimodalTrainer:
         return dict(lips=[lip("lip1"), lip("lip2")], audio=out["audio"], masks=[out["mask1"], out["mask2"]],
                     texts=[out["text1"], out["text2"]], lens=[out["text1_lengths"], out["text2_lengths"]])
 
+    @staticmethod
+    def _host_lengths(batch, key):
+        """Utterance lengths (samples that are not padding, label 3) from the HOST copy of a mask, when there is one:
+        lets the audio encoder draw its SpecAugment spans without reading the lengths back from the GPU."""
+        m = batch.get(key)
+        if torch.is_tensor(m):          # a device-resident mask is read back HERE, before the step's work is enqueued
+            return {"host_lengths": (m != 3).sum(-1).cpu()}
+        return {}
+
     def _ensure_projection(self, D):
         if self.projection_layer is None:           # trainer.py:105-106: created lazily, once per epoch
             self.projection_layer = nn.Linear(D, 128).to(self.device)
@@ -175,12 +191,23 @@ class MultimodalTrainer:
         Returns the detached total loss (device tensor; no host sync)."""
         self.optimizer.zero_grad()
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=str(self.device).startswith("cuda")):
+            kw = [{}, {}]
+            if hasattr(self.audio_encoder, "prefetch_features"):
+                kw = [self._host_lengths(batch, "mask1"), self._host_lengths(batch, "mask2")]
             d = self._to_dev(batch)
+            # Enqueue order.  Default: audio encoder (small H2D) first so that the two 44 MB lip clips copy behind it.
+            # gpu_heavy_first enqueues the conv front ends before the ~1500 small transformer launches; on B200 the
+            # step is GPU-bound (~47 ms of kernels) and that order measured 3 ms slower (tools/exp_step.py).
+            heavy_first = self.gpu_heavy_first and hasattr(self.audio_encoder, "prefetch_features")
+            if heavy_first:
+                self.audio_encoder.prefetch_features(d["audio"])
+                vis = [self.visual_encoder(d["lips"][0]()), self.visual_encoder(d["lips"][1]())]
             aud, mid = [], []
             for s in range(2):
-                a, m = self.audio_encoder(d["audio"], attention_mask=(d["masks"][s] != 3))
+                a, m = self.audio_encoder(d["audio"], attention_mask=(d["masks"][s] != 3), **kw[s])
                 aud.append(a); mid.append(m)
-            vis = [self.visual_encoder(d["lips"][0]()), self.visual_encoder(d["lips"][1]())]
+            if not heavy_first:
+                vis = [self.visual_encoder(d["lips"][0]()), self.visual_encoder(d["lips"][1]())]
             total, c1, c2, k1, k2 = self.hot_path_loss(vis, aud, mid, d["masks"], d["texts"], d["lens"])
         total.backward()
         if self._reducer is not None:

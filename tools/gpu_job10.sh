@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench2.json 2> gpurun_out/bench2.err; tail -n 3 gpurun_out/bench2.err
-python tools/profile_hot.py full > gpurun_out/prof_full2.log 2>&1
-head -c 600 gpurun_out/bench2.json; echo; grep -o '"hot_path": {[^}]*}' gpurun_out/bench2.json; grep -o '"beam": {[^}]*}' gpurun_out/bench2.json; grep -o '"roofline": {[^}]*}' gpurun_out/bench2.json;  grep -o '"cpu_baseline": {[^}]*}' gpurun_out/bench2.json
+timeout 300 python bench.py --workload fusion --steps 3 --warmup 3 > gpurun_out/bench_fusion.json 2> gpurun_out/bench_fusion.err; tail -n 3 gpurun_out/bench_fusion.err; cat gpurun_out/bench_fusion.json
+timeout 300 python tools/profile_fusion.py > gpurun_out/prof_fusion.txt 2>&1; tail -n 60 gpurun_out/prof_fusion.txt

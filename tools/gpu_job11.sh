@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 4 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
-echo "rc=$?"; tail -n 5 gpurun_out/bench_n2.err; head -c 1500 gpurun_out/bench_n2.json
+timeout 600 python -m pytest tests/test_trainer_gpu.py tests/test_fusion_gpu.py -x -q > gpurun_out/t_tr.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t_tr.log
+tail -n 4 gpurun_out/t_tr.log
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err; tail -n 3 gpurun_out/bench_train.err; cat gpurun_out/bench_train.json

@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 40 -c 3 -o gpurun_out/gemm_r1 -f \
-    python tools/profile_fusion.py > gpurun_out/ncu_gemm.log 2>&1
-tail -n 3 gpurun_out/ncu_gemm.log
+timeout 600 python -m pytest tests/test_fusion_gpu.py tests/test_gemm_gpu.py tests/test_trainer_gpu.py tests/test_lstm_gpu.py -x -q > gpurun_out/t_fus.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t_fus.log
+tail -n 8 gpurun_out/t_fus.log
+timeout 300 python bench.py --workload fusion --steps 3 --warmup 3 > gpurun_out/bench_fusion.json 2> gpurun_out/bench_fusion.err; tail -n 3 gpurun_out/bench_fusion.err; cat gpurun_out/bench_fusion.json
