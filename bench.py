@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — the AV-CTC hot path on B200, next to the reference's CPU path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|ctc|beam|fusion]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|ctc|beam|fusion|infonce]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -356,6 +356,48 @@ def bench_fusion(device, peaks, iters=10):
     return out
 
 
+def bench_infonce(device, peaks, iters=10):
+    """SURVEY.md §8(d) 'InfoNCE (kernel 3)': contrastive_loss_with_mask fwd+bwd at config-4 sizes (8 x 249 rows of 1024
+    features, Linear 1024->128 projection, sample-rate masks down-sampled to frame rate), bf16 features as under
+    autocast.  HBM-bound on reading the feature rows once: algorithmic bytes = rows*1024*e + the projection weight.
+    Beside it, the same loss written with stock torch CUDA ops (the reference's formulation, contrastive.py:13-44)."""
+    import torch.nn.functional as F
+    from multimodal_av_model_b200 import contrastive_loss_with_mask
+    from multimodal_av_model_b200.synthetic import make_features
+    f = make_features(pairs=PAIRS_PER_GPU, t_v=T_V, t_enc=249, seed=1234, dtype=torch.bfloat16)
+    x = f["middle"][0].to(device).requires_grad_()
+    mask = F.interpolate(f["masks"][0].to(device).unsqueeze(1).float(), size=249, mode="nearest").squeeze(1).long().reshape(-1)
+    torch.manual_seed(0)
+    proj = torch.nn.Linear(1024, 128).to(device)
+    flush = l2_flusher(device)
+
+    def ours():
+        x.grad = None; proj.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            contrastive_loss_with_mask(x, mask, projection_layer=proj).backward()
+
+    def stock():
+        x.grad = None; proj.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            feat = x.reshape(-1, x.shape[-1]); keep = mask != 3
+            z = F.normalize(proj(feat[keep]), dim=-1); m = mask[keep]
+            loss = torch.zeros((), device=device, requires_grad=True)
+            weak, strong, neg = z[m == 1], z[m == 2], z[m == 0]
+            if len(weak) and len(strong):
+                loss = loss + 1.0 * (-F.log_softmax(weak @ strong.T / 0.07, dim=-1)).mean()
+            if len(weak) and len(neg):
+                loss = loss + 0.3 * (-F.log_softmax(weak @ neg.T / 0.07, dim=-1)).mean()
+            loss.backward()
+    t, _ = event_time(ours, iters, 3, flush, device)
+    t_stock, _ = event_time(stock, iters, 3, flush, device)
+    rows = x.shape[0] * x.shape[1]
+    alg = rows * 1024 * 2 + 128 * 1024 * 4
+    return dict(rows=rows, fwd_bwd_ms=t, torch_cuda_ms=t_stock, speedup_vs_torch_cuda=t_stock / t, algorithmic_bytes=alg,
+                gbs=alg / t / 1e6, hbm_frac=alg / t / 1e6 / peaks["hbm"],
+                note="eager Python op (projection GEMM + fused normalise/pair kernels, fwd+bwd); 4.6 MB of input is ~1 us of "
+                     "HBM time, so the op is launch-latency bound at the reference's batch size")
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_train_sample(pairs, steps, warmup, threads):
     """The reference's train step restated on torch CPU ops (oracle/torch_port.py + the PyTorch encoders)."""
@@ -445,7 +487,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "ctc", "beam", "fusion"])
+    ap.add_argument("--workload", default="train", choices=["train", "ctc", "beam", "fusion", "infonce"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -474,6 +516,8 @@ def main():
     ctc = bench_ctc(device) if args.workload in ("train", "ctc") else None
     beam = bench_beam(device, rank, world) if args.workload in ("train", "beam") else None
     fusion = bench_fusion(device, peaks) if args.workload in ("train", "fusion") else None
+    if args.workload in ("train", "infonce"):
+        line["infonce"] = bench_infonce(device, peaks)
     if beam is not None:
         import torch.distributed as dist
         t = torch.tensor([beam["ms"], beam["e2e_ms"]], device=device)
@@ -498,13 +542,16 @@ def main():
     if fusion is not None:
         line["fusion"] = fusion
     if args.workload != "train":
-        line["metric"] = {"ctc": "ctc_fwd_bwd_gbs", "beam": "beam_decode_utt_per_s", "fusion": "fusion_tensor_frac"}[args.workload]
-        line["unit"] = {"ctc": "GB/s", "beam": "utt/s", "fusion": "fraction of bf16 tensor peak"}[args.workload]
+        line["metric"] = {"ctc": "ctc_fwd_bwd_gbs", "beam": "beam_decode_utt_per_s", "fusion": "fusion_tensor_frac",
+                          "infonce": "infonce_fwd_bwd_gbs"}[args.workload]
+        line["unit"] = {"ctc": "GB/s", "beam": "utt/s", "fusion": "fraction of bf16 tensor peak", "infonce": "GB/s"}[args.workload]
         line["config"] = {"workload": {"ctc": "config2: CTC fwd+bwd micro-benchmark B=64 T=250/1000 V=801 L in [10,80] fp32",
                                        "beam": "config5: beam-10 decode of 4096 x [150,800] log-prob utterances",
-                                       "fusion": "config3: fusion projections + cross attention fwd/bwd bf16 B=32 T_v=150 T_a=249"}[args.workload],
+                                       "fusion": "config3: fusion projections + cross attention fwd/bwd bf16 B=32 T_v=150 T_a=249",
+                                       "infonce": "config4 sizes: InfoNCE fwd+bwd on 8 x 249 rows of 1024 bf16 features"}[args.workload],
                           "l2": "256 MB write between timed iterations flushes L2"}
-        line["value"] = {"ctc": lambda: ctc["T1000"]["gbs"], "beam": lambda: beam["utt_per_s"], "fusion": lambda: fusion["tensor_frac_fwd_bwd"]}[args.workload]()
+        line["value"] = {"ctc": lambda: ctc["T1000"]["gbs"], "beam": lambda: beam["utt_per_s"], "fusion": lambda: fusion["tensor_frac_fwd_bwd"],
+                         "infonce": lambda: line["infonce"]["gbs"]}[args.workload]()
     if rank == 0 and world == 1 and args.workload == "train" and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, sec = cpu_train_sample(2, 1, 1, threads)

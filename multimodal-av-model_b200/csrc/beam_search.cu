@@ -24,6 +24,7 @@ namespace avctc {
 
 constexpr int kBeamMax = 32;       // beam widths supported by the kernel
 constexpr int kCandMax = 64;       // fast-path candidate list
+constexpr int kCandPad = kCandMax + 4;   // + one 16-byte group of padding for the vector rank loop (two-phase kernel)
 constexpr int kRowBufs = 3;
 constexpr int kBpSmemBytes = 24 * 1024;
 
@@ -439,79 +440,102 @@ __device__ __forceinline__ unsigned f2key(float v) {       // order-preserving f
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-template <int NV>
+__host__ __device__ inline size_t topk_smem_per_warp(int row_floats, int use_nth) {
+    const size_t b = (size_t)kCandPad * 8 + (size_t)(kBeamMax + 1) * 8 + (size_t)row_floats * 4 * (use_nth ? 2 : 1);
+    return (b + 15) / 16 * 16;
+}
+
+__device__ __forceinline__ float fmax_nan(float a, float b) {      // NaN-propagating maximum (FMNMX.NAN)
+    float d;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+
+// MODE 0: V == 32*NV (no bounds predicates at all), MODE 1: only slot NV-1 is ragged, MODE 2: any V <= 32*NV.
+// Per row (fast route, ~350 warp instructions): NV coalesced loads; the lane maxima with NaN propagation; a lower
+// bound tau of the (k+1)-th largest element from k+1 rounds of redux.max over the lane maxima (equal maxima retire
+// together, which only lowers tau); a per-lane bitmask of the elements >= tau, compacted into shared memory through
+// a prefix sum of the lane counts (no per-slot votes or branches); ranks by counting greater candidates with 16-byte
+// shared loads.  Any tie inside the first k+1 ranks, a NaN, or a candidate list outside [k+1, kCandMax] sends the row
+// to the literal libstdc++ order of torch.topk (topk_exact / topk_nth_exact).
+template <int NV, int MODE>
 __global__ void __launch_bounds__(kTopkWarps * 32) beam_topk_kernel(const BeamParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = p.beam;
-    // per-warp scratch: candidates, sorted top-(k+1), and (slow path only) a staged row + index queue
-    const size_t per_warp = (size_t)kCandMax * 8 + (size_t)(kBeamMax + 1) * 8 +
-                            (size_t)p.row_floats * 4 * (p.use_nth ? 2 : 1);
+    // per-warp scratch: candidates (+4 floats of padding), sorted top-(k+1), and (slow path only) a staged row + queue
+    const size_t per_warp = topk_smem_per_warp(p.row_floats, p.use_nth);        // multiple of 16 bytes
     unsigned char* mine = smem_raw + (size_t)warp * per_warp;
-    float* cv = reinterpret_cast<float*>(mine);
-    int* ci = reinterpret_cast<int*>(cv + kCandMax);
-    float* tv = reinterpret_cast<float*>(ci + kCandMax);
+    float* cv = reinterpret_cast<float*>(mine);                                 // 16-byte aligned (float4 rank loop)
+    int* ci = reinterpret_cast<int*>(cv + kCandPad);
+    float* tv = reinterpret_cast<float*>(ci + kCandPad);
     int* ti = reinterpret_cast<int*>(tv + kBeamMax + 1);
     float* srow = reinterpret_cast<float*>(ti + kBeamMax + 1);
     int* qi = reinterpret_cast<int*>(srow + p.row_floats);
     const unsigned rows = (unsigned)p.N * (unsigned)p.T;       // host guarantees N*T < 2^31
     const unsigned uT = (unsigned)p.T;
     const bool can_fast = p.fast && (k + 1 <= 32) && (p.V >= k + 1);
-    const int full_slots = p.V / 32;
+    const int full_slots = (MODE == 0) ? NV : (MODE == 1) ? NV - 1 : p.V / 32;
+    const bool tail_ok = lane + 32 * (NV - 1) < p.V;           // MODE 1: the one ragged slot
+    auto valid = [&](int j) -> bool {
+        if (MODE == 0) return true;
+        if (MODE == 1) return j < NV - 1 || tail_ok;
+        return j < full_slots || lane + 32 * j < p.V;
+    };
     for (unsigned r = blockIdx.x * kTopkWarps + warp; r < rows; r += gridDim.x * kTopkWarps) {
-        const unsigned n = r / uT, t = r - n * uT;
         if (p.lengths) {
+            const unsigned n = r / uT, t = r - n * uT;
             const long long fl = p.lengths[n];
             if ((long long)t >= fl) continue;
         }
-        const float* row = p.lp + (int64_t)n * p.stride_n + (int64_t)t * p.stride_t + lane;
+        const float* row;
+        if (p.stride_n == (int64_t)uT * p.stride_t) row = p.lp + (int64_t)r * p.stride_t + lane;     // dense [N,T,V]
+        else { const unsigned n = r / uT, t = r - n * uT; row = p.lp + (int64_t)n * p.stride_n + (int64_t)t * p.stride_t + lane; }
         float x[NV];
-        float ml = AVCTC_NEG_INF;
-        unsigned nanbits = 0;
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            if (j < full_slots || lane + 32 * j < p.V) x[j] = __ldcs(row + 32 * j);      // ragged / empty tail slots
-            else x[j] = AVCTC_NEG_INF;
-            nanbits = max(nanbits, __float_as_uint(x[j]) & 0x7fffffffu);
-            ml = fmaxf(ml, x[j]);
-        }
-        bool ok = can_fast && !__any_sync(kFullMask, nanbits > 0x7f800000u);
+        for (int j = 0; j < NV; ++j) x[j] = valid(j) ? __ldcs(row + 32 * j) : AVCTC_NEG_INF;
+        float ml = x[0];
+#pragma unroll
+        for (int j = 1; j < NV; ++j) ml = fmax_nan(ml, x[j]);
+        bool ok = can_fast && !__any_sync(kFullMask, ml != ml);
         if (ok) {
-            // (k+1)-th largest lane maximum = lower bound of the (k+1)-th largest element
             unsigned key = f2key(ml), m = 0;
             for (int i = 0; i <= k; ++i) {
                 m = __reduce_max_sync(kFullMask, key);
-                const unsigned who = __ballot_sync(kFullMask, key == m);
-                if (lane == __ffs(who) - 1) key = 0u;
+                if (key == m) key = 0u;
             }
-            const float tau = __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);   // inverse of f2key
-            // everything >= tau, in (slot, lane) order
-            int count = 0;
+            const float tau = __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);   // inverse of f2key (m = 0 -> NaN)
+            unsigned mk = 0;
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                const bool take = (x[j] >= tau) && (j < full_slots || lane + 32 * j < p.V);
-                const unsigned bm = __ballot_sync(kFullMask, take);
-                if (bm) {
-                    const int pos = count + __popc(bm & ((1u << lane) - 1));
-                    if (take && pos < kCandMax) { cv[pos] = x[j]; ci[pos] = lane + 32 * j; }
-                    count += __popc(bm);
-                }
+            for (int j = 0; j < NV; ++j) mk |= (x[j] >= tau && valid(j)) ? (1u << j) : 0u;
+            const int c = __popc(mk);
+            int inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int up = __shfl_up_sync(kFullMask, inc, d);
+                if (lane >= d) inc += up;
             }
+            const int count = __shfl_sync(kFullMask, inc, 31);
             ok = (count <= kCandMax) && (count >= k + 1);
             if (ok) {
+                int pos = inc - c;
+#pragma unroll
+                for (int j = 0; j < NV; ++j)
+                    if (mk & (1u << j)) { cv[pos] = x[j]; ci[pos] = lane + 32 * j; ++pos; }
+                if (lane < 3) cv[count + lane] = AVCTC_NEG_INF;          // pad the last 16-byte group
                 __syncwarp();
-                for (int i = lane; i < count; i += 32) {        // rank: value desc, index asc; keep ranks 0..k
-                    const float v = cv[i]; const int idx = ci[i];
-                    int rk = 0;
-                    for (int j = 0; j < count; ++j) {
-                        const float o = cv[j];
-                        rk += (o > v) || (o == v && ci[j] < idx);
+                bool tie = false;
+                for (int i = lane; i < count; i += 32) {        // rank = number of greater candidates; keep ranks 0..k
+                    const float v = cv[i];
+                    int gt = 0, eq = 0;
+                    for (int j = 0; j < count; j += 4) {
+                        const float4 o = *reinterpret_cast<const float4*>(cv + j);
+                        gt += (o.x > v) + (o.y > v) + (o.z > v) + (o.w > v);
+                        eq += (o.x == v) + (o.y == v) + (o.z == v) + (o.w == v);
                     }
-                    if (rk <= k) { tv[rk] = v; ti[rk] = idx; }
+                    if (gt <= k) { tv[gt] = v; ti[gt] = ci[i]; tie = tie || (eq > 1 && gt < k); }
                 }
-                __syncwarp();
-                const bool tie = (lane < k) && (tv[lane] == tv[lane + 1]);
-                ok = !__any_sync(kFullMask, tie);      // k+1 distinct values: the top-k is unique, any algorithm agrees
+                ok = !__any_sync(kFullMask, tie);      // the first k ranks hold distinct values: any algorithm agrees
             }
         }
         if (!ok) {     // ties / NaNs: literal libstdc++ order on a staged copy of the row
@@ -667,8 +691,7 @@ static bool beam_plan(int N, int T, int V, int beam, BeamPlan* pl) {
     pl->off_path = o; o = (o + (size_t)N * (T > 0 ? T : 1) * 4 + 255) / 256 * 256;
     // two-phase path: rows of up to 1024 classes live in registers (32 per lane)
     pl->two_phase = (V <= 1024) && (avctc_tuning_get("beam_two_phase", 1) != 0);
-    pl->smem_topk = (size_t)kTopkWarps * ((size_t)kCandMax * 8 + (size_t)(kBeamMax + 1) * 8 +
-                                          (size_t)pl->row_floats * 4 * (pl->use_nth ? 2 : 1));
+    pl->smem_topk = (size_t)kTopkWarps * topk_smem_per_warp(pl->row_floats, pl->use_nth);
     const size_t recur_fixed = 2 * kBeamMax * 8 + (size_t)pl->n_enum * 8 + 2 * (size_t)pl->n_enum + 16;
     pl->bp_in_smem2 = bp_bytes <= (size_t)kBpSmemBytes / 2;
     pl->smem_recur_per_warp = (recur_fixed + (pl->bp_in_smem2 ? bp_bytes : 0) + 15) / 16 * 16;
@@ -729,22 +752,29 @@ extern "C" int avctc_beam_search(const float* log_probs, int64_t stride_n, int64
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
-#define AVCTC_TOPK(NV)                                                                                              \
+#define AVCTC_TOPK(NV, MODE)                                                                                        \
     do {                                                                                                            \
         static bool cfg = false;                                                                                    \
         if (!cfg && pl.smem_topk > 48 * 1024) {                                                                     \
-            AVCTC_CUDA_RETURN(cudaFuncSetAttribute(beam_topk_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            AVCTC_CUDA_RETURN(cudaFuncSetAttribute(beam_topk_kernel<NV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                    200 * 1024));                                                    \
             cfg = true;                                                                                             \
         }                                                                                                           \
-        beam_topk_kernel<NV><<<(unsigned)blocks, kTopkWarps * 32, pl.smem_topk, st>>>(bp);                          \
+        beam_topk_kernel<NV, MODE><<<(unsigned)blocks, kTopkWarps * 32, pl.smem_topk, st>>>(bp);                    \
     } while (0)
-        if (need <= 4) AVCTC_TOPK(4);
-        else if (need <= 8) AVCTC_TOPK(8);
-        else if (need <= 16) AVCTC_TOPK(16);
-        else if (need <= 25) AVCTC_TOPK(25);
-        else if (need <= 26) AVCTC_TOPK(26);
-        else AVCTC_TOPK(32);
+#define AVCTC_TOPK_M(NV)                                                                                            \
+    do {                                                                                                            \
+        if (V == 32 * NV) AVCTC_TOPK(NV, 0);                                                                        \
+        else if (V > 32 * (NV - 1)) AVCTC_TOPK(NV, 1);                                                              \
+        else AVCTC_TOPK(NV, 2);                                                                                     \
+    } while (0)
+        if (need <= 4) AVCTC_TOPK(4, 2);
+        else if (need <= 8) AVCTC_TOPK(8, 2);
+        else if (need <= 16) AVCTC_TOPK(16, 2);
+        else if (need <= 25) AVCTC_TOPK_M(25);
+        else if (need <= 26) AVCTC_TOPK_M(26);
+        else AVCTC_TOPK_M(32);
+#undef AVCTC_TOPK_M
 #undef AVCTC_TOPK
         AVCTC_CUDA_RETURN(cudaGetLastError());
         const size_t smem2 = pl.smem_recur_per_warp * kRecurWarps;

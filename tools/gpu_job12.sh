@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_lstm_gpu.py -x -q > gpurun_out/t_lstm.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t_lstm.log
-tail -n 25 gpurun_out/t_lstm.log
-timeout 120 python tools/exp_lstm.py 2>&1 | tail -n 10
+timeout 900 python -m pytest tests/test_beam_gpu.py -x -q > gpurun_out/t_beam.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t_beam.log
+tail -n 5 gpurun_out/t_beam.log
+timeout 300 python bench.py --workload beam --steps 3 --warmup 3 > gpurun_out/bench_beam.json 2> gpurun_out/bench_beam.err; tail -n 3 gpurun_out/bench_beam.err; cat gpurun_out/bench_beam.json
