@@ -550,6 +550,7 @@ def main():
                                        "fusion": "config3: fusion projections + cross attention fwd/bwd bf16 B=32 T_v=150 T_a=249",
                                        "infonce": "config4 sizes: InfoNCE fwd+bwd on 8 x 249 rows of 1024 bf16 features"}[args.workload],
                           "l2": "256 MB write between timed iterations flushes L2"}
+        line["dtype"] = {"ctc": "f32", "beam": "f32 values, f64 scores", "fusion": "bf16", "infonce": "bf16 in, f32 math"}[args.workload]
         line["value"] = {"ctc": lambda: ctc["T1000"]["gbs"], "beam": lambda: beam["utt_per_s"], "fusion": lambda: fusion["tensor_frac_fwd_bwd"],
                          "infonce": lambda: line["infonce"]["gbs"]}[args.workload]()
     if rank == 0 and world == 1 and args.workload == "train" and not args.no_cpu_baseline:
