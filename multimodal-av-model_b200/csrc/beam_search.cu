@@ -505,10 +505,13 @@ __global__ void __launch_bounds__(kTopkWarps * 32) beam_topk_kernel(const BeamPa
                 if (key == m) key = 0u;
             }
             const float tau = __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);   // inverse of f2key (m = 0 -> NaN)
-            unsigned mk = 0;
+            int c = 0;
 #pragma unroll
-            for (int j = 0; j < NV; ++j) mk |= (x[j] >= tau && valid(j)) ? (1u << j) : 0u;
-            const int c = __popc(mk);
+            for (int j = 0; j < NV; ++j) {      // FSET + IADD per slot (a predicate per slot would be spilled through P2R)
+                unsigned ge;
+                asm("set.ge.u32.f32 %0, %1, %2;" : "=r"(ge) : "f"(x[j]), "f"(tau));
+                if (valid(j)) c -= (int)ge;
+            }
             int inc = c;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -518,24 +521,51 @@ __global__ void __launch_bounds__(kTopkWarps * 32) beam_topk_kernel(const BeamPa
             const int count = __shfl_sync(kFullMask, inc, 31);
             ok = (count <= kCandMax) && (count >= k + 1);
             if (ok) {
-                int pos = inc - c;
+                float2* cand = reinterpret_cast<float2*>(cv);          // (value, index bits) pairs, dense
+                uint32_t dst = (uint32_t)__cvta_generic_to_shared(cand + (inc - c));
 #pragma unroll
-                for (int j = 0; j < NV; ++j)
-                    if (mk & (1u << j)) { cv[pos] = x[j]; ci[pos] = lane + 32 * j; ++pos; }
-                if (lane < 3) cv[count + lane] = AVCTC_NEG_INF;          // pad the last 16-byte group
+                for (int j = 0; j < NV; ++j) {      // 4 instructions per slot: setp, index, predicated 8-byte store + bump
+                    if (valid(j))
+                        asm volatile("{\n\t.reg .pred p;\n\t"
+                                     "setp.ge.f32 p, %1, %2;\n\t"
+                                     "@p st.shared.v2.b32 [%0], {%4, %3};\n\t"
+                                     "@p add.u32 %0, %0, 8;\n\t}"
+                                     : "+r"(dst) : "f"(x[j]), "f"(tau), "r"(lane + 32 * j), "r"(__float_as_uint(x[j])) : "memory");
+                }
+                if (lane == 0) cand[count] = make_float2(AVCTC_NEG_INF, 0.f);      // pad the last 16-byte group
                 __syncwarp();
                 bool tie = false;
-                for (int i = lane; i < count; i += 32) {        // rank = number of greater candidates; keep ranks 0..k
-                    const float v = cv[i];
-                    int gt = 0, eq = 0;
-                    for (int j = 0; j < count; j += 4) {
-                        const float4 o = *reinterpret_cast<const float4*>(cv + j);
-                        gt += (o.x > v) + (o.y > v) + (o.z > v) + (o.w > v);
-                        eq += (o.x == v) + (o.y == v) + (o.z == v) + (o.w == v);
+                if (count <= 32) {
+                    // one candidate per lane: rank = number of greater values; equal values collide on the rank
+                    const bool have = lane < count;
+                    const float2 me = have ? cand[lane] : make_float2(0.f, 0.f);
+                    int gt = 0;
+                    for (int j = 0; j < count; j += 2) {
+                        const float4 o = *reinterpret_cast<const float4*>(cand + j);
+                        unsigned g0, g1;            // FSET masks (0 / ~0): one IADD3 retires two compares
+                        asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(g0) : "f"(o.x), "f"(me.x));
+                        asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(g1) : "f"(o.z), "f"(me.x));
+                        gt -= (int)g0 + (int)g1;
                     }
-                    if (gt <= k) { tv[gt] = v; ti[gt] = ci[i]; tie = tie || (eq > 1 && gt < k); }
+                    const bool top = have && gt <= k;
+                    const unsigned tm = __ballot_sync(kFullMask, top);
+                    if (top) {
+                        tie = __popc(__match_any_sync(tm, gt)) > 1;
+                        tv[gt] = me.x; ti[gt] = __float_as_int(me.y);
+                    }
+                } else {
+                    for (int i = lane; i < count; i += 32) {
+                        const float2 me = cand[i];
+                        int gt = 0, eq = 0;
+                        for (int j = 0; j < count; j += 2) {
+                            const float4 o = *reinterpret_cast<const float4*>(cand + j);
+                            gt += (o.x > me.x) + (o.z > me.x);
+                            eq += (o.x == me.x) + (o.z == me.x);
+                        }
+                        if (gt <= k) { tv[gt] = me.x; ti[gt] = __float_as_int(me.y); tie = tie || (eq > 1); }
+                    }
                 }
-                ok = !__any_sync(kFullMask, tie);      // the first k ranks hold distinct values: any algorithm agrees
+                ok = !__any_sync(kFullMask, tie);      // the first k+1 ranks hold distinct values: any algorithm agrees
             }
         }
         if (!ok) {     // ties / NaNs: literal libstdc++ order on a staged copy of the row
@@ -567,8 +597,8 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
     const int k = p.beam;
     unsigned char* mine = smem_raw + (size_t)warp * per_warp_bytes;
     double* score = reinterpret_cast<double*>(mine);                        // 2 * kBeamMax
-    double* cand_s = score + 2 * kBeamMax;                                  // n_enum
-    unsigned char* en_b = reinterpret_cast<unsigned char*>(cand_s + p.n_enum);
+    double* cand_s = score + 2 * kBeamMax;                                  // max(n_enum, 32), 16-byte aligned
+    unsigned char* en_b = reinterpret_cast<unsigned char*>(cand_s + (p.n_enum > 32 ? p.n_enum : 32));
     unsigned char* en_j = en_b + p.n_enum;
     uint32_t* bp_s = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(en_j + p.n_enum) + 15) & ~(uintptr_t)15);
 
@@ -585,6 +615,8 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
     }
     __syncwarp();
     int nb = 1, cur = 0;
+    const bool fast_enum = p.n_enum <= 32;
+    const int my_b = (lane < p.n_enum) ? en_b[lane] : 0, my_j = (lane < p.n_enum) ? en_j[lane] : 0;
     const float* tvp = p.tk_val + (size_t)n * p.T * k;
     const int32_t* tip = p.tk_idx + (size_t)n * p.T * k;
     float tv_n = 0.f; int ti_n = 0;
@@ -592,6 +624,46 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
     for (int t = 0; t < frames; ++t) {
         const float tvv = tv_n; const int tii = ti_n;
         if (t + 1 < frames && lane < k) { tv_n = tvp[(size_t)(t + 1) * k + lane]; ti_n = tip[(size_t)(t + 1) * k + lane]; }
+        if (fast_enum) {
+            // <= 32 candidates: lane m IS candidate m.  Rank = number of strictly greater scores (16-byte shared loads,
+            // NaN padding compares false); equal scores give equal ranks, which match.any detects -> exact route below.
+            const bool in = (lane < p.n_enum) && (my_b < nb);
+            const unsigned inmask = __ballot_sync(kFullMask, in);
+            const int M = __popc(inmask);                      // candidates are ordered by beam: `in` is a prefix
+            const double* sc = score + cur * kBeamMax;
+            double* sn = score + (cur ^ 1) * kBeamMax;
+            const float lpv = __shfl_sync(kFullMask, tvv, my_j);
+            const int tok = __shfl_sync(kFullMask, tii, my_j);
+            const double s = in ? sc[my_b] + (double)lpv : __longlong_as_double(0x7ff8000000000000ll);
+            cand_s[lane] = s;
+            __syncwarp();
+            const int keep = min(k, M);
+            int r = 0;
+            const double2* c2 = reinterpret_cast<const double2*>(cand_s);
+#pragma unroll 4
+            for (int q = 0; q < M; q += 2) {
+                const double2 o = c2[q >> 1];
+                r += (o.x > s) ? 1 : 0;
+                r += (o.y > s) ? 1 : 0;
+            }
+            bool clash = false;
+            if (in) clash = (__popc(__match_any_sync(inmask, r)) > 1) || (s != s);
+            if (__any_sync(kFullMask, clash)) {                // ties (or NaNs): insertion-order tie-break, as the reference's stable sort
+                r = 0;
+                for (int q = 0; q < M; ++q) {
+                    const double o = cand_s[q];
+                    r += (o > s) || (o == s && q < lane);
+                }
+            }
+            if (in && r < keep) {
+                sn[r] = s;
+                bp[(size_t)t * k + r] = ((uint32_t)my_b << 24) | (uint32_t)tok;
+            }
+            __syncwarp();
+            cur ^= 1;
+            nb = keep;
+            continue;
+        }
         int M = 0;
         for (int m0 = 0; m0 < p.n_enum; m0 += 32) {
             const int m = m0 + lane;
@@ -692,7 +764,7 @@ static bool beam_plan(int N, int T, int V, int beam, BeamPlan* pl) {
     // two-phase path: rows of up to 1024 classes live in registers (32 per lane)
     pl->two_phase = (V <= 1024) && (avctc_tuning_get("beam_two_phase", 1) != 0);
     pl->smem_topk = (size_t)kTopkWarps * topk_smem_per_warp(pl->row_floats, pl->use_nth);
-    const size_t recur_fixed = 2 * kBeamMax * 8 + (size_t)pl->n_enum * 8 + 2 * (size_t)pl->n_enum + 16;
+    const size_t recur_fixed = 2 * kBeamMax * 8 + (size_t)(pl->n_enum > 32 ? pl->n_enum : 32) * 8 + 2 * (size_t)pl->n_enum + 16;
     pl->bp_in_smem2 = bp_bytes <= (size_t)kBpSmemBytes / 2;
     pl->smem_recur_per_warp = (recur_fixed + (pl->bp_in_smem2 ? bp_bytes : 0) + 15) / 16 * 16;
     const bool need_bp_global = pl->two_phase ? !pl->bp_in_smem2 : !pl->bp_in_smem;
