@@ -40,6 +40,7 @@ struct BeamParams {
     int row_floats;        // smem floats per staged row
     int n_enum;            // number of (b,j) candidate pairs
     int use_nth;           // k*64 > V: torch.topk's nth_element + sort route for tied rows
+    int prefetch;          // top-k kernel: L2-prefetch the warp's next row (tuning knob "beam_pf")
     float* tk_val;         // [N][T][beam] per-frame top-k values (two-phase path)
     int32_t* tk_idx;       // [N][T][beam] per-frame top-k indices
 };
@@ -489,11 +490,17 @@ __global__ void __launch_bounds__(kTopkWarps * 32) beam_topk_kernel(const BeamPa
             if ((long long)t >= fl) continue;
         }
         const float* row;
-        if (p.stride_n == (int64_t)uT * p.stride_t) row = p.lp + (int64_t)r * p.stride_t + lane;     // dense [N,T,V]
+        const bool dense = p.stride_n == (int64_t)uT * p.stride_t;
+        if (dense) row = p.lp + (int64_t)r * p.stride_t + lane;     // dense [N,T,V]
         else { const unsigned n = r / uT, t = r - n * uT; row = p.lp + (int64_t)n * p.stride_n + (int64_t)t * p.stride_t + lane; }
         float x[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) x[j] = valid(j) ? __ldcs(row + 32 * j) : AVCTC_NEG_INF;
+        if (p.prefetch && dense) {       // the warp's next row: one 128-byte line per lane into L2
+            const unsigned rn = r + gridDim.x * kTopkWarps;
+            if (rn < rows && lane * 32 < p.V)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.lp + (int64_t)rn * p.stride_t + lane * 32));
+        }
         float ml = x[0];
 #pragma unroll
         for (int j = 1; j < NV; ++j) ml = fmax_nan(ml, x[j]);
@@ -804,6 +811,7 @@ extern "C" int avctc_beam_search(const float* log_probs, int64_t stride_n, int64
     bp.lp = log_probs; bp.stride_n = stride_n; bp.stride_t = stride_t;
     bp.N = N; bp.T = T; bp.V = V; bp.lengths = lengths; bp.beam = beam; bp.blank = blank;
     bp.fast = avctc_tuning_get("beam_fast", 1);
+    bp.prefetch = avctc_tuning_get("beam_pf", 1);
     bp.out_ids = out_ids; bp.out_len = out_len; bp.dbg_scores = dbg_scores; bp.dbg_paths = dbg_paths;
     bp.bp_global = pl.bp_in_smem ? nullptr : reinterpret_cast<uint32_t*>(w + pl.off_bp);
     bp.path_ws = reinterpret_cast<int32_t*>(w + pl.off_path);

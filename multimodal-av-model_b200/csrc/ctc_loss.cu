@@ -661,6 +661,7 @@ struct GradParams {
     const double* nll2; const int* chain;
     int K, W, S_pad, Lpad, linear;
     int cw; const int* flag; int run_if;
+    int prefetch;     // grad_lin: L2-prefetch the warp's next log-prob row (tuning knob "ctc_pf")
     int row_floats;   // per-warp smem floats for one staged row (>= V + 8, multiple of 4)
     int w_floats;     // per-warp smem floats for state weights (>= 2*Lmax+1, multiple of 4)
 };
@@ -881,6 +882,7 @@ constexpr int kWsRing = 8;   // frames per ring (power of two)
 
 constexpr int kWsGroup = 4;  // frames per TMA mbarrier phase
 constexpr int kWsGroups = 4; // groups in flight per producer warp
+constexpr int kWsThreads = 192;   // warps: 0,1 producers, 2 recurrence, 3 writer, 4,5 DMA (bulk-copy issue)
 
 __device__ __forceinline__ int ws_wait_ge(const int* word, int need) {
     int v = ld_volatile_shared_s32(word);
@@ -898,6 +900,9 @@ __device__ __forceinline__ void ws_mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void ws_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void ws_mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -917,7 +922,7 @@ __device__ __forceinline__ void ws_bulk_g2s(uint32_t dst, const void* src, uint3
 }
 
 template <int K, typename TIn, bool STORE>
-__global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, const int row_stride_bytes) {
+__global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParams p, const int row_stride_bytes) {
     constexpr int KL = K / 2;
     constexpr int G = kWsGroup, NG = kWsGroups;
     constexpr int PW = (K + 1 + 3) & ~3;      // payload words per lane per frame: K floats + one int
@@ -930,7 +935,8 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
     float* pring = reinterpret_cast<float*>(ws_smem + (size_t)2 * NG * G * row_stride_bytes);   // [RD][32][PW]
     float* sring = pring + RD * 32 * PW;                                           // [RD][32][PW]
     int* prog = reinterpret_cast<int*>(sring + RD * 32 * PW);                      // [4][32]: P0, P1, R, W next frame
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(prog + 128);  // [2][NG]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(prog + 128);  // [2][NG] rows landed ("full")
+    unsigned long long* mbar_empty = mbar + 2 * NG;                                // [2][NG] rows consumed ("empty")
     __shared__ double fin[2];
 
     long long tbl = p.input_lengths[b];
@@ -949,10 +955,10 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
             for (int j = threadIdx.x; j < L; j += blockDim.x) p.chain[(size_t)b * p.Lpad + j] = kChainFirst | kChainNone;
         return;
     }
-    prog[threadIdx.x] = 1;
+    if (threadIdx.x < 128) prog[threadIdx.x] = 1;
     if (threadIdx.x < 2) fin[threadIdx.x] = -(double)CUDART_INF_F;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * NG; ++i) ws_mbar_init(ws_smem_u32(&mbar[i]), 1);
+        for (int i = 0; i < 4 * NG; ++i) ws_mbar_init(ws_smem_u32(&mbar[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -966,19 +972,12 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
     float* pmine = pring + lane * PW;
     float* smine = sring + lane * PW;
 
-    if (warp < 2) {
-        // ================================================================ producers (warp pw: groups pw, pw+2, ...)
-        const int pw = warp;
-        int lab[KL];
-#pragma unroll
-        for (int i = 0; i < KL; ++i) {
-            const int j = g * KL + i;
-            lab[i] = p.blank;
-            if (j < L) {
-                long long c = tgt[dir ? (L - 1 - j) : j];
-                lab[i] = (int)(c < 0 ? 0 : (c >= p.V ? p.V - 1 : c));
-            }
-        }
+    if (warp >= 4) {
+        // ================================================================ DMA warps (warp 4+pw feeds producer pw)
+        // Issuing the bulk copies of a group (address arithmetic, expect_tx, the rare software row) was ~40 % of a
+        // producer's instruction stream and the producers were what the recurrence warp waited for; it now runs here,
+        // NG groups ahead, gated by the "empty" mbarrier the producer arrives on when it has consumed a slot group.
+        const int pw = warp - 4;
         // A row's 16-byte aligned window may read up to 15 bytes of its neighbours.  Below the tensor that is always
         // inside the allocation (an unaligned base is an interior pointer); above it only the row with the highest
         // address can leave the tensor: that single frame (if any) is copied by plain loads instead.
@@ -999,7 +998,6 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
         int f_arm = 1 + pw * G;
         auto arm = [&](int sl) {             // warp-wide: start the copies of frames f_arm .. f_arm+G-1 into slot group sl
             const uint32_t bar = ws_smem_u32(&mybar[sl]);
-            __syncwarp();                    // every lane is done reading the rows this group replaces
             if (bad_f >= f_arm && bad_f < f_arm + G) {
                 const int j = bad_f - f_arm;
                 const uintptr_t src = src_arm + (uintptr_t)((long long)j * fstep_b);
@@ -1031,7 +1029,34 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
         };
         const int ngroups_all = (Tb - 1 + G - 1) / G;
         const int mygroups = (ngroups_all - pw + 1) / 2;       // groups pw, pw+2, ... < ngroups_all
-        for (int k = 0; k < NG && k < mygroups; ++k) arm(k);
+#pragma unroll 1
+        for (int k = 0; k < mygroups; ++k) {
+            const int sl = k % NG;
+            if (k >= NG) ws_mbar_wait(ws_smem_u32(&mbar_empty[pw * NG + sl]), (uint32_t)((k / NG) - 1) & 1u);
+            arm(sl);
+        }
+        return;
+    }
+
+    if (warp < 2) {
+        // ================================================================ producers (warp pw: groups pw, pw+2, ...)
+        const int pw = warp;
+        int lab[KL];
+#pragma unroll
+        for (int i = 0; i < KL; ++i) {
+            const int j = g * KL + i;
+            lab[i] = p.blank;
+            if (j < L) {
+                long long c = tgt[dir ? (L - 1 - j) : j];
+                lab[i] = (int)(c < 0 ? 0 : (c >= p.V ? p.V - 1 : c));
+            }
+        }
+        const long long fstep_b = fstep * ES;
+        unsigned char* myrows = rowbuf + (size_t)pw * NG * G * row_stride_bytes;
+        const uint32_t myrows_s = ws_smem_u32(myrows);
+        unsigned long long* mybar = mbar + pw * NG;
+        const int ngroups_all = (Tb - 1 + G - 1) / G;
+        const int mygroups = (ngroups_all - pw + 1) / 2;       // groups pw, pw+2, ... < ngroups_all
         const uint32_t off_b = (uint32_t)p.blank * ES;
         uint32_t off_l[KL];
         float ninf_l[KL], one_b[KL];                            // validity as arithmetic (no predicate re-materialisation)
@@ -1104,7 +1129,8 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
             }
             f += G;                                   // skip the other producer's group
             src_c += (uintptr_t)(fstep_b * G);
-            if (k + NG < mygroups) arm(sl);
+            __syncwarp();                             // every lane is done reading this group's rows
+            if (lane == 0) ws_mbar_arrive(ws_smem_u32(&mbar_empty[pw * NG + sl]));   // the DMA warp may refill the slot
             if (++sl == NG) { sl = 0; par ^= 1u; }
         }
         if (risky && p.flag) *p.flag = 1;     // the host's conditional log-domain launches redo this batch
@@ -1195,11 +1221,17 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
     // one frame of the chain; RENORM frames bring the lane maximum back into [1,2) (exact power of two), the frames
     // in between only accumulate the emission exponent — two frames cannot move a lane by more than fp32's range
     // unless a class the mass sits on is > e^-40 below the best class of its lane twice in a row.
-    auto frame = [&](const int tau, const int slot, const int owner, const bool renorm) {   // slot = tau & (RD-1), static
+    // `ahead` = frames (this one included) whose ring slots are checked by this call: the full-group loop polls the
+    // producer and the writer once per group of G frames (a branch costs ~8 ALU slots on this lone warp), the tail
+    // polls every frame.  ahead = 0: no poll.  Neither wait can deadlock: the producer of group [tau, tau+G) needs the
+    // recurrence at tau+G-RD <= tau, the writer can reach tau.
+    auto frame = [&](const int tau, const int slot, const int owner, const bool renorm, const int ahead) {   // slot = tau & (RD-1), static
         const float up_a = __shfl_up_sync(kFullMask, a[K - 1], 1);
         const int up_C = __shfl_up_sync(kFullMask, C, 1);
-        if (availP[owner] <= tau) availP[owner] = ws_wait_ge(&prog[owner * 32 + lane], tau + 1);
-        if (do_store && tau - doneW >= RD) doneW = ws_wait_ge(&prog[96 + lane], tau - RD + 1);
+        if (ahead > 0) {
+            if (availP[owner] < tau + ahead) availP[owner] = ws_wait_ge(&prog[owner * 32 + lane], tau + ahead);
+            if (do_store && tau + ahead - doneW > RD) doneW = ws_wait_ge(&prog[96 + lane], tau + ahead - RD);
+        }
         const int roff = slot * 32 * PW;
         float pr[PW];
         {
@@ -1264,12 +1296,12 @@ __global__ void __launch_bounds__(128) ctc_scan_ws_kernel(const ScanParams p, co
 #pragma unroll 1
     for (; base + 2 * G <= Tb; base += 2 * G) {          // full groups: no bounds checks on the chain
 #pragma unroll
-        for (int u = 0; u < 2 * G; ++u) frame(base + u, (1 + u) & (RD - 1), (u / G) & 1, (u & 1) == 1);
+        for (int u = 0; u < 2 * G; ++u) frame(base + u, (1 + u) & (RD - 1), (u / G) & 1, (u & 1) == 1, (u % G == 0) ? G : 0);
     }
 #pragma unroll
     for (int u = 0; u < 2 * G; ++u) {
         const int tau = base + u;
-        if (tau < Tb) frame(tau, (1 + u) & (RD - 1), (u / G) & 1, (u & 1) == 1);
+        if (tau < Tb) frame(tau, (1 + u) & (RD - 1), (u / G) & 1, (u & 1) == 1, 1);
     }
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -1392,6 +1424,10 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
     const long long nitems = (long long)p.B * WS;
     TIn* grad = reinterpret_cast<TIn*>(p.grad);
     const TIn* lpbase = reinterpret_cast<const TIn*>(p.lp);
+    const int pf_lines = p.prefetch ? min(32, (int)((p.V * sizeof(TIn) + 127) / 128) + 1) : 0;
+    const int pf_dist = max(1, p.prefetch & 3);
+    const bool pf_ab = (p.prefetch & 4) != 0;
+    const int ab_lines = min(16, (p.S_pad * 4 + 127) / 128);
 
     for (long long item = gw; item < nitems; item += Wtot) {
         const int b = (int)(item % p.B), r = (int)(item / p.B);
@@ -1446,6 +1482,18 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
                 continue;
             }
             const TIn* lrow = lpbase + (int64_t)t * p.stride_t + (int64_t)b * p.stride_b;
+            if (pf_lines > 0 && t + pf_dist * WS < Tb) {      // a later row of this warp: pull its lines into L2 now
+                if (lane < pf_lines) {
+                    const char* nx = reinterpret_cast<const char*>(lrow + (int64_t)pf_dist * WS * p.stride_t) + lane * 128;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                }
+                if (pf_ab && lane < 2 * ab_lines) {
+                    const size_t rn = ((size_t)b * p.T + t + (size_t)pf_dist * WS) * p.S_pad;
+                    const char* nx = reinterpret_cast<const char*>((lane < ab_lines ? p.alpha : p.beta) + rn) +
+                                     (lane < ab_lines ? lane : lane - ab_lines) * 128;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                }
+            }
             const size_t rowi = (size_t)b * p.T + t;
             const float* arow = p.alpha + rowi * p.S_pad + s0;
             const float* brow = p.beta + rowi * p.S_pad;
@@ -1583,10 +1631,10 @@ template <int K, typename TIn>
 static int launch_scan_ws(const ScanParams& sp, int ndir, cudaStream_t st) {
     constexpr int PW = (K + 1 + 3) & ~3;
     constexpr int D = 2 * kWsGroup * kWsGroups;
-    dim3 grid(sp.B, ndir), block(128);
+    dim3 grid(sp.B, ndir), block(kWsThreads);
     const int row_stride = (int)(((size_t)sp.V * sizeof(TIn) + 32 + 127) & ~(size_t)127);
     const size_t smem = (size_t)D * row_stride + sizeof(float) * 2 * kWsRing * 32 * PW + sizeof(int) * 128 +
-                        sizeof(unsigned long long) * 2 * kWsGroups;
+                        sizeof(unsigned long long) * 4 * kWsGroups;
     if (smem > 200 * 1024) return -1000;     // rows too long for the shared-memory ring: caller falls back
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
@@ -1799,6 +1847,7 @@ extern "C" int avctc_ctc_backward(const void* log_probs, int dtype, int64_t stri
     gp.chain = reinterpret_cast<const int*>(w + pl.off_chain);
     gp.K = pl.K; gp.W = pl.W; gp.S_pad = pl.S_pad; gp.Lpad = pl.Lpad; gp.linear = pl.linear;
     gp.cw = pl.CW; gp.flag = nullptr; gp.run_if = 0;
+    gp.prefetch = avctc_tuning_get("ctc_pf", 1);
     gp.row_floats = (V + 8 + 3) & ~3;
     gp.w_floats = (2 * max_target_len + 1 + 3) & ~3;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
