@@ -1221,13 +1221,15 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
     // one frame of the chain; RENORM frames bring the lane maximum back into [1,2) (exact power of two), the frames
     // in between only accumulate the emission exponent — two frames cannot move a lane by more than fp32's range
     // unless a class the mass sits on is > e^-40 below the best class of its lane twice in a row.
+    float nx_up_a = __shfl_up_sync(kFullMask, a[K - 1], 1);
+    int nx_up_C = __shfl_up_sync(kFullMask, C, 1);
     // `ahead` = frames (this one included) whose ring slots are checked by this call: the full-group loop polls the
     // producer and the writer once per group of G frames (a branch costs ~8 ALU slots on this lone warp), the tail
     // polls every frame.  ahead = 0: no poll.  Neither wait can deadlock: the producer of group [tau, tau+G) needs the
     // recurrence at tau+G-RD <= tau, the writer can reach tau.
     auto frame = [&](const int tau, const int slot, const int owner, const bool renorm, const int ahead) {   // slot = tau & (RD-1), static
-        const float up_a = __shfl_up_sync(kFullMask, a[K - 1], 1);
-        const int up_C = __shfl_up_sync(kFullMask, C, 1);
+        const float up_a = nx_up_a;          // shuffled by the previous frame as soon as its top state was known
+        const int up_C = nx_up_C;
         if (ahead > 0) {
             if (availP[owner] < tau + ahead) availP[owner] = ws_wait_ge(&prog[owner * 32 + lane], tau + ahead);
             if (do_store && tau + ahead - doneW > RD) doneW = ws_wait_ge(&prog[96 + lane], tau + ahead - RD);
@@ -1262,6 +1264,10 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
             nw[2 * i] = (a[2 * i] + below) * pr[2 * i];
             nw[2 * i + 1] = fmaf(skipf[i], below, a[2 * i + 1] + a[2 * i]) * pr[2 * i + 1];
         }
+        // the neighbour lane needs (top state, exponent) as a consistent pair, not the renormalised one: send the raw
+        // pair now, so that the shuffle latency overlaps the renormalisation and the ring store below
+        nx_up_a = __shfl_up_sync(kFullMask, nw[K - 1], 1);
+        nx_up_C = __shfl_up_sync(kFullMask, C + Ecur, 1);
         if (renorm) {
             float mm = nw[0];
 #pragma unroll
