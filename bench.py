@@ -529,9 +529,9 @@ def main():
     if ctc is not None:
         line["ctc"] = ctc
         top = ctc["T1000"]
-        # dram__bytes_read.sum + dram__bytes_write.sum of the two kernels from ncu --set full (profiles/
-        # r01_ctc_scan_ws_full.txt launch 1 = 334.7 MB, r01_ctc_grad_lin_full.txt = 356.1 MB), same config
-        traffic = (334.70e6 + 356.12e6) if os.path.exists(os.path.join(ROOT, "profiles", "r01_ctc_grad_lin_full.txt")) else None
+        # dram__bytes_read.sum + dram__bytes_write.sum of the two kernels from one ncu --set full capture of this config
+        # (profiles/r01_ctc_scan_grad_full_v3.txt: scan 264.42 + 68.57 MB, gradient 209.43 + 152.86 MB)
+        traffic = (332.99e6 + 362.28e6) if os.path.exists(os.path.join(ROOT, "profiles", "r01_ctc_scan_grad_full_v3.txt")) else None
         line["roofline"] = {"bound": "hbm", "kernel": "ctc_scan_ws_kernel + ctc_grad_lin_kernel (CTC fwd+bwd, config 2: B=64 T=1000 V=801 fp32)",
                             "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s", "frac": top["gbs"] / peaks["hbm"],
                             "peak_src": peaks["src"] + " (burst copy bandwidth, MEASURED_PEAKS.json)", "traffic": traffic,
