@@ -388,6 +388,23 @@ class CrossAttentionFusion(nn.Module):
         fused, _mask_rs, input_lengths = self.fused_projection(visual_feat, audio_feat, mask)
         return self.temporal(fused), input_lengths
 
+    def forward_pair(self, visual_feats, audio_feats, masks):
+        """Both speakers of a mixed pair: forward(visual_feats[s], audio_feats[s], masks[s]) for s = 0, 1 with ONE pass
+        of the recurrent model over the 2B concatenated sequences.  The projections / attention stay per speaker (the
+        reference resamples the audio stream to the longest speech segment of ITS batch, fusion_module.py:47-55, so
+        the two speakers must not share a batch there); the BiLSTM treats every sequence independently, so running
+        it once over both halves the number of sequential time steps and changes no value.
+        Returns ((fused_seq_0, fused_seq_1), (input_lengths_0, input_lengths_1))."""
+        f, lens = [], []
+        for s in range(2):
+            fs, _m, il = self.fused_projection(visual_feats[s], audio_feats[s], masks[s])
+            f.append(fs); lens.append(il)
+        if f[0].shape[1:] != f[1].shape[1:] or f[0].shape[0] + f[1].shape[0] > 32:
+            return (self.temporal(f[0]), self.temporal(f[1])), tuple(lens)
+        y = self.temporal(torch.cat(f, dim=0))
+        b0 = f[0].shape[0]
+        return (y[:b0], y[b0:]), tuple(lens)
+
     def temporal(self, fused):
         """temporal_model over all padded frames (fusion_module.py:64).  The reference's configuration (hidden 512,
         also 256; batch <= 32) runs on the persistent kernels of csrc/lstm.cu; other shapes use nn.LSTM (cuDNN)."""

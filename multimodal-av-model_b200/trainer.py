@@ -92,6 +92,7 @@ class MultimodalTrainer:
         self.projection_layer = None
         self.verbose = True
         self.beam_width = 5                       # trainer.py:230,237
+        self.batch_speakers = True                # BiLSTM + CTC head over both speakers at once (hot_path_loss)
         self.gpu_heavy_first = False              # train_step enqueue order (see there); measured slower on B200, kept as a switch
         self.world_size = dist.get_world_size() if dist.is_initialized() else 1
         self._reducer = None
@@ -172,17 +173,29 @@ class MultimodalTrainer:
 
     def hot_path_loss(self, visual_feats, audio_feats, middle_feats, masks, texts, lens):
         """trainer.py:98-119 from encoder features on (two speakers): returns (total, ctc1, ctc2, con1, con2)."""
-        ctc, con = [], []
+        ctc, con, mask_ds = [], [], []
         for s in range(2):
             t_enc = audio_feats[s].shape[1]
-            mask_ds = F.interpolate(masks[s].unsqueeze(1).float(), size=t_enc, mode="nearest").squeeze(1).long()
+            mask_ds.append(F.interpolate(masks[s].unsqueeze(1).float(), size=t_enc, mode="nearest").squeeze(1).long())
             self._ensure_projection(audio_feats[s].shape[2])
-            con.append(contrastive_loss_with_mask(middle_feats[s], mask_ds.reshape(-1), projection_layer=self.projection_layer))
-            fused, input_lengths = self.fusion_module(visual_feats[s], audio_feats[s], mask=mask_ds)
-            log_probs = self.decoder1(fused)
-            ctc.append(self.ctc_loss(log_probs.transpose(0, 1), texts[s], input_lengths, lens[s]))
-            if s == 0:
-                self._last_log_probs = log_probs
+            con.append(contrastive_loss_with_mask(middle_feats[s], mask_ds[s].reshape(-1), projection_layer=self.projection_layer))
+        if self.batch_speakers and hasattr(self.fusion_module, "forward_pair"):
+            # the recurrent model and the CTC head see both speakers as one batch of 2B sequences (same values, half
+            # the sequential steps); everything whose result depends on the batch it is computed in stays per speaker
+            fused, in_lens = self.fusion_module.forward_pair(visual_feats, audio_feats, mask_ds)
+            if fused[0].shape == fused[1].shape:
+                lp = self.decoder1(torch.cat(fused, dim=0))
+                log_probs = (lp[:fused[0].shape[0]], lp[fused[0].shape[0]:])
+            else:
+                log_probs = (self.decoder1(fused[0]), self.decoder1(fused[1]))
+        else:
+            fused, in_lens, log_probs = [None, None], [None, None], [None, None]
+            for s in range(2):
+                fused[s], in_lens[s] = self.fusion_module(visual_feats[s], audio_feats[s], mask=mask_ds[s])
+                log_probs[s] = self.decoder1(fused[s])
+        for s in range(2):
+            ctc.append(self.ctc_loss(log_probs[s].transpose(0, 1), texts[s], in_lens[s], lens[s]))
+        self._last_log_probs = log_probs[0]
         total = (ctc[0] + ctc[1]) / 2 + self.lambda_ * (con[0] + con[1]) / 2
         return total, ctc[0], ctc[1], con[0], con[1]
 

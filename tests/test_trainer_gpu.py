@@ -91,3 +91,39 @@ def test_wer_matches_jiwer_definition():
     from multimodal_av_model_b200.trainer import word_error_rate
     assert word_error_rate(["a b c", "d e"], ["a x c", "d e f"]) == pytest.approx(2 / 5)
     assert word_error_rate(["a b"], ["a b"]) == 0.0
+
+
+def test_batching_both_speakers_through_the_bilstm_changes_no_value():
+    """hot_path_loss with batch_speakers (one BiLSTM / CTC-head pass over 2B sequences) equals the per-speaker
+    order of the reference (trainer.py:110-117): same losses, same parameter and feature gradients."""
+    pkg = _pkg()
+    from multimodal_av_model_b200.synthetic import CharTokenizer, make_features
+    torch.manual_seed(0)
+    fus = pkg.CrossAttentionFusion(512, 1024, 512)
+    dec = pkg.CTCDecoder(1024, 800, blank_id=3)
+    tr = pkg.MultimodalTrainer(_Enc(), _Enc(), fus, dec, CharTokenizer(800), device="cuda")
+    f = make_features(pairs=3, t_v=40, t_enc=99, seed=5, n_samples=32000, dtype=torch.bfloat16)
+    out = {}
+    for mode in (False, True):
+        tr.batch_speakers = mode
+        fd = {k: [t.cuda() for t in v] for k, v in f.items()}
+        for k in ("audio", "middle"):
+            fd[k] = [t.requires_grad_() for t in fd[k]]
+        for m in (fus, dec):
+            m.zero_grad(set_to_none=True)
+        if tr.projection_layer is not None:
+            tr.projection_layer.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            parts = tr.hot_path_loss(fd["visual"], fd["audio"], fd["middle"], fd["masks"], fd["texts"], fd["lens"])
+        parts[0].backward()
+        out[mode] = ([float(x) for x in parts], {n: p.grad.clone() for n, p in list(fus.named_parameters()) +
+                                                 list(dec.named_parameters()) if p.grad is not None},
+                     [t.grad.clone() for t in fd["audio"]])
+    a, b = out[False], out[True]
+    assert np.allclose(a[0], b[0], rtol=1e-5, atol=1e-6), (a[0], b[0])
+    assert a[1].keys() == b[1].keys()
+    for n in a[1]:       # split-K / atomics order may differ between a B and a 2B launch: fp32 accumulation noise only
+        scale = a[1][n].abs().max() + 1e-12
+        assert (a[1][n] - b[1][n]).abs().max() <= 2e-3 * scale, n
+    for x, y in zip(a[2], b[2]):
+        assert (x.float() - y.float()).abs().max() <= 2e-2 * (x.float().abs().max() + 1e-12)
