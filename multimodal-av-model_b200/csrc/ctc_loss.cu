@@ -867,13 +867,17 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const GradParams p) {
 // ctc_scan_ws_kernel — the probability-domain scan, warp-specialised.  The frame loop of one (sample, direction)
 // is a dependent chain on a single in-order warp (~0.25-0.5 instructions/cycle), so everything that is not the
 // recurrence itself runs on the other three SM sub-partitions of the CTA:
-//   warps 0,1  producers  (even / odd frame groups) whole log-prob rows arrive by TMA bulk copies (cp.async.bulk,
-//                         kWsGroup rows per mbarrier phase, 2*kWsGroup*kWsGroups frames ahead); each lane picks its
+//   warps 0,1  producers  (even / odd frame groups) wait for their group's rows (mbarrier "full"), each lane picks its
 //                         lattice states' emissions out of shared memory and publishes 2^(lp*log2e - E) per state plus
-//                         the lane exponent E into the ring "pring"
-//   warp 2     recurrence the dependent chain only: shuffle, exponent conversion, adds/multiplies, exact power-of-two
-//                         renormalisation every second frame -> ring "sring" (lane states + exponent)
+//                         the lane exponent E into the ring "pring"; a consumed slot group is handed back through an
+//                         "empty" mbarrier
+//   warp 2     recurrence the dependent chain only: exponent conversion, adds/multiplies, exact power-of-two
+//                         renormalisation every second frame -> ring "sring" (lane states + exponent); the (top state,
+//                         exponent) pair for the neighbour lane is shuffled BEFORE the renormalisation so that the
+//                         shuffle latency overlaps it; ring polls once per group of kWsGroup frames
 //   warp 3     writer     sring -> alpha/beta workspace in HBM
+//   warps 4,5  DMA        issue the TMA bulk copies (cp.async.bulk, whole log-prob rows, kWsGroup rows per mbarrier
+//                         phase, kWsGroups groups ahead per producer) as soon as a slot group is empty
 // Lane l of a role talks only to lane l of its neighbour role through per-lane progress words (volatile shared
 // accesses, payload before progress in program order), so neither fences nor block barriers sit in the frame loop.
 // Per-lane 4-byte gathers straight from HBM (ctc_scan_lin_kernel) are bound by DRAM random-access efficiency
