@@ -61,6 +61,24 @@ def test_beam_batch_vs_oracle_with_debug_export():
     assert pkg.beam_search_batch(lp.cuda(), beam_width=k, blank=3) == res
 
 
+@pytest.mark.parametrize("V,k", [(1024, 10), (1000, 10), (993, 5), (500, 10), (832, 11), (31, 5)])
+def test_beam_vocab_shapes_cover_every_topk_mode(V, k):
+    """Top-k kernel template modes: V = 32*NV exactly (1024, 832), one ragged slot (1000, 993), generic (500, 31),
+    all with exact ties (bf16-rounded values, one constant row, one row with -inf), all beams vs the oracle."""
+    pkg = _pkg()
+    g = torch.Generator().manual_seed(V * 31 + k)
+    lp = (2 * torch.randn(4, 40, V, generator=g)).log_softmax(-1)
+    lp[1] = lp[1].bfloat16().float()
+    lp[2, 7] = -2.5
+    lp[3, 3, : V // 2] = float("-inf")
+    res, scores, paths = pkg.beam_search_batch(lp.cuda(), beam_width=k, blank=0, return_debug=True)
+    for i in range(4):
+        ids, sc, pa = oracle.beam_search(lp[i].numpy(), k, 0, debug=True)
+        assert res[i] == ids
+        assert np.array_equal(paths[i].numpy(), pa)
+        assert np.array_equal(scores[i].numpy(), sc)
+
+
 def test_beam_lengths_long_T_and_strides():
     pkg = _pkg()
     g = torch.Generator().manual_seed(1)
