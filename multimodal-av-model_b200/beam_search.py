@@ -20,9 +20,10 @@ def beam_search_batch(log_probs, beam_width: int = 5, blank: int = 0, lengths=No
     lengths: optional int64 [N] frames to decode per utterance (the reference decodes all T padded
     frames, trainer.py:230, which is the default).  Returns N token lists; with return_debug also
     (final beam scores [N,beam] float64, raw beam paths [N,beam,T] int32)."""
-    _lib.require_cuda(log_probs, "log_probs")
     if log_probs.dim() != 3:
         raise RuntimeError("log_probs must be (N, T, V)")
+    if not log_probs.is_cuda:
+        return _beam_search_from_host(log_probs, beam_width, blank, lengths, return_debug)
     lp = log_probs.detach()
     if lp.dtype != torch.float32:
         lp = lp.float()
@@ -70,6 +71,59 @@ def beam_search_batch(log_probs, beam_width: int = 5, blank: int = 0, lengths=No
             o += l
     if return_debug:
         return res, dbg_s.cpu(), dbg_p.cpu()
+    return res
+
+
+def _beam_search_from_host(log_probs, beam_width, blank, lengths, return_debug, chunk_bytes=32 << 20, device=None):
+    """Host-resident log-probs (the reference accepts any device): streamed to the GPU in ~32 MB chunks of whole
+    utterances on a copy stream, two device buffers, so that the decode of chunk i runs under the transfer of chunk
+    i+1 and the call is bound by the PCIe copy alone.  Nothing is decoded on the host."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("beam_search_batch: the sm_100a beam kernel needs a CUDA device (no CPU path)")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    lp = log_probs.detach()
+    if lp.dtype != torch.float32:
+        lp = lp.float()
+    lp = lp.contiguous()
+    N, T, V = lp.shape
+    per = max(1, T * V * 4)
+    step = max(1, min(N, chunk_bytes // per)) if N else 1
+    if N <= step:
+        return beam_search_batch(lp.to(dev, non_blocking=True), beam_width, blank,
+                                 None if lengths is None else torch.as_tensor(lengths), return_debug)
+    if lengths is not None:
+        lengths = torch.as_tensor(lengths).to(torch.long)
+    main = torch.cuda.current_stream(dev)
+    copy = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty((step, T, V), dtype=torch.float32, device=dev) for _ in range(2)]
+    free = [None, None]                # event: the decode that last read buffer j has been enqueued and finished
+    res, dbg_s, dbg_p = [], [], []
+    pending = None                     # (buffer index, n, lengths slice, copy-done event)
+    starts = list(range(0, N, step))
+
+    def issue(ci):
+        j = ci % 2
+        n = min(step, N - starts[ci])
+        with torch.cuda.stream(copy):
+            if free[j] is not None:
+                copy.wait_event(free[j])
+            bufs[j][:n].copy_(lp[starts[ci]:starts[ci] + n], non_blocking=True)
+            ev = copy.record_event()
+        return (j, n, None if lengths is None else lengths[starts[ci]:starts[ci] + n], ev)
+
+    pending = issue(0)
+    for ci in range(len(starts)):
+        j, n, ln, ev = pending
+        pending = issue(ci + 1) if ci + 1 < len(starts) else None          # next transfer first, then this decode
+        main.wait_event(ev)
+        out = beam_search_batch(bufs[j][:n], beam_width, blank, ln, return_debug)   # syncs on this chunk only
+        free[j] = main.record_event()
+        if return_debug:
+            res.extend(out[0]); dbg_s.append(out[1]); dbg_p.append(out[2])
+        else:
+            res.extend(out)
+    if return_debug:
+        return res, torch.cat(dbg_s), torch.cat(dbg_p)
     return res
 
 

@@ -91,6 +91,28 @@ def test_beam_lengths_long_T_and_strides():
     assert res[2] == []
 
 
+def test_beam_host_input_streams_in_chunks():
+    """Host-resident log-probs are decoded on the GPU through a chunked copy/decode pipeline: same token lists as
+    the device-resident call (pinned and pageable sources, ragged last chunk, per-utterance lengths, debug export)."""
+    pkg = _pkg()
+    from multimodal_av_model_b200.beam_search import _beam_search_from_host
+    g = torch.Generator().manual_seed(3)
+    N, T, V = 23, 30, 800
+    lp = (3 * torch.randn(N, T, V, generator=g)).log_softmax(-1)
+    lens = torch.randint(0, T + 1, (N,), generator=g)
+    want = pkg.beam_search_batch(lp.cuda(), beam_width=10, blank=3)
+    want_l = pkg.beam_search_batch(lp.cuda(), beam_width=10, blank=3, lengths=lens)
+    for src in (lp, lp.pin_memory()):
+        assert pkg.beam_search_batch(src, beam_width=10, blank=3) == want                   # one chunk
+        got = _beam_search_from_host(src, 10, 3, None, False, chunk_bytes=5 * T * V * 4)    # 5 utterances per chunk
+        assert got == want
+        assert _beam_search_from_host(src, 10, 3, lens, False, chunk_bytes=4 * T * V * 4) == want_l
+    r, sc, pa = _beam_search_from_host(lp, 10, 3, None, True, chunk_bytes=6 * T * V * 4)
+    r0, sc0, pa0 = pkg.beam_search_batch(lp.cuda(), beam_width=10, blank=3, return_debug=True)
+    assert r == r0 and torch.equal(sc, sc0) and torch.equal(pa, pa0)
+    assert pkg.simple_beam_search(lp[0], beam_width=5, blank=3) == pkg.simple_beam_search(lp[0].cuda(), beam_width=5, blank=3)
+
+
 def test_fast_decode_and_errors():
     pkg = _pkg()
 
