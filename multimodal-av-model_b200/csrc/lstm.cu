@@ -363,11 +363,25 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(const LstmBwd
 // ---- small helpers
 struct LCastJob { const float* src; __nv_bfloat16* dst; long long n; };
 struct LCastJobs { LCastJob j[8]; int count; };
+// fp32 -> bf16 of up to 8 weight tensors in one launch: one flat index space over all of them, 4 elements per step
+// (16-byte loads, 8-byte stores; element counts are multiples of 4 and the tensors 16-byte aligned, else scalar)
 __global__ void lstm_cast_kernel(const LCastJobs jobs) {
-    for (int t = 0; t < jobs.count; ++t) {
+    long long total4 = 0;
+    for (int t = 0; t < jobs.count; ++t) total4 += (jobs.j[t].n + 3) >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        int t = 0;
+        while (r >= ((jobs.j[t].n + 3) >> 2)) { r -= (jobs.j[t].n + 3) >> 2; ++t; }
         const LCastJob jb = jobs.j[t];
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < jb.n; i += (long long)gridDim.x * blockDim.x)
-            jb.dst[i] = __float2bfloat16(jb.src[i]);
+        const long long e = r << 2;
+        if (e + 4 <= jb.n && ((reinterpret_cast<uintptr_t>(jb.src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(jb.dst) & 7) == 0)) {
+            const float4 v = *reinterpret_cast<const float4*>(jb.src + e);
+            __nv_bfloat162* d = reinterpret_cast<__nv_bfloat162*>(jb.dst + e);
+            d[0] = __floats2bfloat162_rn(v.x, v.y);
+            d[1] = __floats2bfloat162_rn(v.z, v.w);
+        } else {
+            for (long long k = e; k < jb.n && k < e + 4; ++k) jb.dst[k] = __float2bfloat16(jb.src[k]);
+        }
     }
 }
 // out[0:4H] = a0 + b0 ; out[4H:8H] = a1 + b1
@@ -512,7 +526,7 @@ extern "C" int avctc_bilstm_forward(const void* x_bf16, int B, int T, int In, in
             cj.j[4 * l + 2] = {pp[1], s.l[l].whh, (long long)(4 * Hh * Hh)};
             cj.j[4 * l + 3] = {pp[5], s.l[l].whh + 4 * Hh * Hh, (long long)(4 * Hh * Hh)};
         }
-        lstm_cast_kernel<<<296, 256, 0, st>>>(cj);
+        lstm_cast_kernel<<<1184, 256, 0, st>>>(cj);
         AVCTC_CUDA_RETURN(cudaGetLastError());
     }
     const __nv_bfloat16* xin = reinterpret_cast<const __nv_bfloat16*>(x_bf16);

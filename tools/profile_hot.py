@@ -29,3 +29,13 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3): fn()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
+# kernel-by-kernel timeline of the last iteration
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+evs.sort(key=lambda e: e.time_range.start)
+n = len(evs) // 3
+t00 = evs[2 * n].time_range.start
+busy = 0.0
+for e in evs[2 * n:]:
+    busy += e.time_range.elapsed_us()
+    print(f"{(e.time_range.start - t00):9.1f} us  dur {e.time_range.elapsed_us():7.1f}  {e.name[:90]}")
+print("GPU busy us in the last iteration:", busy, "span", evs[-1].time_range.end - t00)
