@@ -1434,7 +1434,8 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
     const long long nitems = (long long)p.B * WS;
     TIn* grad = reinterpret_cast<TIn*>(p.grad);
     const TIn* lpbase = reinterpret_cast<const TIn*>(p.lp);
-    const int pf_lines = p.prefetch ? min(32, (int)((p.V * sizeof(TIn) + 127) / 128) + 1) : 0;
+    // lane l prefetches the line holding byte 128*l of the row: every address stays inside the row (and the tensor)
+    const int pf_lines = p.prefetch ? min(32, (int)((p.V * sizeof(TIn) + 127) / 128)) : 0;
     const int pf_dist = max(1, p.prefetch & 3);
     const bool pf_ab = (p.prefetch & 4) != 0;
     const int ab_lines = min(16, (p.S_pad * 4 + 127) / 128);

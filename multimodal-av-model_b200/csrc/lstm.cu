@@ -44,6 +44,40 @@ __device__ __forceinline__ void step_barrier_wait(const unsigned* bar, unsigned 
         if (++spins > (1 << 24)) __trap();      // never hang the GPU
     }
 }
+// Sentinel exchange: the host fills an exchange buffer with 0xFF bytes (bf16 0xFFFF, a NaN pattern no conversion
+// produces: cvt.rn.bf16.f32 gives the canonical 0x7FFF); a reader polls the 16-byte chunk itself until none of its
+// eight halves is the sentinel, so a step needs no fence + counter + counter poll (one L2 round trip instead of three).
+__device__ __forceinline__ bool has_sentinel16(const uint4& v) {
+    const uint32_t a = ~v.x, b = ~v.y, c = ~v.z, d = ~v.w;             // a half equal to 0xFFFF is zero in the complement
+    const uint32_t z = ((a - 0x00010001u) & ~a) | ((b - 0x00010001u) & ~b) | ((c - 0x00010001u) & ~c) | ((d - 0x00010001u) & ~d);
+    return (z & 0x80008000u) != 0u;
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// loads n 16-byte chunks (chunk c of this thread: src(c) -> dst(c)), four in flight, re-polling the ones not yet written
+template <typename SrcF, typename DstF>
+__device__ __forceinline__ void poll_load_chunks(int first, int n, int stride, SrcF src, DstF dst) {
+    for (int c0 = first; c0 < n; c0 += 4 * stride) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int c = c0 + u * stride; if (c < n) v[u] = ld_relaxed_v4(src(c)); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u * stride;
+            if (c < n) {
+                int spins = 0;
+                while (has_sentinel16(v[u])) {
+                    v[u] = ld_relaxed_v4(src(c));
+                    if (++spins > (1 << 22)) __trap();          // never hang the GPU
+                }
+                *dst(c) = v[u];
+            }
+        }
+    }
+}
 // one MUFU each (tanh.approx.f32, |err| ~ 5e-4): well inside the bf16 rounding of h; sigmoid(x) = 0.5 tanh(x/2) + 0.5
 __device__ __forceinline__ float tanh_fast(float x) {
     float y;
@@ -64,6 +98,7 @@ struct LstmFwdParams {
     float* cst;                  // [2][T][B][H] cell state, or nullptr
     unsigned* bar;               // [2] step counters, zeroed by the host
     int B, T;
+    int tagged;                  // 1: y was filled with the 0xFFFF sentinel by the host; exchange by polling the data
 };
 
 // NB = batch tiles of 8 (B <= 8*NB)
@@ -98,8 +133,9 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(const LstmFwd
         }
     }
     float creg[PP];
+    __nv_bfloat16 hcur_reg[PP], hprev_reg[PP];
 #pragma unroll
-    for (int i = 0; i < PP; ++i) creg[i] = 0.f;
+    for (int i = 0; i < PP; ++i) { creg[i] = 0.f; hcur_reg[i] = __float2bfloat16(0.f); hprev_reg[i] = __float2bfloat16(0.f); }
     for (int i = tid; i < BP * HS; i += kLstmThreads) hs[i] = __float2bfloat16(0.f);
     __syncthreads();
 
@@ -126,12 +162,19 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(const LstmFwd
             for (int g = 0; g < 4; ++g) xg[i][g] = xnext[i][g];
         load_x(s + 1);
         if (s > 0) {
-            if (tid == 0) step_barrier_wait(p.bar + d, (unsigned)NC * s);
-            __syncthreads();
-            for (int c = tid; c < B * (H / 8); c += kLstmThreads) {        // h_{t-1}: L2 loads (written by other SMs)
-                const int b = c / (H / 8), q = c % (H / 8);
-                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p.y + ((size_t)b * T + tprev) * 2 * H + (size_t)d * H) + q);
-                *reinterpret_cast<uint4*>(hs + b * HS + q * 8) = v;
+            if (p.tagged) {                                              // h_{t-1}: poll the data itself
+                poll_load_chunks(tid, B * (H / 8), kLstmThreads,
+                    [&](int c) { const int b = c / (H / 8), q = c % (H / 8);
+                                 return reinterpret_cast<const uint4*>(p.y + ((size_t)b * T + tprev) * 2 * H + (size_t)d * H) + q; },
+                    [&](int c) { const int b = c / (H / 8), q = c % (H / 8); return reinterpret_cast<uint4*>(hs + b * HS + q * 8); });
+            } else {
+                if (tid == 0) step_barrier_wait(p.bar + d, (unsigned)NC * s);
+                __syncthreads();
+                for (int c = tid; c < B * (H / 8); c += kLstmThreads) {    // h_{t-1}: L2 loads (written by other SMs)
+                    const int b = c / (H / 8), q = c % (H / 8);
+                    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p.y + ((size_t)b * T + tprev) * 2 * H + (size_t)d * H) + q);
+                    *reinterpret_cast<uint4*>(hs + b * HS + q * 8) = v;
+                }
             }
             __syncthreads();
         }
@@ -179,12 +222,16 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(const LstmFwd
                 const float c = fg * creg[i] + ig * gg;
                 creg[i] = c;
                 const float h = og * tanh_fast(c);
-                p.y[((size_t)b * T + t) * 2 * H + (size_t)d * H + u0 + u] = __float2bfloat16(h);
+                hprev_reg[i] = hcur_reg[i];                     // the h_{t-1} of my own unit that this step consumed
+                hcur_reg[i] = __float2bfloat16(h);
+                p.y[((size_t)b * T + t) * 2 * H + (size_t)d * H + u0 + u] = hcur_reg[i];
                 sv[i][0] = ig; sv[i][1] = fg; sv[i][2] = gg; sv[i][3] = og;
             }
         }
-        __syncthreads();
-        if (tid == 0) { __threadfence(); atomicAdd(p.bar + d, 1u); }
+        if (!p.tagged) {
+            __syncthreads();
+            if (tid == 0) { __threadfence(); atomicAdd(p.bar + d, 1u); }
+        }
         // everything only the backward pass needs is stored AFTER the arrive: the fence above must not wait for it
         if (p.gates) {
 #pragma unroll
@@ -194,7 +241,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(const LstmFwd
                     float* gp = p.gates + (((size_t)d * T + t) * B + b) * 4 * H + u0 + u;
                     gp[0] = sv[i][0]; gp[H] = sv[i][1]; gp[2 * H] = sv[i][2]; gp[3 * H] = sv[i][3];
                     p.cst[(((size_t)d * T + t) * B + b) * H + u0 + u] = creg[i];
-                    p.hprev[((size_t)b * T + t) * 2 * H + (size_t)d * H + u0 + u] = hs[b * HS + u0 + u];
+                    p.hprev[((size_t)b * T + t) * 2 * H + (size_t)d * H + u0 + u] = hprev_reg[i];
                 }
             }
         }
@@ -209,6 +256,7 @@ struct LstmBwdParams {
     __nv_bfloat16* dG;           // [B*T][8H] gate pre-activation gradients (output; also the exchange buffer)
     unsigned* bar;               // [2]
     int B, T;
+    int tagged;                  // 1: dG was filled with the 0xFFFF sentinel by the host; exchange by polling the data
 };
 
 template <int H, int NB>
@@ -295,17 +343,24 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(const LstmBwd
             }
         }
         if (s == T - 1) break;                       // nothing precedes the first forward step
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(p.bar + d, 1u);
-            step_barrier_wait(p.bar + d, (unsigned)NC * (s + 1));
-        }
-        __syncthreads();
-        for (int c = tid; c < B * (4 * H / 8); c += kLstmThreads) {       // all gate gradients of step t, every unit
-            const int b = c / (4 * H / 8), q = c % (4 * H / 8);
-            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p.dG + ((size_t)b * T + t) * 8 * H + (size_t)d * 4 * H) + q);
-            *reinterpret_cast<uint4*>(dgs + b * GS + q * 8) = v;
+        if (p.tagged) {                                                    // all gate gradients of step t: poll the data
+            poll_load_chunks(tid, B * (4 * H / 8), kLstmThreads,
+                [&](int c) { const int b = c / (4 * H / 8), q = c % (4 * H / 8);
+                             return reinterpret_cast<const uint4*>(p.dG + ((size_t)b * T + t) * 8 * H + (size_t)d * 4 * H) + q; },
+                [&](int c) { const int b = c / (4 * H / 8), q = c % (4 * H / 8); return reinterpret_cast<uint4*>(dgs + b * GS + q * 8); });
+        } else {
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(p.bar + d, 1u);
+                step_barrier_wait(p.bar + d, (unsigned)NC * (s + 1));
+            }
+            __syncthreads();
+            for (int c = tid; c < B * (4 * H / 8); c += kLstmThreads) {   // all gate gradients of step t, every unit
+                const int b = c / (4 * H / 8), q = c % (4 * H / 8);
+                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p.dG + ((size_t)b * T + t) * 8 * H + (size_t)d * 4 * H) + q);
+                *reinterpret_cast<uint4*>(dgs + b * GS + q * 8) = v;
+            }
         }
         __syncthreads();
         float accp[4][NB][4];          // four independent accumulator chains (mma.sync latency), summed below
@@ -546,6 +601,12 @@ extern "C" int avctc_bilstm_forward(const void* x_bf16, int B, int T, int In, in
         fp.gates = need_grad ? s.l[l].gates : nullptr;
         fp.cst = need_grad ? s.l[l].cst : nullptr;
         fp.bar = w.bar; fp.B = B; fp.T = T;
+        // measured (tools/exp_lstm_tag.py, B200): forward 766 -> 546 us at B=8, no gain at B=16 (more chunks to poll per
+        // step); backward is slower with it at every batch size (every CTA polls all B x 4H gate gradients).
+        // knob lstm_tag: 0 off, 1 forward when B <= 8 (default), 2 forward always, 3 forward and backward.
+        const int tagk = avctc_tuning_get("lstm_tag", 1);
+        fp.tagged = (tagk >= 2 || (tagk == 1 && B <= 8)) ? 1 : 0;
+        if (fp.tagged) AVCTC_CUDA_RETURN(cudaMemsetAsync(fp.y, 0xFF, (size_t)d.BT * 2 * H * sizeof(__nv_bfloat16), st));
         LSTM_TRY(dispatch_fwd(H, d.NB, fp, st));
         xin = fp.y;
     }
@@ -572,6 +633,8 @@ extern "C" int avctc_bilstm_backward(const void* dy_bf16, const void* x_bf16, in
         LstmBwdParams bp;
         bp.dy = dy; bp.whh = s.l[l].whh; bp.gates = s.l[l].gates; bp.cst = s.l[l].cst; bp.dG = w.dG; bp.bar = w.bar;
         bp.B = B; bp.T = T;
+        bp.tagged = avctc_tuning_get("lstm_tag", 1) >= 3 ? 1 : 0;
+        if (bp.tagged) AVCTC_CUDA_RETURN(cudaMemsetAsync(w.dG, 0xFF, (size_t)d.BT * 8 * H * sizeof(__nv_bfloat16), st));
         LSTM_TRY(dispatch_bwd(H, d.NB, bp, st));
         for (int dir = 0; dir < 2; ++dir) {
             // dW_ih[dir] [4H,In] = dG[:, dir*4H:+4H]^T . x ; dW_hh[dir] [4H,H] = dG_dir^T . hprev[:, dir*H:+H]

@@ -56,3 +56,32 @@ def test_fusion_module_uses_custom_lstm_and_matches_cudnn_route():
         pkg._lib.set_py_tuning("lstm_custom", 1)
     assert y_custom.dtype == torch.float32 and y_custom.shape == y_cudnn.shape
     assert relerr(y_custom, y_cudnn) < 2e-2
+
+
+@pytest.mark.parametrize("B,T,H", [(8, 60, 512), (16, 30, 512), (5, 21, 256)])
+def test_bilstm_exchange_modes_are_bitwise_identical(B, T, H):
+    """Step exchange between the CTAs of a direction: counter barrier (lstm_tag=0) vs polling the data itself for a
+    0xFFFF sentinel (forward only: 1/2, forward and backward: 3) — same arithmetic, so outputs and gradients must be
+    bit-identical in every mode (weight gradients up to the order of their split-K atomics)."""
+    pkg = _pkg()
+    from multimodal_av_model_b200.fusion_module import _BiLSTMFn
+    torch.manual_seed(B + T)
+    ref = torch.nn.LSTM(H, H, num_layers=2, batch_first=True, bidirectional=True).cuda()
+    x = torch.randn(B, T, H, device="cuda")
+    r = torch.randn(B, T, 2 * H, device="cuda")
+    res = {}
+    try:
+        for mode in (0, 1, 2, 3):
+            pkg._lib.set_tuning("lstm_tag", mode)
+            for p in ref.parameters():
+                p.grad = None
+            xi = x.clone().requires_grad_()
+            y = _BiLSTMFn.apply(xi, *ref._flat_weights)
+            (y.float() * r).sum().backward()
+            res[mode] = [y.detach().clone(), xi.grad.clone()] + [p.grad.clone() for p in ref._flat_weights]
+    finally:
+        pkg._lib.set_tuning("lstm_tag", 1)
+    for mode in (1, 2, 3):
+        assert torch.equal(res[0][0], res[mode][0]) and torch.equal(res[0][1], res[mode][1]), mode   # y, dx
+        for a, b in zip(res[0][2:], res[mode][2:]):      # weight gradients: split-K fp32 atomics, order not fixed
+            assert (a - b).abs().max() <= 1e-4 * (a.abs().max() + 1e-12), mode
