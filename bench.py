@@ -442,6 +442,14 @@ def cpu_train_sample(pairs, steps, warmup, threads):
     return 2 * pairs * steps / dt, dt / steps
 
 
+def train_config(world):
+    """The workload both arms run (BASELINE config 4); each arm adds how it runs it."""
+    return {"workload": "config4: full AV-CTC + InfoNCE train step (encoders + fusion + BiLSTM + CTC head + CTC + InfoNCE + Adam)",
+            "pairs_per_gpu": PAIRS_PER_GPU, "utterances_per_step": 2 * PAIRS_PER_GPU * world, "audio_s": SECONDS,
+            "lip_frames": T_V, "t_enc": 249, "vocab": VOCAB, "blank": BLANK,
+            "encoders": "random-init ResNet-18 front-end + wav2vec2-large (XLSR layout)"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -453,8 +461,8 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": "train_utt_per_s", "value": val, "unit": "utt/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config4: full AV-CTC + InfoNCE train step (encoders + fusion + CTC head + CTC + InfoNCE + Adam)",
-                       "pairs_per_step": pairs, "audio_s": SECONDS, "lip_frames": T_V, "vocab": VOCAB, "blank": BLANK},
+            "config": dict(train_config(1), implementation="torch CPU ops (oracle/torch_port.py + the PyTorch encoders), fp32",
+                           sample_pairs_per_step=pairs),
             "cpu_baseline": {"value": val, "unit": "utt/s", "cores": threads, "kind": "port",
                              "sample": f"{steps} step(s) of {pairs} pairs (= {2 * pairs} utterances) of the config-4 step on torch CPU ops"},
             "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -502,12 +510,11 @@ def main():
     peaks = measured_peaks()
     line = {"metric": "train_utt_per_s", "unit": "utt/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "config4: full AV-CTC + InfoNCE train step (PyTorch encoders + sm_100a fusion/CTC head/CTC/InfoNCE "
-                                   "kernels + Adam), utterance-sharded data parallel",
-                       "pairs_per_gpu": PAIRS_PER_GPU, "utterances_per_step": 2 * PAIRS_PER_GPU * world, "audio_s": SECONDS,
-                       "lip_frames": T_V, "t_enc": 249, "vocab": VOCAB, "blank": BLANK, "encoders": "random-init ResNet-18 front-end + wav2vec2-large (XLSR layout)",
-                       "parallelism": f"dp{world}", "l2": "per-step working set (1.3 GB of parameters + activations) exceeds the 126 MB L2; "
-                                                       "sub-benchmarks flush L2 with a 256 MB write between iterations"}}
+            "config": dict(train_config(world),
+                           implementation="PyTorch encoders + sm_100a fusion/BiLSTM/CTC head/CTC/InfoNCE kernels, bf16 autocast",
+                           parallelism=f"dp{world}, utterance-sharded",
+                           l2="per-step working set (1.3 GB of parameters + activations) exceeds the 126 MB L2; "
+                              "sub-benchmarks flush L2 with a 256 MB write between iterations")}
     if args.workload == "train":
         out, tr = bench_train(args, rank, local, world, device)
         line.update(out)
