@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(32 * kMaxWarps) ctc_scan_kernel(const ScanPara
     constexpr int KL = K / 2;
     constexpr int D = (K >= 16) ? kScanPrefetch / 4 : (K >= 8) ? kScanPrefetch / 2 : kScanPrefetch;
     constexpr int RN = (D < kRenorm) ? D : kRenorm;
+    pdl_launch_dependents();
+    pdl_wait();             // PDL launch: the probability-domain scan (and its guard flag) is complete from here on
     if (p.flag && *reinterpret_cast<volatile int*>(p.flag) != p.run_if) return;   // fallback launch, not needed
     const int b = blockIdx.x;
     const int dir = blockIdx.y;  // 0: alpha (forward in time), 1: beta (mirrored problem)
@@ -743,6 +745,8 @@ __global__ void __launch_bounds__(256) ctc_grad_kernel(const GradParams p) {
     extern __shared__ __align__(16) float smem[];
     constexpr int kVec = VecTraits<TIn>::kVec;
     constexpr int NS = 6;   // states per lane whose alpha/beta loads are issued before the row lands
+    pdl_launch_dependents();
+    pdl_wait();             // PDL launch: everything before it on the stream (scan, guard flag) is complete from here on
     if (p.flag && *p.flag != p.run_if) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     float* rowbuf = smem + (size_t)warp * (2 * p.row_floats + p.w_floats);
@@ -934,6 +938,7 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
     constexpr int ES = (int)sizeof(TIn);
     const int b = blockIdx.x, dir = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();     // the small kernels behind this one (guarded log-domain scan, reduce) wait for it themselves
     extern __shared__ __align__(128) unsigned char ws_smem[];
     unsigned char* rowbuf = ws_smem;                                               // [2][NG][G][row_stride_bytes]
     float* pring = reinterpret_cast<float*>(ws_smem + (size_t)2 * NG * G * row_stride_bytes);   // [RD][32][PW]
@@ -1424,6 +1429,8 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
     constexpr int kVec = VecTraits<TIn>::kVec;
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    pdl_launch_dependents();
+    pdl_wait();             // PDL launch: the scan kernels and whatever produced grad_out are complete from here on
     if (p.flag && *p.flag != p.run_if) return;
     float* delta = smem + (size_t)warp * (p.row_floats + p.w_floats);   // class posteriors; all-zero between rows
     float* wbuf = delta + p.row_floats;                                  // label-state weights of the current row
@@ -1578,6 +1585,8 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
 __global__ void ctc_reduce_kernel(const float* __restrict__ nll, const int64_t* __restrict__ tl, int B,
                                   int reduction, int zero_infinity, float* __restrict__ loss) {
     __shared__ double part[32];
+    pdl_launch_dependents();
+    pdl_wait();                  // launched with the PDL attribute: the scan kernels before it must have finished
     double acc = 0.0;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         float v = nll[b];
@@ -1611,7 +1620,7 @@ static int launch_scan_impl(const ScanParams& sp, int ndir, cudaStream_t st) {
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         configured = true;
     }
-    ctc_scan_kernel<K, TIn, MULTI><<<grid, block, smem, st>>>(sp);
+    AVCTC_CUDA_RETURN(avctc_launch_pdl(ctc_scan_kernel<K, TIn, MULTI>, grid, block, smem, st, sp));
     return (int)cudaGetLastError();
 }
 template <int K, typename TIn>
@@ -1717,7 +1726,7 @@ static int launch_grad(const GradParams& gp_in, cudaStream_t st) {
     const long long cap = (long long)num_sms() * occ;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) return AVCTC_OK;
-    ctc_grad_kernel<TIn><<<(unsigned)blocks, warps * 32, smem, st>>>(gp);
+    AVCTC_CUDA_RETURN(avctc_launch_pdl(ctc_grad_kernel<TIn>, dim3((unsigned)blocks), dim3(warps * 32), smem, st, gp));
     return (int)cudaGetLastError();
 }
 
@@ -1740,7 +1749,7 @@ static int launch_grad_lin(const GradParams& gp, cudaStream_t st) {
     const long long cap = (long long)num_sms() * occ;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) return AVCTC_OK;
-    ctc_grad_lin_kernel<K, TIn><<<(unsigned)blocks, warps * 32, smem, st>>>(gp);
+    AVCTC_CUDA_RETURN(avctc_launch_pdl(ctc_grad_lin_kernel<K, TIn>, dim3((unsigned)blocks), dim3(warps * 32), smem, st, gp));
     return (int)cudaGetLastError();
 }
 template <typename TIn>
@@ -1821,9 +1830,8 @@ extern "C" int avctc_ctc_reduce(const float* nll, const int64_t* target_lengths,
     if (B < 0 || !loss) return AVCTC_ERR_BAD_ARG;
     if (reduction < AVCTC_REDUCE_NONE || reduction > AVCTC_REDUCE_SUM) return AVCTC_ERR_BAD_ARG;
     if (B > 0 && (!nll || !target_lengths)) return AVCTC_ERR_BAD_ARG;
-    ctc_reduce_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(nll, target_lengths, B, reduction,
-                                                                           zero_infinity, loss);
-    return (int)cudaGetLastError();
+    return (int)avctc_launch_pdl(ctc_reduce_kernel, dim3(1), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), nll,
+                                 target_lengths, B, reduction, zero_infinity, loss);
 }
 
 extern "C" int avctc_ctc_backward(const void* log_probs, int dtype, int64_t stride_t, int64_t stride_b,
