@@ -44,9 +44,15 @@ enum { AVCTC_REDUCE_NONE = 0, AVCTC_REDUCE_MEAN = 1, AVCTC_REDUCE_SUM = 2 };
 AVCTC_API const char* avctc_version(void);
 /* Human-readable text for a status returned by any entry point (host pointer, static storage). */
 AVCTC_API const char* avctc_status_string(int status);
-/* Tuning knobs for benchmarking (host-side process-global ints; not needed for correctness).
- * key: "ctc_lin" (1 = probability-domain single-warp CTC scan when 2L+1 <= 512, 0 = log-domain scan),
- * "ctc_k" (log-domain scan, states per lane: 0 = auto, 2/4/8/16), "beam_fast" (1 = threshold top-k fast path). */
+/* Tuning knobs for benchmarking and A/B measurements (host-side process-global ints; no knob changes a result).
+ * key: "ctc_lin" (1 = probability-domain CTC scan when 2L+1 <= 512, 0 = log-domain scan),
+ * "ctc_ws" (1 = warp-specialised TMA-fed scan, 0 = single-warp scan), "ctc_k" (log-domain scan, states per lane:
+ * 0 = auto, 2/4/8/16), "ctc_pf" (gradient pass: L2 prefetch distance in rows, 0 = off, +4 = also alpha/beta),
+ * "ctc_grad_warps", "beam_fast" (1 = threshold top-k fast path), "beam_two_phase" (1 = top-k for all rows first),
+ * "beam_pf" (1 = L2 prefetch of the next row), "pdl" (1 = programmatic dependent launch for the GEMM / softmax / CTC
+ * kernel chains), "lstm_tag" (BiLSTM step exchange: 0 counter barrier, 1 sentinel polling in the forward pass when
+ * B <= 8, 2 forward always, 3 forward and backward), "gemm_dbg" (per-CTA timestamps).  Unknown keys return
+ * AVCTC_ERR_BAD_ARG. */
 AVCTC_API int avctc_set_tuning(const char* key, int value);
 
 /* ------------------------------------------------------------------------------------------------
