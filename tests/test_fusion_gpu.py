@@ -163,3 +163,27 @@ def test_fused_path_odd_shapes_full_module_vs_torch_port(B, Tv, Ta, E, H):
             assert p.grad is None, k
         else:
             assert relerr(p.grad, q.grad) < 6e-2, k
+
+
+@pytest.mark.parametrize("Tv2", [40, 33])
+def test_forward_pair_equals_two_forward_calls(Tv2):
+    """CrossAttentionFusion.forward_pair (one BiLSTM pass over both speakers) against two forward() calls: same
+    outputs and input_lengths; with different lip lengths the pair falls back to two recurrent passes."""
+    pkg = _pkg()
+    torch.manual_seed(0)
+    fus = pkg.CrossAttentionFusion(512, 1024, 512).cuda()
+    B, Ta = 4, 99
+    vis = [torch.randn(B, 40, 512, device="cuda", dtype=torch.bfloat16), torch.randn(B, Tv2, 512, device="cuda", dtype=torch.bfloat16)]
+    aud = [torch.randn(B, Ta, 1024, device="cuda", dtype=torch.bfloat16) for _ in range(2)]
+    masks = []
+    for s in range(2):
+        m = torch.zeros(B, Ta, dtype=torch.long, device="cuda")
+        m[:, :50 + 7 * s] = 1; m[:, 50 + 7 * s:70] = 2; m[:, 90:] = 3
+        masks.append(m)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        (y0, y1), (l0, l1) = fus.forward_pair(vis, aud, masks)
+        r0, rl0 = fus(vis[0], aud[0], mask=masks[0])
+        r1, rl1 = fus(vis[1], aud[1], mask=masks[1])
+    assert torch.equal(l0, rl0) and torch.equal(l1, rl1)
+    assert y0.shape == r0.shape and y1.shape == r1.shape
+    assert torch.equal(y0, r0) and torch.equal(y1, r1)        # per-sequence arithmetic does not depend on the batch
