@@ -628,9 +628,13 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
     const int32_t* tip = p.tk_idx + (size_t)n * p.T * k;
     float tv_n = 0.f; int ti_n = 0;
     if (frames > 0 && lane < k) { tv_n = tvp[lane]; ti_n = tip[lane]; }
-    for (int t = 0; t < frames; ++t) {
+    const float* tv_nx = tvp + lane;           // running pointers: the next frame's list / this frame's back-pointer row
+    const int32_t* ti_nx = tip + lane;
+    uint32_t* bp_t = bp;
+    for (int t = 0; t < frames; ++t, bp_t += k) {
         const float tvv = tv_n; const int tii = ti_n;
-        if (t + 1 < frames && lane < k) { tv_n = tvp[(size_t)(t + 1) * k + lane]; ti_n = tip[(size_t)(t + 1) * k + lane]; }
+        tv_nx += k; ti_nx += k;
+        if (t + 1 < frames && lane < k) { tv_n = *tv_nx; ti_n = *ti_nx; }
         if (fast_enum) {
             // <= 32 candidates: lane m IS candidate m.  Rank = number of strictly greater scores (16-byte shared loads,
             // NaN padding compares false); equal scores give equal ranks, which match.any detects -> exact route below.
@@ -645,14 +649,15 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
             cand_s[lane] = s;
             __syncwarp();
             const int keep = min(k, M);
-            int r = 0;
+            int r = 0, r1 = 0;                 // two chains of predicated increments (DSETP + @p IADD per compare)
             const double2* c2 = reinterpret_cast<const double2*>(cand_s);
 #pragma unroll 4
             for (int q = 0; q < M; q += 2) {
                 const double2 o = c2[q >> 1];
-                r += (o.x > s) ? 1 : 0;
-                r += (o.y > s) ? 1 : 0;
+                asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(r) : "d"(o.x), "d"(s));
+                asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(r1) : "d"(o.y), "d"(s));
             }
+            r += r1;
             bool clash = false;
             if (in) clash = (__popc(__match_any_sync(inmask, r)) > 1) || (s != s);
             if (__any_sync(kFullMask, clash)) {                // ties (or NaNs): insertion-order tie-break, as the reference's stable sort
@@ -664,7 +669,7 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
             }
             if (in && r < keep) {
                 sn[r] = s;
-                bp[(size_t)t * k + r] = ((uint32_t)my_b << 24) | (uint32_t)tok;
+                bp_t[r] = ((uint32_t)my_b << 24) | (uint32_t)tok;
             }
             __syncwarp();
             cur ^= 1;
