@@ -611,7 +611,10 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
 
     long long fl = p.lengths ? p.lengths[n] : p.T;
     const int frames = (int)(fl < 0 ? 0 : (fl > p.T ? p.T : fl));
+    // back-pointers: in shared memory as 16-bit (parent << 10 | token; the two-phase path has V <= 1024, beam <= 32),
+    // which doubles the resident warps per SM of this latency-bound kernel; the global spill keeps 32-bit entries
     uint32_t* bp = bp_in_smem ? bp_s : p.bp_global + (size_t)n * p.T * k;
+    uint16_t* bp16 = reinterpret_cast<uint16_t*>(bp_s);
     int32_t* path = p.path_ws + (size_t)n * p.T;
     if (lane == 0) {
         int m = 0;
@@ -631,7 +634,8 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
     const float* tv_nx = tvp + lane;           // running pointers: the next frame's list / this frame's back-pointer row
     const int32_t* ti_nx = tip + lane;
     uint32_t* bp_t = bp;
-    for (int t = 0; t < frames; ++t, bp_t += k) {
+    uint16_t* bp16_t = bp16;
+    for (int t = 0; t < frames; ++t, bp_t += k, bp16_t += k) {
         const float tvv = tv_n; const int tii = ti_n;
         tv_nx += k; ti_nx += k;
         if (t + 1 < frames && lane < k) { tv_n = *tv_nx; ti_n = *ti_nx; }
@@ -669,7 +673,8 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
             }
             if (in && r < keep) {
                 sn[r] = s;
-                bp_t[r] = ((uint32_t)my_b << 24) | (uint32_t)tok;
+                if (bp_in_smem) bp16_t[r] = (uint16_t)((my_b << 10) | tok);
+                else bp_t[r] = ((uint32_t)my_b << 24) | (uint32_t)tok;
             }
             __syncwarp();
             cur ^= 1;
@@ -705,7 +710,8 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
                 }
                 if (r < keep) {
                     sn[r] = s;
-                    bp[(size_t)t * k + r] = ((uint32_t)en_b[m] << 24) | (uint32_t)tok;
+                    if (bp_in_smem) bp16_t[r] = (uint16_t)(((int)en_b[m] << 10) | tok);
+                    else bp_t[r] = ((uint32_t)en_b[m] << 24) | (uint32_t)tok;
                 }
             }
         }
@@ -719,9 +725,15 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
             int32_t* dst = dbg ? p.dbg_paths + ((size_t)n * k + lane) * p.T : path;
             int idx = lane;
             for (int t = frames - 1; t >= 0; --t) {
-                const uint32_t e = bp[(size_t)t * k + idx];
-                dst[t] = (int32_t)(e & 0xffffffu);
-                idx = (int)(e >> 24);
+                if (bp_in_smem) {
+                    const unsigned e = bp16[(size_t)t * k + idx];
+                    dst[t] = (int32_t)(e & 0x3ffu);
+                    idx = (int)(e >> 10);
+                } else {
+                    const uint32_t e = bp[(size_t)t * k + idx];
+                    dst[t] = (int32_t)(e & 0xffffffu);
+                    idx = (int)(e >> 24);
+                }
             }
             if (dbg && lane == 0)
                 for (int t = 0; t < frames; ++t) path[t] = dst[t];
@@ -777,8 +789,9 @@ static bool beam_plan(int N, int T, int V, int beam, BeamPlan* pl) {
     pl->two_phase = (V <= 1024) && (avctc_tuning_get("beam_two_phase", 1) != 0);
     pl->smem_topk = (size_t)kTopkWarps * topk_smem_per_warp(pl->row_floats, pl->use_nth);
     const size_t recur_fixed = 2 * kBeamMax * 8 + (size_t)(pl->n_enum > 32 ? pl->n_enum : 32) * 8 + 2 * (size_t)pl->n_enum + 16;
-    pl->bp_in_smem2 = bp_bytes <= (size_t)kBpSmemBytes / 2;
-    pl->smem_recur_per_warp = (recur_fixed + (pl->bp_in_smem2 ? bp_bytes : 0) + 15) / 16 * 16;
+    const size_t bp16_bytes = bp_bytes / 2;              // two-phase recurrence: 16-bit entries in shared memory
+    pl->bp_in_smem2 = bp16_bytes <= (size_t)kBpSmemBytes / 2;
+    pl->smem_recur_per_warp = (recur_fixed + (pl->bp_in_smem2 ? bp16_bytes : 0) + 15) / 16 * 16;
     const bool need_bp_global = pl->two_phase ? !pl->bp_in_smem2 : !pl->bp_in_smem;
     pl->off_bp = o; if (need_bp_global) o = (o + (size_t)N * bp_bytes + 255) / 256 * 256;
     pl->off_tv = o; if (pl->two_phase) o = (o + (size_t)N * (T > 0 ? T : 1) * beam * 4 + 255) / 256 * 256;
