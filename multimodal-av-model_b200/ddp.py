@@ -54,6 +54,17 @@ def broadcast_module(module, src=0, group=None):
         dist.broadcast(t.data, src=src, group=group)
 
 
+def broadcast_buffers(module, src=0, group=None):
+    """Buffers only (BatchNorm running statistics, num_batches_tracked): every rank adopts rank `src`'s values, as
+    torch's DistributedDataParallel(broadcast_buffers=True) keeps them.  The frozen visual encoder runs in train mode
+    (trainer.py:54), so its running statistics follow each rank's own batches; evaluation and checkpoints must not
+    depend on which rank they came from."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for t in module.buffers():
+        dist.broadcast(t.data, src=src, group=group)
+
+
 class GradBucketReducer:
     def __init__(self, params, bucket_bytes=64 << 20, group=None, overlap=True):
         self.group = group

@@ -27,7 +27,7 @@ from . import _lib
 from .beam_search import beam_search_batch, fast_decode
 from .contrastive import contrastive_loss_with_mask
 from .ctc import CTCLoss
-from .ddp import GradBucketReducer, broadcast_module
+from .ddp import GradBucketReducer, broadcast_buffers, broadcast_module
 
 
 def word_error_rate(refs, hyps):
@@ -255,6 +255,8 @@ class MultimodalTrainer:
     def evaluate(self, dataloader):
         for m in (self.visual_encoder, self.audio_encoder, self.fusion_module, self.decoder1):
             m.eval()
+            if self.world_size > 1:
+                broadcast_buffers(m)          # BatchNorm running statistics: rank 0's, on every rank
         refs, hyps = [[], []], [[], []]
         total_loss = 0.0
         blank = self.tokenizer.blank_id

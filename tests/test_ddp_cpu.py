@@ -73,3 +73,41 @@ def test_shard_range_partitions_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _buffer_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from multimodal_av_model_b200 import ddp
+    ddp.init_distributed("gloo")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv1d(2, 4, 3), torch.nn.BatchNorm1d(4))
+    net.train()
+    g = torch.Generator().manual_seed(10 + rank)                 # every rank sees its own batches
+    for _ in range(3):
+        net(torch.randn(5, 2, 9, generator=g))
+    mine = net[1].running_mean.clone()
+    w_before = net[0].weight.clone()
+    ddp.broadcast_buffers(net)
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, net[1].running_mean)
+    same = all(torch.equal(gathered[0], t) for t in gathered)
+    q.put((rank, bool(same), bool(torch.equal(mine, net[1].running_mean)), bool(torch.equal(w_before, net[0].weight)),
+           int(net[1].num_batches_tracked)))
+    dist.destroy_process_group()
+
+
+def test_broadcast_buffers_aligns_running_statistics_only():
+    """BatchNorm running statistics drift per rank in train mode; broadcast_buffers (used by evaluate()) makes every
+    rank adopt rank 0's, and leaves parameters alone."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_buffer_worker, args=(r, 2, 29621, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(same for _, same, _, _, _ in res), res
+    assert res[0][2] is True and res[1][2] is False          # rank 0 kept its statistics, rank 1 adopted them
+    assert all(w_ok for _, _, _, w_ok, _ in res) and all(n == 3 for *_, n in res)
