@@ -13,6 +13,9 @@ Differences that matter (all deliberate, none changes a result):
   * mixed precision is bf16 autocast (no GradScaler needed); the reference uses fp16 + GradScaler (trainer.py:9,40)
   * the reference's per-sample label sanity prints (trainer.py:77-85, 3B host syncs per step) are dropped
   * evaluate() decodes a whole batch with one beam-search launch instead of 2B Python loops
+  * train_epoch() never blocks on the GPU inside the loop: the next batch's host->device copies are issued (side
+    stream) as soon as the current step is enqueued, and each step's loss goes to the host through a non-blocking
+    copy into the pinned `loss_log` (the reference's `loss.item()` per batch, trainer.py:125, is one sync per step)
   * when torch.distributed is initialised the step is utterance-sharded data parallel: every rank runs its own
     batch, gradients are averaged with a bucketed NCCL all-reduce overlapped with backward (ddp.py)
 """
@@ -63,6 +66,14 @@ def _log_softmax_again(lp):
     return out
 
 
+class StagedBatch(dict):
+    """A collated batch whose host->device copies have been issued (MultimodalTrainer.stage): device tensors, the
+    per-clip wait callables and the host-side lengths the audio encoder uses."""
+
+
+_END = object()          # train_epoch: the dataloader is exhausted
+
+
 class MultimodalTrainer:
     cache_frozen_casts = True       # encoders.install_frozen_cast_cache on the two encoders (frozen weights only)
 
@@ -94,6 +105,10 @@ class MultimodalTrainer:
         self.beam_width = 5                       # trainer.py:230,237
         self.batch_speakers = True                # BiLSTM + CTC head over both speakers at once (hot_path_loss)
         self.gpu_heavy_first = False              # train_step enqueue order (see there); measured slower on B200, kept as a switch
+        self.prefetch_batches = True              # train_epoch: stage batch i+1 while step i runs on the GPU
+        self.loss_log = None                      # pinned fp32 ring: per-step total loss of the current epoch (async D2H)
+        self.loss_log_count = 0                   # steps logged this epoch; entries are valid after a synchronize
+        self.last_epoch_steps = 0                 # steps of the last train_epoch that did not raise
         self.world_size = dist.get_world_size() if dist.is_initialized() else 1
         self._reducer = None
         if self.world_size > 1:
@@ -165,6 +180,29 @@ class MultimodalTrainer:
             return {"host_lengths": (m != 3).sum(-1).cpu()}
         return {}
 
+    def stage(self, batch):
+        """Issue the host->device copies of one collated batch and return it as a StagedBatch that train_step accepts
+        in place of the batch.  Nothing here waits for the GPU; train_epoch calls it one batch ahead."""
+        if isinstance(batch, StagedBatch):
+            return batch
+        kw = [{}, {}]
+        if hasattr(self.audio_encoder, "prefetch_features"):
+            kw = [self._host_lengths(batch, "mask1"), self._host_lengths(batch, "mask2")]
+        d = StagedBatch(self._to_dev(batch))
+        d["enc_kw"] = kw
+        return d
+
+    _LOSS_LOG_CAP = 1 << 16
+
+    def _log_loss(self, loss):
+        """Device scalar -> pinned host ring, non-blocking: the per-step read-back without a per-step sync."""
+        if not loss.is_cuda:
+            return
+        if self.loss_log is None:
+            self.loss_log = torch.zeros(self._LOSS_LOG_CAP, dtype=torch.float32).pin_memory()
+        self.loss_log[self.loss_log_count % self._LOSS_LOG_CAP].copy_(loss.detach().float(), non_blocking=True)
+        self.loss_log_count += 1
+
     def _ensure_projection(self, D):
         if self.projection_layer is None:           # trainer.py:105-106: created lazily, once per epoch
             self.projection_layer = nn.Linear(D, 128).to(self.device)
@@ -200,14 +238,12 @@ class MultimodalTrainer:
         return total, ctc[0], ctc[1], con[0], con[1]
 
     def train_step(self, batch):
-        """One optimisation step on one collated batch (the body of the reference's loop, trainer.py:64-125).
-        Returns the detached total loss (device tensor; no host sync)."""
+        """One optimisation step on one collated batch, or on a StagedBatch from stage() (the body of the reference's
+        loop, trainer.py:64-125).  Returns the detached total loss (device tensor; no host sync)."""
         self.optimizer.zero_grad()
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=str(self.device).startswith("cuda")):
-            kw = [{}, {}]
-            if hasattr(self.audio_encoder, "prefetch_features"):
-                kw = [self._host_lengths(batch, "mask1"), self._host_lengths(batch, "mask2")]
-            d = self._to_dev(batch)
+            d = self.stage(batch)
+            kw = d["enc_kw"]
             # Enqueue order.  Default: audio encoder (small H2D) first so that the two 44 MB lip clips copy behind it.
             # gpu_heavy_first enqueues the conv front ends before the ~1500 small transformer launches; on B200 the
             # step is GPU-bound (~47 ms of kernels) and that order measured 3 ms slower (tools/exp_step.py).
@@ -230,26 +266,57 @@ class MultimodalTrainer:
         return total.detach()
 
     # ------------------------------------------------------------------------------------------ epochs
+    def _stage_next(self, it):
+        """Next batch of the iterator, staged; _END when exhausted.  A staging error is returned, not raised: it
+        belongs to that batch's turn in the loop (same `except Exception: continue` policy as a failing step)."""
+        try:
+            batch = next(it)
+        except StopIteration:
+            return _END
+        if not self.prefetch_batches or not str(self.device).startswith("cuda"):
+            return batch
+        try:
+            return self.stage(batch)
+        except Exception as e:
+            return e
+
     def train_epoch(self, dataloader):
         for m in (self.visual_encoder, self.audio_encoder, self.fusion_module, self.decoder1):
             m.train()
         self.projection_layer = None
         total_loss = torch.zeros((), device=self.device)
+        self.loss_log_count = 0
         n = 0
-        for batch_idx, batch in enumerate(dataloader):
+        it = iter(dataloader)
+        cur = self._stage_next(it)
+        batch_idx = -1
+        while cur is not _END:
+            batch_idx += 1
+            loss = None
             try:
-                loss = self.train_step(batch)
+                if isinstance(cur, Exception):
+                    raise cur
+                loss = self.train_step(cur)
+            except Exception as e:                      # same policy as trainer.py:162-164
+                print(f"Error at batch {batch_idx}: {e}", flush=True)
+            # the next batch's copies run (side stream) under this step's GPU work; an error of the iterator itself
+            # propagates, as it does out of the reference's `for` statement
+            cur = self._stage_next(it)
+            if loss is None:
+                continue
+            try:
                 total_loss += loss.float()
+                self._log_loss(loss)
                 if self.verbose and batch_idx % 100 == 0:
                     c1, c2, k1, k2 = (float(x) for x in self._last_parts)
                     print(f"[Batch {batch_idx}] CTC1: {c1:.4f}, CTC2: {c2:.4f}, Contrast1: {k1:.4f}, "
                           f"Contrast2: {k2:.4f}, Total: {float(loss):.4f}", flush=True)
                     pred = torch.argmax(self._last_log_probs[0], dim=-1).cpu().tolist()
                     print(f"[pred] {self.tokenizer.decode(self.ctc_decode(pred))}", flush=True)
-            except Exception as e:                      # same policy as trainer.py:162-164
+                n += 1
+            except Exception as e:
                 print(f"Error at batch {batch_idx}: {e}", flush=True)
-                continue
-            n += 1
+        self.last_epoch_steps = n
         return float(total_loss) / max(len(dataloader), 1)
 
     def evaluate(self, dataloader):

@@ -123,3 +123,34 @@ def test_fast_decode_and_errors():
     assert pkg.fast_decode([5, 4, 6, 3, 99, -1, 4], Tok()) == "a b"
     with pytest.raises(RuntimeError):
         pkg.simple_beam_search(torch.zeros(4, 6).cuda(), beam_width=7, blank=0)
+
+
+def test_beam_config5_full_size_equals_collapsed_row_maximum():
+    """BASELINE config 5 at full size (4096 x [150, 800], beam 10).  Size-independent property of the reference's
+    search (beam_search.py:13-40): candidate (beam 0, k 0) is always inserted first and fp addition
+    is monotone, so the winning path is the per-frame first top-k index, i.e. the row argmax wherever the maximum is
+    unique; the returned ids are its CTC collapse.  Checked for all 4096 utterances against torch ops on the GPU, and
+    for a sample of them against the oracle."""
+    pkg = _pkg()
+    N, T, V, k, blank = 4096, 150, 800, 10, 3
+    g = torch.Generator(device="cuda").manual_seed(7)
+    lp = (3 * torch.randn(N, T, V, generator=g, device="cuda")).log_softmax(-1)
+    res = pkg.beam_search_batch(lp, beam_width=k, blank=blank)
+    top2 = lp.topk(2, dim=-1).values
+    unique_max = (top2[..., 0] > top2[..., 1]).all(dim=1).cpu().numpy()                   # [N]
+    assert unique_max.mean() > 0.9
+    am = lp.argmax(-1).cpu().numpy()                                                      # [N,T]
+    checked = 0
+    for i in range(N):
+        if not unique_max[i]:
+            continue
+        row = am[i]
+        keep = (row != blank) & np.concatenate(([True], row[1:] != row[:-1]))
+        assert res[i] == row[keep].tolist(), i
+        checked += 1
+    assert checked > 3600
+    for i in range(0, N, 512):
+        assert res[i] == oracle.beam_search(lp[i].cpu().numpy(), k, blank)
+    # decoding is a pure function of the utterance: any sub-batch, in any order, gives the same lists
+    sub = torch.tensor([4095, 17, 2048, 17], device="cuda")
+    assert pkg.beam_search_batch(lp[sub], beam_width=k, blank=blank) == [res[4095], res[17], res[2048], res[17]]

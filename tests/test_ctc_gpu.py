@@ -164,3 +164,54 @@ def test_ctc_peaked_inputs_take_the_log_domain_route(scale, gtol):
     assert abs(out[1][0] - ref["loss"]) <= 1e-4 * abs(ref["loss"])
     assert rel(out[1][1], ref["grad"]) < gtol
     assert out[1][0] == out[0][0] and np.array_equal(out[1][1], out[0][1])      # same kernels ran
+
+
+def test_ctc_config2_full_size_properties():
+    """BASELINE config 2 at its largest size (B=64, T=1000, V=801, the shape bench.py's roofline is quoted on).
+    The float64 oracle would take minutes here, so the check is (1) torch's own CTC run in float64 on the same GPU
+    (the arithmetic the reference's nn.CTCLoss calls, trainer.py:25) with the 1e-4 bar, and (2) size-independent
+    properties of the gradient convention: every row inside input_length sums to 0
+    (softmax-folded gradient), rows beyond input_length are exactly 0, loss 'sum' of 'none' equals 'sum'."""
+    pkg = _pkg()
+    T, B, V = 1000, 64, 801
+    lp, tg, il, tl = make_case(T, B, V, 0, 10, 80, seed=1000)
+    tgc, ilc, tlc = (torch.from_numpy(a).cuda() for a in (tg, il, tl))
+    x = lp.cuda().requires_grad_()
+    loss = pkg.ctc_loss(x, tgc, ilc, tlc, blank=0, reduction="mean", zero_infinity=True)
+    loss.backward()
+    y = lp.cuda().double().requires_grad_()
+    ref = torch.nn.functional.ctc_loss(y, tgc, ilc, tlc, blank=0, reduction="mean", zero_infinity=True)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())
+    err = (x.grad.double() - y.grad).abs().max() / y.grad.abs().max()
+    assert err.item() < 1e-4
+    g = x.grad
+    inside = torch.arange(T, device="cuda")[:, None] < ilc[None, :]                       # [T,B]
+    assert torch.all(g[~inside] == 0)
+    rows = g.double().sum(-1)                                                             # [T,B]
+    scale = g.double().abs().sum(-1).clamp_min(1e-30)
+    assert (rows.abs() / scale)[inside].max().item() < 1e-4
+    with torch.no_grad():
+        per = pkg.ctc_loss(lp.cuda(), tgc, ilc, tlc, blank=0, reduction="none")
+        tot = pkg.ctc_loss(lp.cuda(), tgc, ilc, tlc, blank=0, reduction="sum")
+    assert per.shape == (B,) and torch.isfinite(per).all()
+    assert abs(per.double().sum().item() - tot.item()) <= 1e-5 * abs(tot.item())
+
+
+def test_ctc_gradient_is_linear_in_grad_output_and_per_sample():
+    """Backward with per-sample grad_output w[b] equals w[b] times the backward with ones (reduction 'none'), and a
+    sample's gradient does not depend on the rest of the batch."""
+    pkg = _pkg()
+    lp, tg, il, tl = make_case(180, 6, 800, 3, 10, 40, seed=77)
+    tgc, ilc, tlc = (torch.from_numpy(a).cuda() for a in (tg, il, tl))
+    w = torch.tensor([0.5, -2.0, 1.0, 3.0, 0.0, 1.5], device="cuda")
+    x = lp.cuda().requires_grad_()
+    (pkg.ctc_loss(x, tgc, ilc, tlc, blank=3, reduction="none", zero_infinity=True) * w).sum().backward()
+    y = lp.cuda().requires_grad_()
+    pkg.ctc_loss(y, tgc, ilc, tlc, blank=3, reduction="none", zero_infinity=True).sum().backward()
+    want = y.grad * w[None, :, None]
+    assert rel(x.grad.cpu().numpy(), want.cpu().numpy()) < 1e-5
+    assert torch.all(x.grad[:, 4] == 0)
+    z = lp[:, 2:3].cuda().requires_grad_()
+    pkg.ctc_loss(z, tgc[2:3], ilc[2:3], tlc[2:3], blank=3, reduction="none", zero_infinity=True).sum().backward()
+    assert rel(z.grad[:, 0].cpu().numpy(), y.grad[:, 2].cpu().numpy()) < 5e-5     # other states-per-lane layout

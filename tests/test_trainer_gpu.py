@@ -79,12 +79,48 @@ def test_train_epoch_and_evaluate_end_to_end():
     l0 = tr.train_epoch(batches)
     l1 = tr.train_epoch(batches)
     assert np.isfinite(l0) and np.isfinite(l1) and l0 > 0
+    assert tr.last_epoch_steps == 3 and tr.loss_log_count == 3        # every step ran; its loss was logged to the host
+    assert float(tr.loss_log[:3].mean()) == pytest.approx(l1, rel=1e-5)
     assert not torch.equal(w0, dec.net[0].weight.detach())            # the optimiser moved the CTC head
     assert fus.cross_attn_visual.in_proj_weight.grad is None         # never used, like the reference
     assert any(p.grad is not None for n, p in aud.model.named_parameters() if "encoder.layers.7." in n)
     loss, wer = tr.evaluate(batches[:2])
     assert np.isfinite(loss) and 0.0 <= wer
     assert tr.ctc_decode([5, 5, 3, 5, 6, 3, 3, 6]) == [5, 6]          # blank does not reset prev (trainer.py:168-177)
+
+
+def test_train_epoch_prefetch_changes_no_value():
+    """train_epoch stages batch i+1 (side-stream H2D) while step i runs; the losses are those of the plain loop."""
+    pkg = _pkg()
+    from multimodal_av_model_b200.synthetic import CharTokenizer, make_batch
+    batches = [make_batch(pairs=2, seconds=1.0, t_v=30, seed=s, l_range=(3, 8), pin=(s % 2 == 0)) for s in range(4)]
+    logs = {}
+    for prefetch in (False, True):
+        vis, aud, fus, dec = tiny_models(pkg)
+        tr = pkg.MultimodalTrainer(vis, aud, fus, dec, CharTokenizer(800), device="cuda")
+        tr.verbose = False
+        tr.prefetch_batches = prefetch
+        torch.manual_seed(11)
+        np.random.seed(11)                      # transformers draws the SpecAugment spans from numpy's global RNG
+        avg = tr.train_epoch(batches)
+        assert tr.last_epoch_steps == 4
+        logs[prefetch] = (avg, tr.loss_log[:4].clone())
+    assert logs[True][0] == pytest.approx(logs[False][0], rel=2e-3)
+    assert torch.allclose(logs[True][1], logs[False][1], rtol=5e-3)     # fp32 atomics order in split-K weight gradients
+
+
+def test_train_epoch_keeps_going_after_a_bad_batch(capsys):
+    """trainer.py:162-164: a batch that raises is reported and skipped, also when it fails while being staged."""
+    pkg = _pkg()
+    from multimodal_av_model_b200.synthetic import CharTokenizer, make_batch
+    vis, aud, fus, dec = tiny_models(pkg)
+    tr = pkg.MultimodalTrainer(vis, aud, fus, dec, CharTokenizer(800), device="cuda")
+    tr.verbose = False
+    good = make_batch(pairs=2, seconds=1.0, t_v=30, seed=0, l_range=(3, 8))
+    bad = {k: v for k, v in good.items() if k != "lip2"}             # KeyError inside stage()
+    loss = tr.train_epoch([good, bad, good])
+    assert tr.last_epoch_steps == 2 and np.isfinite(loss)
+    assert "Error at batch 1" in capsys.readouterr().out
 
 
 def test_wer_matches_jiwer_definition():
