@@ -35,6 +35,12 @@ constexpr int kChainFirst = 0x40000000;
 // probability-domain scan is used: p = exp(lp - max) >= e^-40 = 2^-58, so two frames between renormalisations stay
 // inside fp32's exponent range.  Beyond it the batch is recomputed by the log-domain kernels (device-side flag).
 constexpr float kLinSafeRange = 40.f;
+// Workspace tail: the guard flag (first int of kFlagBytes) followed by one completion counter per sample.  Every
+// probability-domain scan CTA adds 2 to done[b] (release) when all of its alpha/beta rows, nll and repeat chains are
+// in memory; kDoneTarget = both directions.  The gradient pass, when it is launched right behind the scan (PDL), starts
+// on a sample as soon as its counter is complete instead of waiting for the whole scan grid (see ctc_grad_lin_kernel).
+constexpr size_t kFlagBytes = 256;
+constexpr int kDoneTarget = 4;
 
 struct CtcPlan {
     int K, W, S_pad, Lpad, linear;
@@ -85,7 +91,7 @@ static bool make_plan(int T, int B, int Lmax, CtcPlan* pl) {
     pl->off_coff_b = o; o = align_up(o + TB * pl->CW * sizeof(int), 256);
     pl->off_nll2 = o; o = align_up(o + (size_t)B * sizeof(double), 256);
     pl->off_chain = o; o = align_up(o + (size_t)B * pl->Lpad * sizeof(int), 256);
-    pl->off_flag = o; o = align_up(o + 256, 256);
+    pl->off_flag = o; o = align_up(o + kFlagBytes + (size_t)B * sizeof(int), 256);   // guard flag, then done[B]
     pl->total = o;
     return true;
 }
@@ -103,7 +109,37 @@ struct ScanParams {
     int* flag;         // device int: set to 1 by the probability-domain scan when an emission ratio is out of its safe
                        // range; the log-domain kernels run only when run_if == *flag (flag == nullptr: always)
     int run_if;
+    int* done;         // per-sample completion counters (nullptr: not signalled)
+    int stamp;         // debug timestamps into the flag block
 };
+
+// all lanes of a warp: everything this warp stored is visible device-wide before the counter moves
+__device__ __forceinline__ void signal_done(int* done, int b, int lane, int amount) {
+    if (!done) return;
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(done + b, amount);
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Debug stamps (tuning knob "ctc_stamp"): four u64 at byte 64 of the flag block = first scan CTA start (stored as ~t),
+// last scan CTA end, last gradient warp end, first gradient chunk started in early mode (~t; 0 = none) -- globaltimer ns.  The flag block is zeroed by avctc_ctc_forward.
+__device__ __forceinline__ void stamp_min(int* flag, int slot) {      // stored as max(~t): the block starts as zeros
+    unsigned long long* s = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(flag) + 64) + slot;
+    atomicMax(s, ~global_timer_ns());
+}
+__device__ __forceinline__ void stamp_max(int* flag, int slot) {
+    unsigned long long* s = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(flag) + 64) + slot;
+    atomicMax(s, global_timer_ns());
+}
+__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 template <int K>
 __device__ __forceinline__ void store_states(float* dst, const float (&a)[K]) {
@@ -426,6 +462,7 @@ __global__ void __launch_bounds__(32) ctc_scan_lin_kernel(const ScanParams p) {
         }
         if (dir == 0 && p.chain)
             for (int j = lane; j < L; j += 32) p.chain[(size_t)b * p.Lpad + j] = kChainFirst | kChainNone;
+        signal_done(p.done, b, lane, 2);
         return;
     }
     if (lane < 2) fin[lane] = -(double)CUDART_INF_F;
@@ -648,6 +685,7 @@ __global__ void __launch_bounds__(32) ctc_scan_lin_kernel(const ScanParams p) {
             }
         }
     }
+    signal_done(p.done, b, lane, 2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -663,6 +701,8 @@ struct GradParams {
     const double* nll2; const int* chain;
     int K, W, S_pad, Lpad, linear;
     int cw; const int* flag; int run_if;
+    int stamp;        // debug timestamps into the flag block
+    const int* done;  // grad_lin: per-sample completion counters of the scan (nullptr: wait for the whole grid)
     int prefetch;     // grad_lin: L2-prefetch the warp's next log-prob row (tuning knob "ctc_pf")
     int row_floats;   // per-warp smem floats for one staged row (>= V + 8, multiple of 4)
     int w_floats;     // per-warp smem floats for state weights (>= 2*Lmax+1, multiple of 4)
@@ -939,6 +979,7 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
     const int b = blockIdx.x, dir = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_launch_dependents();     // the small kernels behind this one (guarded log-domain scan, reduce) wait for it themselves
+    if (p.stamp && p.flag && threadIdx.x == 0) stamp_min(p.flag, 0);
     extern __shared__ __align__(128) unsigned char ws_smem[];
     unsigned char* rowbuf = ws_smem;                                               // [2][NG][G][row_stride_bytes]
     float* pring = reinterpret_cast<float*>(ws_smem + (size_t)2 * NG * G * row_stride_bytes);   // [RD][32][PW]
@@ -962,6 +1003,11 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
         }
         if (dir == 0 && p.chain)
             for (int j = threadIdx.x; j < L; j += blockDim.x) p.chain[(size_t)b * p.Lpad + j] = kChainFirst | kChainNone;
+        if (p.done) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(p.done + b, 2);
+        }
         return;
     }
     if (threadIdx.x < 128) prog[threadIdx.x] = 1;
@@ -1148,7 +1194,7 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
 
     if (warp == 3) {
         // ================================================================ writer
-        if (!do_store || Tb < 2) return;
+        if (!do_store || Tb < 2) { signal_done(p.done, b, lane, 1); return; }
         const size_t rowi1 = (size_t)b * p.T + (dir ? Tb - 2 : 1);       // scan frame 1
         float* wsp = (dir ? p.beta : p.alpha) + rowi1 * p.S_pad + (size_t)g * K;
         int* cfp = (dir ? p.coff_b : p.coff_a) + rowi1 * p.cw + g;
@@ -1179,6 +1225,8 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
             *cfp = __float_as_int(pay[K]);
             wsp += wstep; cfp += cstep;
         }
+        signal_done(p.done, b, lane, 1);          // this direction's rows 1 .. Tb-1 are in memory
+        if (p.stamp && p.flag && lane == 0) stamp_max(p.flag, 1);
         return;
     }
 
@@ -1347,6 +1395,8 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
             }
         }
     }
+    signal_done(p.done, b, lane, 1);              // frame 0, nll and the repeat chains are in memory
+    if (p.stamp && p.flag && lane == 0) stamp_max(p.flag, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1423,6 +1473,9 @@ __device__ __forceinline__ void grad_stream_row(const TIn* __restrict__ lrow, TI
     }
 }
 
+constexpr int kZeroChunk = 4;          // early mode: rows beyond the input length are handed out four at a time
+constexpr int kSpreadMaxB = 256;      // batch sizes whose completion order is sorted inside the gradient kernel
+
 template <int K, typename TIn>
 __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(const GradParams p) {
     constexpr int KL = K / 2;
@@ -1430,14 +1483,105 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     pdl_launch_dependents();
-    pdl_wait();             // PDL launch: the scan kernels and whatever produced grad_out are complete from here on
-    if (p.flag && *p.flag != p.run_if) return;
+    // Launched with the PDL attribute, this grid can be resident while the scan before it on the stream is still
+    // running (backward enqueued right behind forward).  If every sample's completion counter is already full the
+    // kernel takes the ordinary route: griddepcontrol.wait, after which everything before it on the stream (scan,
+    // guard flag, whatever produced grad_out) is complete, then a fixed set of warps per sample.  Otherwise the scan
+    // is still in flight -- which implies that nothing but this library's own PDL-chained kernels sits between it and
+    // this launch, so grad_out predates the scan -- and the grid works "early": samples are taken in the order their
+    // scans finish (= order of input length), cut into chunks of consecutive frames that the resident warps draw from
+    // a ticket counter, each chunk waiting only for ITS sample's counter.  The bandwidth-bound gradient rows of the
+    // short utterances then stream while the latency-bound recurrences of the long ones still run.  (Tickets, not a
+    // fixed chunk -> warp map: while the scan holds its shared memory only part of this grid is resident, and a
+    // chunk owned by a CTA that cannot start yet would wait for the whole scan.)
+    // Control words in the flag block (zeroed by avctc_ctc_forward, re-zeroed by the last warp of this grid):
+    // int[32] mode (0 undecided, 1 ordinary, 2 early; the first CTA decides for the grid), int[33] next ticket,
+    // int[34] CTAs finished, int[35] next ticket of the zero rows.
+    __shared__ int early_s, chunk_s, warps_left_s;
+    __shared__ int tb_s[kSpreadMaxB], order_s[kSpreadMaxB], start_s[kSpreadMaxB + 1], zstart_s[kSpreadMaxB + 1];
+    int* const ctrl = p.done ? const_cast<int*>(p.flag) + 32 : nullptr;
+    if (threadIdx.x < 32) {
+        int mode = 1;
+        if (ctrl && p.B <= kSpreadMaxB) {
+            bool all = true;
+            for (int i = lane; i < p.B; i += 32) all = all && (ld_acquire_gpu_s32(p.done + i) >= kDoneTarget);
+            all = __all_sync(kFullMask, all);
+            if (lane == 0) {
+                const int want = all ? 1 : 2;
+                const int old = atomicCAS(ctrl, 0, want);
+                mode = old ? old : want;
+            }
+        }
+        if (lane == 0) { early_s = (mode == 2) ? 1 : 0; warps_left_s = nwarp; }
+    }
+    __syncthreads();
+    const bool early = early_s != 0;
+    const int gw = blockIdx.x * nwarp + warp, Wtot = gridDim.x * nwarp;
+    // ---- balanced mapping (set up before any waiting; input lengths are inputs of the forward pass too): samples in
+    // order of input length (= the order in which their scans finish), each cut into chunks of consecutive frames;
+    // chunk i of that list goes to warp i mod Wtot.  Every warp gets the same number of chunks (utterances of
+    // different lengths no longer decide which warps finish last) and meets the samples in the order they complete.
+    const bool use_spread = early;
+    auto finish = [&]() {            // every warp, exactly once, on its way out
+        if (p.stamp && p.flag && lane == 0) stamp_max(const_cast<int*>(p.flag), 2);
+        // Last warp of the CTA reports the CTA; the last CTA of the grid re-arms the control words for the next launch.
+        // No fence needed: a warp's ticket draws have returned (it compared them) before it gets here.
+        if (ctrl && lane == 0 && atomicSub(&warps_left_s, 1) == 1) {
+            if (atomicAdd(ctrl + 2, 1) == (int)gridDim.x - 1) {
+                ctrl[1] = 0; ctrl[2] = 0; ctrl[3] = 0;
+                __threadfence();
+                ctrl[0] = 0;
+            }
+        }
+    };
+    if (use_spread) {
+        const int tid = threadIdx.x;
+        int mine = 0;
+        if (tid < p.B) {
+            const long long v = p.input_lengths[tid];
+            mine = (int)(v < 0 ? 0 : (v > p.T ? p.T : v));
+            tb_s[tid] = mine;
+        }
+        __syncthreads();
+        if (tid < p.B) {
+            int R = 0;
+            for (int j = 0; j < p.B; ++j) R += tb_s[j];
+            int c = R / (Wtot * 4);
+            c = c < 1 ? 1 : (c > 16 ? 16 : c);
+            order_s[tid] = (mine + c - 1) / c;               // chunks of this sample (order_s is scratch until below)
+            if (tid == 0) chunk_s = c;
+        }
+        __syncthreads();
+        int rank = 0, start = 0, nch = 0, zs = 0;
+        if (tid < p.B) {
+            nch = order_s[tid];
+            for (int j = 0; j < p.B; ++j) {
+                const int o = tb_s[j];
+                const bool before = (o < mine) || (o == mine && j < tid);
+                rank += before ? 1 : 0;
+                start += before ? order_s[j] : 0;
+                zs += (j < tid) ? (p.T - o + kZeroChunk - 1) / kZeroChunk : 0;
+            }
+            zstart_s[tid] = zs;
+            if (tid == p.B - 1) zstart_s[p.B] = zs + (p.T - mine + kZeroChunk - 1) / kZeroChunk;
+        }
+        __syncthreads();
+        if (tid < p.B) {
+            order_s[rank] = tid;
+            start_s[rank] = start;
+            if (rank == p.B - 1) start_s[p.B] = start + nch;
+        }
+        __syncthreads();
+    }
+    if (!early) {
+        pdl_wait();
+        if (p.flag && *p.flag != p.run_if) { finish(); return; }
+    }
     float* delta = smem + (size_t)warp * (p.row_floats + p.w_floats);   // class posteriors; all-zero between rows
     float* wbuf = delta + p.row_floats;                                  // label-state weights of the current row
     for (int i = lane; i < p.row_floats; i += 32) delta[i] = 0.f;
     __syncwarp();
-    const int gw = blockIdx.x * nwarp + warp, Wtot = gridDim.x * nwarp;
-    const int WS = max(1, Wtot / p.B);                                   // warps per sample
+    const int WS = max(1, Wtot / p.B);                                   // warps per sample (static mapping)
     const long long nitems = (long long)p.B * WS;
     TIn* grad = reinterpret_cast<TIn*>(p.grad);
     const TIn* lpbase = reinterpret_cast<const TIn*>(p.lp);
@@ -1447,14 +1591,76 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
     const bool pf_ab = (p.prefetch & 4) != 0;
     const int ab_lines = min(16, (p.S_pad * 4 + 127) / 128);
 
-    for (long long item = gw; item < nitems; item += Wtot) {
-        const int b = (int)(item % p.B), r = (int)(item / p.B);
-        long long tbl = p.input_lengths[b], tll = p.target_lengths[b];
-        const int Tb = (int)(tbl < 0 ? 0 : (tbl > p.T ? p.T : tbl));
+    auto clamp_tb = [&](int bb) -> int {
+        const long long v = p.input_lengths[bb];
+        return (int)(v < 0 ? 0 : (v > p.T ? p.T : v));
+    };
+    auto zero_row = [&](TIn* grow) {
+        const int o_out = (int)((reinterpret_cast<uintptr_t>(grow) / sizeof(TIn)) & (kVec - 1));
+        const int nq = (o_out + p.V + kVec - 1) / kVec;
+        for (int q = lane; q < nq; q += 32) {
+            const int c0 = q * kVec - o_out;
+            if (c0 >= 0 && c0 + kVec <= p.V) __stcs(reinterpret_cast<uint4*>(grow + c0), make_uint4(0, 0, 0, 0));
+            else
+                for (int k = 0; k < kVec; ++k)
+                    if (c0 + k >= 0 && c0 + k < p.V) {
+                        if constexpr (sizeof(TIn) == 4) grow[c0 + k] = 0.f;
+                        else grow[c0 + k] = __float2bfloat16(0.f);
+                    }
+        }
+    };
+
+    // ---- rows beyond the input length are zero whatever the scan finds: written first, before any waiting (early
+    // mode: drawn from their own ticket counter, so the CTAs that are resident from the start write all of them while
+    // no sample is complete yet)
+    if (early) {
+        const int nz = zstart_s[p.B];
+        for (;;) {
+            int z = 0;
+            if (lane == 0) z = atomicAdd(ctrl + 3, 1);
+            z = __shfl_sync(kFullMask, z, 0);
+            if (z >= nz) break;
+            int lo = 0, hi = p.B - 1;                       // last sample whose first zero chunk is <= z
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (zstart_s[mid] <= z) lo = mid; else hi = mid - 1;
+            }
+            const int t0 = tb_s[lo] + (z - zstart_s[lo]) * kZeroChunk;
+            for (int t = t0; t < min(t0 + kZeroChunk, p.T); ++t) zero_row(grad + ((size_t)t * p.B + lo) * p.V);
+        }
+    } else {
+        for (long long item = gw; item < nitems; item += Wtot) {
+            const int b = (int)(item % p.B), r = (int)(item / p.B);
+            const int Tb = clamp_tb(b);
+            int t = r + ((max(Tb - r, 0) + WS - 1) / WS) * WS;           // first row of this warp with t >= Tb
+            for (; t < p.T; t += WS) zero_row(grad + ((size_t)t * p.B + b) * p.V);
+        }
+    }
+
+    // ---- rows t0, t0+step, ... < t1 of sample b
+    auto process = [&](const int b, const int t0, const int t1, const int step) {
+        if (t0 >= t1) return;
+        if (early) {
+            if (lane == 0) {
+                int spins = 0;
+                while (ld_acquire_gpu_s32(p.done + b) < kDoneTarget) {
+                    __nanosleep(500);
+                    if (++spins > (1 << 23)) __trap();      // never hang the GPU on a protocol bug
+                }
+            }
+            __syncwarp();
+            __threadfence();
+            if (p.stamp && lane == 0) stamp_min(const_cast<int*>(p.flag), 3);
+        }
+        long long tll = p.target_lengths[b];
         const int L = (int)(tll < 0 ? 0 : (tll > p.Lmax ? p.Lmax : tll));
         const int S = 2 * L + 1;
         const float nllb = p.nll[b];
         const bool zero_all = (p.zero_infinity && nllb == CUDART_INF_F);
+        if (zero_all) {
+            for (int t = t0; t < t1; t += step) zero_row(grad + ((size_t)t * p.B + b) * p.V);
+            return;
+        }
         const double nll2 = p.nll2[b];                                   // -log2 P
         const bool bad = !(fabs(nll2) < 1.0e300);                        // infeasible without zero_infinity: NaN rows
         const double nfl = bad ? 0.0 : floor(nll2);
@@ -1481,32 +1687,18 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
         const int nval = min(max(S - s0, 0), K);
         const int sm0 = S - 1 - s0;              // beta (mirrored) index of state s0; state s0+j -> sm0 - j
 
-        for (int t = r; t < p.T; t += WS) {
+        for (int t = t0; t < t1; t += step) {
             const long long row = (long long)t * p.B + b;
             TIn* grow = grad + (size_t)row * p.V;
             const int o_out = (int)((reinterpret_cast<uintptr_t>(grow) / sizeof(TIn)) & (kVec - 1));
-            if (t >= Tb || zero_all) {
-                const int nq = (o_out + p.V + kVec - 1) / kVec;
-                for (int q = lane; q < nq; q += 32) {
-                    const int c0 = q * kVec - o_out;
-                    if (c0 >= 0 && c0 + kVec <= p.V) __stcs(reinterpret_cast<uint4*>(grow + c0), make_uint4(0, 0, 0, 0));
-                    else
-                        for (int k = 0; k < kVec; ++k)
-                            if (c0 + k >= 0 && c0 + k < p.V) {
-                                if constexpr (sizeof(TIn) == 4) grow[c0 + k] = 0.f;
-                                else grow[c0 + k] = __float2bfloat16(0.f);
-                            }
-                }
-                continue;
-            }
             const TIn* lrow = lpbase + (int64_t)t * p.stride_t + (int64_t)b * p.stride_b;
-            if (pf_lines > 0 && t + pf_dist * WS < Tb) {      // a later row of this warp: pull its lines into L2 now
+            if (pf_lines > 0 && t + pf_dist * step < t1) {    // a later row of this warp: pull its lines into L2 now
                 if (lane < pf_lines) {
-                    const char* nx = reinterpret_cast<const char*>(lrow + (int64_t)pf_dist * WS * p.stride_t) + lane * 128;
+                    const char* nx = reinterpret_cast<const char*>(lrow + (int64_t)pf_dist * step * p.stride_t) + lane * 128;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
                 }
                 if (pf_ab && lane < 2 * ab_lines) {
-                    const size_t rn = ((size_t)b * p.T + t + (size_t)pf_dist * WS) * p.S_pad;
+                    const size_t rn = ((size_t)b * p.T + t + (size_t)pf_dist * step) * p.S_pad;
                     const char* nx = reinterpret_cast<const char*>((lane < ab_lines ? p.alpha : p.beta) + rn) +
                                      (lane < ab_lines ? lane : lane - ab_lines) * 128;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
@@ -1579,7 +1771,54 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
             if (lane == 0) delta[o_out + p.blank] = 0.f;
             __syncwarp();
         }
+    };
+
+    if (use_spread) {
+        const int c = chunk_s, ntasks = start_s[p.B];
+        auto draw = [&]() -> int {
+            int v = 0;
+            if (lane == 0) v = atomicAdd(ctrl + 1, 1);
+            return __shfl_sync(kFullMask, v, 0);
+        };
+        int task = draw();
+        while (task < ntasks) {
+            const int nxt = draw();                         // its round trip hides behind this chunk
+            auto locate = [&](const int tk, int& bb, int& tt) {
+                int lo = 0, hi = p.B - 1;                   // last rank whose first chunk is <= tk
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (start_s[mid] <= tk) lo = mid; else hi = mid - 1;
+                }
+                bb = order_s[lo];
+                tt = (tk - start_s[lo]) * c;
+            };
+            int b, t0;
+            locate(task, b, t0);
+            if (nxt < ntasks && pf_lines > 0) {             // first row of the next chunk: log-probs (and alpha/beta) into L2
+                int bn, tn;
+                locate(nxt, bn, tn);
+                if (lane < pf_lines)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(
+                        lpbase + (int64_t)tn * p.stride_t + (int64_t)bn * p.stride_b) + lane * 128));
+                if (lane < 2 * ab_lines) {
+                    const size_t rn = ((size_t)bn * p.T + tn) * p.S_pad;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(
+                        (lane < ab_lines ? p.alpha : p.beta) + rn) + (lane < ab_lines ? lane : lane - ab_lines) * 128));
+                }
+            }
+            // guard tripped (so far): the log-domain kernels behind this one redo the whole batch, also when the guard
+            // trips later and rows computed here from half-rewritten workspaces are garbage
+            if (p.flag && *reinterpret_cast<const volatile int*>(p.flag) != p.run_if) break;
+            process(b, t0, min(t0 + c, tb_s[b]), 1);
+            task = nxt;
+        }
+    } else {
+        for (long long item = gw; item < nitems; item += Wtot) {
+            const int b = (int)(item % p.B), r = (int)(item / p.B);
+            process(b, r, clamp_tb(b), WS);
+        }
     }
+    finish();
 }
 
 __global__ void ctc_reduce_kernel(const float* __restrict__ nll, const int64_t* __restrict__ tl, int B,
@@ -1804,14 +2043,15 @@ extern "C" int avctc_ctc_forward(const void* log_probs, int dtype, int64_t strid
     sp.nll2 = need_grad ? reinterpret_cast<double*>(w + pl.off_nll2) : nullptr;
     sp.chain = need_grad ? reinterpret_cast<int*>(w + pl.off_chain) : nullptr;
     sp.W = pl.W; sp.S_pad = pl.S_pad; sp.Lpad = pl.Lpad;
-    sp.cw = pl.CW; sp.flag = nullptr; sp.run_if = 0;
+    sp.cw = pl.CW; sp.flag = nullptr; sp.run_if = 0; sp.done = nullptr; sp.stamp = avctc_tuning_get("ctc_stamp", 0);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int ndir = need_grad ? 2 : 1;
     // The probability-domain scan needs the device flag of the workspace for its range guard; a forward-only call
     // without workspace (evaluation) goes straight to the log-domain kernel.
     if (pl.linear && need_grad) {
         sp.flag = reinterpret_cast<int*>(w + pl.off_flag);
-        AVCTC_CUDA_RETURN(cudaMemsetAsync(sp.flag, 0, sizeof(int), st));
+        sp.done = reinterpret_cast<int*>(w + pl.off_flag + kFlagBytes);
+        AVCTC_CUDA_RETURN(cudaMemsetAsync(sp.flag, 0, kFlagBytes + (size_t)B * sizeof(int), st));
         int rc = (dtype == AVCTC_F32) ? dispatch_scan_lin<float>(sp, pl.K, ndir, st)
                                       : dispatch_scan_lin<__nv_bfloat16>(sp, pl.K, ndir, st);
         if (rc) return rc;
@@ -1865,7 +2105,7 @@ extern "C" int avctc_ctc_backward(const void* log_probs, int dtype, int64_t stri
     gp.nll2 = reinterpret_cast<const double*>(w + pl.off_nll2);
     gp.chain = reinterpret_cast<const int*>(w + pl.off_chain);
     gp.K = pl.K; gp.W = pl.W; gp.S_pad = pl.S_pad; gp.Lpad = pl.Lpad; gp.linear = pl.linear;
-    gp.cw = pl.CW; gp.flag = nullptr; gp.run_if = 0;
+    gp.cw = pl.CW; gp.flag = nullptr; gp.run_if = 0; gp.done = nullptr; gp.stamp = avctc_tuning_get("ctc_stamp", 0);
     gp.prefetch = avctc_tuning_get("ctc_pf", 1);
     gp.row_floats = (V + 8 + 3) & ~3;
     gp.w_floats = (2 * max_target_len + 1 + 3) & ~3;
@@ -1873,6 +2113,8 @@ extern "C" int avctc_ctc_backward(const void* log_probs, int dtype, int64_t stri
     if (pl.linear) {
         gp.flag = reinterpret_cast<const int*>(w + pl.off_flag);
         gp.run_if = 0;                            // guard not tripped: probability-domain workspaces
+        if (avctc_tuning_get("ctc_overlap", 1) != 0)
+            gp.done = reinterpret_cast<const int*>(w + pl.off_flag + kFlagBytes);
         int rc = (dtype == AVCTC_F32) ? dispatch_grad_lin<float>(gp, st) : dispatch_grad_lin<__nv_bfloat16>(gp, st);
         if (rc) return rc;
         GradParams gl = gp;                       // guard tripped: the log-domain scan rewrote the workspaces

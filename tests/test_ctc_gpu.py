@@ -215,3 +215,65 @@ def test_ctc_gradient_is_linear_in_grad_output_and_per_sample():
     z = lp[:, 2:3].cuda().requires_grad_()
     pkg.ctc_loss(z, tgc[2:3], ilc[2:3], tlc[2:3], blank=3, reduction="none", zero_infinity=True).sum().backward()
     assert rel(z.grad[:, 0].cpu().numpy(), y.grad[:, 2].cpu().numpy()) < 5e-5     # other states-per-lane layout
+
+
+def _c_abi_fwd_bwd(pkg, lp, tg, il, tl, blank, nbwd=1, stamp=False):
+    """avctc_ctc_forward / reduce / backward enqueued back to back (no other stream work in between): the gradient
+    kernel is then resident while the scan still runs and takes its 'early' route.  Returns (loss, grad, stamps)."""
+    L = pkg._lib.lib()
+    T, B, V = lp.shape
+    Lm = int(tg.shape[1])
+    wsb = int(L.avctc_ctc_workspace_bytes(T, B, Lm))
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    nll = torch.empty(B, device="cuda"); loss = torch.empty(1, device="cuda")
+    go = torch.ones(1, device="cuda"); grad = torch.full_like(lp, float("nan"))
+    st = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+    pkg._lib.set_tuning("ctc_stamp", 1 if stamp else 0)
+    try:
+        pkg._lib.check(L.avctc_ctc_forward(lp.data_ptr(), 0, lp.stride(0), lp.stride(1), T, B, V, tg.data_ptr(), tg.stride(0),
+                                           None, il.data_ptr(), tl.data_ptr(), Lm, blank, 1, nll.data_ptr(), ws.data_ptr(), wsb, st), "fwd")
+        pkg._lib.check(L.avctc_ctc_reduce(nll.data_ptr(), tl.data_ptr(), B, 1, 1, loss.data_ptr(), st), "reduce")
+        for _ in range(nbwd):
+            pkg._lib.check(L.avctc_ctc_backward(lp.data_ptr(), 0, lp.stride(0), lp.stride(1), T, B, V, tg.data_ptr(), tg.stride(0),
+                                                None, il.data_ptr(), tl.data_ptr(), Lm, blank, 1, 1, nll.data_ptr(), go.data_ptr(), 0,
+                                                grad.data_ptr(), ws.data_ptr(), wsb, st), "bwd")
+        torch.cuda.synchronize()
+    finally:
+        pkg._lib.set_tuning("ctc_stamp", 0)
+    blk = ws[wsb - ((256 + 4 * B + 255) // 256) * 256:]
+    stamps = blk[64:96].cpu().numpy().view(np.uint64)
+    ctrl = blk[128:144].cpu().numpy().view(np.int32)
+    assert not ctrl.any()                       # mode / tickets / counters re-armed by the last CTA
+    return loss.item(), grad, stamps
+
+
+@pytest.mark.parametrize("scale", [1.0, 60.0])
+def test_ctc_backward_launched_right_behind_forward(scale):
+    """Backward enqueued directly behind forward (bench.py's fwd+bwd, any caller that computes the gradient at once):
+    the gradient kernel starts on each utterance as soon as that utterance's alpha/beta rows are complete instead of
+    waiting for the whole scan grid.  Same bits as the serialised order (ctc_overlap=0), also when the launch is
+    repeated on one workspace, when backward runs twice, and (scale 60) when the range guard trips while gradient
+    rows are already being written and the log-domain kernels redo the batch."""
+    pkg = _pkg()
+    T, B, V = 1000, 64, 801
+    lp, tg, il, tl = make_case(T, B, V, 0, 10, 80, seed=5, scale=scale)
+    lp = lp.cuda(); tgc, ilc, tlc = (torch.from_numpy(a).cuda() for a in (tg, il, tl))
+    pkg._lib.set_tuning("ctc_overlap", 0)
+    try:
+        loss0, grad0, _ = _c_abi_fwd_bwd(pkg, lp, tgc, ilc, tlc, 0)
+    finally:
+        pkg._lib.set_tuning("ctc_overlap", 1)
+    assert torch.isfinite(grad0).all()
+    overlapped = 0
+    for rep in range(3):
+        loss1, grad1, stamps = _c_abi_fwd_bwd(pkg, lp, tgc, ilc, tlc, 0, nbwd=1 + (rep == 2), stamp=True)
+        assert loss1 == loss0
+        assert torch.equal(grad1, grad0)
+        scan_end, first_early = int(stamps[1]), int(~stamps[3]) if stamps[3] else 0
+        overlapped += int(first_early != 0 and first_early < scan_end)
+    if scale == 1.0:
+        assert overlapped >= 2                  # the early route really ran under the scan
+    x = lp.clone().requires_grad_()
+    pkg.ctc_loss(x, tgc, ilc, tlc, blank=0, reduction="mean", zero_infinity=True).backward()
+    assert torch.equal(x.grad, grad0)           # the autograd route (serialised by torch's own kernels) agrees
