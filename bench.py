@@ -544,8 +544,11 @@ def main():
                             "peak_src": peaks["src"] + " (burst copy bandwidth, MEASURED_PEAKS.json)", "traffic": traffic,
                             "algorithmic_bytes": top["algorithmic_bytes"],
                             "grad_kernel_frac": top["grad_kernel_gbs"] / peaks["hbm"],
-                            "note": "achieved = 2*T*B*V*4 bytes / (scan + grad) time, both kernels timed back to back with CUDA events; "
-                                    "the scan is a 1000-step dependent recurrence over 128 CTAs (latency-bound), the gradient pass streams"}
+                            "note": "achieved = 2*T*B*V*4 bytes / time of forward + backward enqueued back to back (one pair of CUDA "
+                                    "events around both); the scan is a 1000-step dependent recurrence over 128 CTAs (latency-bound), "
+                                    "the gradient pass streams and starts on each utterance as soon as its alpha/beta rows are "
+                                    "complete, so fwd_bwd_ms < scan_ms + grad_ms (each timed alone); traffic is the sum of the two "
+                                    "kernels' DRAM bytes from the round-1 ncu capture"}
     if fusion is not None:
         line["fusion"] = fusion
     if args.workload != "train":

