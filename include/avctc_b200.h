@@ -86,7 +86,13 @@ AVCTC_API int avctc_ctc_reduce(const float* nll, const int64_t* target_lengths, 
 /* grad[T,B,V] (contiguous, dtype = log_probs dtype) = d loss / d log_probs in ATen's softmax-folded
  * convention: (exp(lp) - posterior) * g_b for t < input_length, 0 elsewhere and 0 for infeasible
  * samples when zero_infinity.  g_b = grad_out[b*grad_out_stride] * (mean: 1/(B*max(L_b,1)); else 1);
- * grad_out is a DEVICE fp32 scalar (stride 0) or [B] vector. */
+ * grad_out is a DEVICE fp32 scalar (stride 0) or [B] vector.
+ * `workspace` is the one avctc_ctc_forward(need_grad=1) filled, untouched in between, on the same stream (or ordered
+ * behind it); it is declared const because alpha/beta are only read, but the kernel does update a few control words in
+ * its last block and leaves them as it found them.  The call may be enqueued directly behind avctc_ctc_forward
+ * (avctc_ctc_reduce in between is fine): the gradient of each utterance then starts as soon as that utterance's
+ * lattice rows are complete, under the scans of the longer ones; grad_out must in that case have been written
+ * before avctc_ctc_forward was enqueued (anything else on the stream between the two calls orders them fully). */
 AVCTC_API int avctc_ctc_backward(const void* log_probs, int dtype, int64_t stride_t, int64_t stride_b,
                        int T, int B, int V,
                        const int64_t* targets, int64_t target_stride, const int64_t* target_offsets,
