@@ -38,6 +38,28 @@ def test_library_exports_every_declared_symbol():
     assert lib.avctc_beam_workspace_bytes(8, 150, 800, 33) == 0
 
 
+def test_ctc_workspace_plan_and_tuning_knobs():
+    """Host-only entry points: the CTC workspace holds alpha and beta ([B,T,32K] fp32 each, K >= ceil((2L+1)/32)) plus the
+    flag block with one completion counter per sample, and every documented knob is known."""
+    import multimodal_av_model_b200 as pkg
+    lib = pkg._lib.lib()
+    T, L = 1000, 80
+    s_pad = 32 * 6                                              # 2L+1 = 161 states -> 6 per lane
+    sizes = [lib.avctc_ctc_workspace_bytes(T, B, L) for B in (1, 64, 65, 256)]
+    assert sizes == sorted(sizes) and len(set(sizes)) == 4
+    assert sizes[1] >= 2 * T * 64 * s_pad * 4 + 256 + 4 * 64
+    assert lib.avctc_ctc_workspace_bytes(0, 4, 3) > 0 and lib.avctc_ctc_workspace_bytes(-1, 4, 3) == 0
+    hdr = open(HEADER).read()
+    knobs = set(re.findall(r'"((?:ctc|beam|lstm|gemm)_\w+|pdl)"', hdr))
+    assert {"ctc_overlap", "ctc_stamp", "ctc_ws", "ctc_lin", "pdl", "beam_fast"} <= knobs
+    for k in sorted(knobs):
+        assert lib.avctc_set_tuning(k.encode(), 1 if k not in ("ctc_k", "ctc_grad_warps", "gemm_dbg", "ctc_stamp") else 0) == 0, k
+    assert lib.avctc_set_tuning(b"no_such_knob", 1) != 0
+    for k, v in (("ctc_overlap", 1), ("ctc_ws", 1), ("ctc_lin", 1), ("pdl", 1), ("ctc_pf", 1), ("beam_fast", 1),
+                 ("beam_two_phase", 1), ("beam_pf", 1), ("lstm_tag", 1)):
+        pkg._lib.set_tuning(k, v)                               # leave the defaults behind
+
+
 def test_product_fails_loudly_without_gpu_tensor():
     import torch
     import multimodal_av_model_b200 as pkg
