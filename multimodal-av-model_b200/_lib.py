@@ -63,8 +63,9 @@ class GemmOperand(ctypes.Structure):
                 ("z_inner", _i), ("mn_major", _i)]
 
 
-# kernels launched by each entry point (bench.py reports "gpu_launches" from this table)
-KERNELS = {"avctc_ctc_forward": 1, "avctc_ctc_reduce": 1, "avctc_ctc_backward": 1, "avctc_beam_search": 2,
+# kernels launched by each entry point (bench.py reports "gpu_launches" from this table); CTC forward / backward with a
+# workspace = the probability-domain kernel + its guarded log-domain twin (which exits at once unless the range guard tripped)
+KERNELS = {"avctc_ctc_forward": 2, "avctc_ctc_reduce": 1, "avctc_ctc_backward": 2, "avctc_beam_search": 2,
            "avctc_gemm_bf16": 1, "avctc_resample_forward": 2, "avctc_resample_backward": 1, "avctc_softmax_forward": 1,
            "avctc_softmax_backward": 1, "avctc_colsum": 1, "avctc_log_softmax_forward": 1,
            "avctc_log_softmax_backward": 1, "avctc_infonce_forward": 4, "avctc_infonce_backward": 2,
