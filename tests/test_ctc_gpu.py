@@ -268,7 +268,7 @@ def test_ctc_backward_launched_right_behind_forward(scale):
         pkg._lib.set_tuning("ctc_overlap", 1)
     assert torch.isfinite(grad0).all()
     overlapped = 0
-    for rep in range(3):
+    for rep in range(4):          # (the first launch of a kernel may pay lazy module loading and miss the scan)
         loss1, grad1, stamps = _c_abi_fwd_bwd(pkg, lp, tgc, ilc, tlc, 0, nbwd=1 + (rep == 2), stamp=True)
         assert loss1 == loss0
         assert torch.equal(grad1, grad0)
