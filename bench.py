@@ -13,11 +13,16 @@ Headline (BASELINE.json metric "train utt/s at 1/2/4/8 B200; CTC loss GB/s; beam
   inside the timed region).  The same JSON line carries the other two parts of the metric measured live:
   "ctc" (config 2, GB/s, the "roofline" object is this kernel pair), "beam" (config 5, utt/s), plus "fusion"
   (config 3, tensor-pipe fraction) and "hot_path" (the step from encoder features on).
-  --impl reference times the oracle port of the reference (torch CPU ops, oracle/torch_port.py) on the host.
+  Every sub-benchmark carries, next to the sm_100a kernels, (1) the reference's arithmetic on the box's host cores
+  ("cpu": torch CPU ops = what the reference executes, core count stated) and (2) the stock-torch CUDA formulation on
+  the same B200 ("torch_cuda_ms": ATen/cuDNN/cuBLAS kernels, the library bar).  Rank 0 at N=1 only.
+  --impl reference times the reference's train step on the host CPU: oracle/torch_port.py + oracle/encoder_port.py (the
+  reference modules restated on stock torch/HF ops; /root/reference itself cannot travel to the GPU box), same config.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -94,11 +99,23 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def build_models(device, seed=0):
+class _NoEncoder(torch.nn.Module):
+    def forward(self, *a, **k):
+        raise RuntimeError("hot-path-only benchmark: the encoders are not built")
+
+
+def build_models(device, seed=0, encoders=True):
     import multimodal_av_model_b200 as pkg
     from multimodal_av_model_b200.encoders import unfreeze_middle_layers, xlsr_large_config
     from multimodal_av_model_b200.synthetic import CharTokenizer
     torch.manual_seed(seed)
+    if not encoders:
+        fus = pkg.CrossAttentionFusion(512, 1024, 512)
+        dec = pkg.CTCDecoder(1024, VOCAB, blank_id=BLANK)
+        tr = pkg.MultimodalTrainer(_NoEncoder(), _NoEncoder(), fus, dec, CharTokenizer(VOCAB), device=device)
+        tr.verbose = False
+        fus.train(); dec.train()
+        return tr
     vis = pkg.VisualEncoder(relu_type="prelu")
     for p in vis.parameters():                 # main.py:100-103
         p.requires_grad = False
@@ -135,31 +152,34 @@ def timed_loop(fn, steps, warmup, device, world):
     return float(ms.item())
 
 
-def bench_train(args, rank, local, world, device):
+def bench_train(args, rank, local, world, device, hot_only=False):
     from multimodal_av_model_b200 import _lib
     from multimodal_av_model_b200.synthetic import make_batch
-    tr = build_models(device)
-    host = make_batch(pairs=PAIRS_PER_GPU, seconds=SECONDS, t_v=T_V, vocab=VOCAB, seed=1234 + rank, pin=True)
-    dev_batch = {k: v.to(device) for k, v in host.items()}
+    tr = build_models(device, encoders=not hot_only)
     utt_per_step = 2 * PAIRS_PER_GPU * world
+    out = {}
+    if not hot_only:
+        host = make_batch(pairs=PAIRS_PER_GPU, seconds=SECONDS, t_v=T_V, vocab=VOCAB, seed=1234 + rank, pin=True)
+        dev_batch = {k: v.to(device) for k, v in host.items()}
 
-    def step_resident():
-        tr.train_step(dev_batch)
+        def step_resident():
+            tr.train_step(dev_batch)
 
-    def step_e2e():
-        return float(tr.train_step(host))          # H2D of the pinned batch + D2H read of the loss
+        def step_e2e():
+            return float(tr.train_step(host))          # H2D of the pinned batch + D2H read of the loss
 
-    c0 = _lib.launch_count
-    with ClockSampler(local) as cs:
-        ms = timed_loop(step_resident, args.steps, args.warmup, device, world)
-    launches = (_lib.launch_count - c0) // (args.steps + args.warmup)
-    ms_e2e = timed_loop(step_e2e, args.steps, max(1, args.warmup // 2), device, world)
-    h2d = int(sum(v.numel() * v.element_size() for k, v in host.items() if not k.endswith("_lengths") or k.startswith("text")))
-    grad_params = sum(p.numel() for p in tr.parameters if p.requires_grad)
-    out = dict(value=utt_per_step * args.steps / (ms / 1e3), ms_per_step=ms / args.steps,
-               e2e=dict(value=utt_per_step * args.steps / (ms_e2e / 1e3), unit="utt/s", h2d_bytes_per_step=h2d,
-                        d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
-               gpu_launches=int(launches), clocks=cs.summary(), allreduce_bytes_per_step=grad_params * 4 if world > 1 else 0)
+        c0 = _lib.launch_count
+        with ClockSampler(local) as cs:
+            ms = timed_loop(step_resident, args.steps, args.warmup, device, world)
+        launches = (_lib.launch_count - c0) // (args.steps + args.warmup)
+        ms_e2e = timed_loop(step_e2e, args.steps, max(1, args.warmup // 2), device, world)
+        h2d = int(sum(v.numel() * v.element_size() for k, v in host.items() if not k.endswith("_lengths") or k.startswith("text")))
+        grad_params = sum(p.numel() for p in tr.parameters if p.requires_grad)
+        out = dict(value=utt_per_step * args.steps / (ms / 1e3), ms_per_step=ms / args.steps,
+                   e2e=dict(value=utt_per_step * args.steps / (ms_e2e / 1e3), unit="utt/s", h2d_bytes_per_step=h2d,
+                            d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
+                   gpu_launches=int(launches), clocks=cs.summary(), allreduce_bytes_per_step=grad_params * 4 if world > 1 else 0)
+        del dev_batch
     # hot path only (number A): from encoder features on, same trainer
     from multimodal_av_model_b200.synthetic import make_features
     f = make_features(pairs=PAIRS_PER_GPU, t_v=T_V, t_enc=249, seed=1234 + rank, dtype=torch.bfloat16)
@@ -168,18 +188,76 @@ def bench_train(args, rank, local, world, device):
         fd[k] = [t.requires_grad_() for t in fd[k]]
 
     def hot_step():
-        tr.optimizer.zero_grad(set_to_none=True)
+        if tr._reducer is not None:
+            tr._reducer.zero_grad()
+        else:
+            tr.optimizer.zero_grad(set_to_none=True)
         for k in ("audio", "middle"):
             for t in fd[k]:
                 t.grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16):
             total = tr.hot_path_loss(fd["visual"], fd["audio"], fd["middle"], fd["masks"], fd["texts"], fd["lens"])[0]
         total.backward()
+        if tr._reducer is not None:
+            tr._reducer.finish()
     ms_hot = timed_loop(hot_step, args.steps, args.warmup, device, world)
     out["hot_path"] = dict(value=utt_per_step * args.steps / (ms_hot / 1e3), unit="utt/s", ms_per_step=ms_hot / args.steps,
-                           note="fusion+CTC head+CTC+InfoNCE fwd+bwd from encoder features on (no encoders, no optimizer)")
+                           note="fusion+BiLSTM+CTC head+CTC+InfoNCE fwd+bwd from encoder features on (no encoders, no optimizer)")
+    if world == 1 and not args.no_comparators:
+        out["hot_path"].update(hot_path_comparators(tr, f, device, args))
     return out, tr
 
+
+
+def hot_path_comparators(tr, f, device, args):
+    """The same hot-path step (a) on the stock torch CUDA kernels of the same box — the reference's modules restated in
+    oracle/torch_port.py moved to the GPU under bf16 autocast: cuBLAS projections, unfused MHA, cuDNN LSTM, ATen
+    log_softmax / CTC / InfoNCE ops (the library kernels to beat) — and (b) on the host CPU in fp32."""
+    from oracle import torch_port as tp
+    res = {}
+    torch.manual_seed(0)
+    ref_f, ref_d, proj = tp.FusionPort(512, 1024, 512), tp.DecoderPort(1024, VOCAB, BLANK), torch.nn.Linear(1024, 128)
+    ref_f.load_state_dict(tr.fusion_module.state_dict()); ref_d.load_state_dict(tr.decoder1.state_dict())
+
+    def feats_on(dev, dtype):
+        return [dict(visual=f["visual"][s].to(dev, dtype), audio=f["audio"][s].to(dev, dtype).requires_grad_(),
+                     middle=f["middle"][s].to(dev, dtype).requires_grad_(), mask=f["masks"][s].to(dev),
+                     text=f["texts"][s].to(dev), text_len=f["lens"][s].to(dev)) for s in range(2)]
+    mods = [m.to(device) for m in (ref_f, ref_d, proj)]
+    fg = feats_on(device, torch.bfloat16)
+
+    def stock():
+        for m in mods:
+            m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = tp.hot_path_losses(mods[0], mods[1], mods[2], fg, blank=BLANK)
+        loss.backward()
+    ms = timed_loop(stock, max(3, args.steps // 2), 3, device, 1) / max(3, args.steps // 2)
+    res["torch_cuda_ms_per_step"] = ms
+    res["torch_cuda_note"] = "oracle/torch_port modules on cuda, bf16 autocast: cuBLAS + unfused MHA + cuDNN LSTM + ATen CTC"
+    mods = [m.to("cpu") for m in mods]
+    fc = feats_on("cpu", torch.float32)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+
+    def cpu():
+        for m in mods:
+            m.zero_grad(set_to_none=True)
+        tp.hot_path_losses(mods[0], mods[1], mods[2], fc, blank=BLANK).backward()
+    cpu()
+    t0 = time.perf_counter(); cpu(); dt = time.perf_counter() - t0
+    res["cpu"] = {"ms_per_step": dt * 1e3, "value": 2 * PAIRS_PER_GPU / dt, "unit": "utt/s", "cores": threads, "kind": "port",
+                  "sample": "1 step (after 1 warm-up) of the same 8-pair hot-path step, torch CPU ops fp32 (oracle/torch_port.py)"}
+    return res
+
+
+def cpu_time(fn, reps=2, warm=1):
+    for _ in range(warm):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps * 1e3
 
 def l2_flusher(device):
     buf = torch.empty(256 << 20, dtype=torch.uint8, device=device)
@@ -218,8 +296,13 @@ def ctc_case(T, device, B=64, V=801, blank=0, dtype=torch.float32):
     return lp, torch.from_numpy(tg).to(device), torch.from_numpy(il).to(device), torch.from_numpy(tl).to(device), Lm
 
 
-def bench_ctc(device, iters=10, Ts=(250, 1000)):
-    """BASELINE config 2 through the C ABI with preallocated buffers: fwd (alpha||beta scan) + bwd (grad)."""
+def bench_ctc(device, iters=10, Ts=(250, 1000), comparators=True):
+    """BASELINE config 2.  product_ms = pkg.ctc_loss(x, ...).backward() — the autograd route a trainer uses: the scan, the
+    reduction and the gradient pass are enqueued back to back at forward time (ctc.py), backward() applies grad_out.
+    abi_* = the same kernels through the C ABI with preallocated buffers (no allocator / autograd bookkeeping);
+    scan_ms / grad_ms = each kernel pair alone.  Next to it: F.ctc_loss on the same GPU (ATen's sm_100 SIMT kernels) and
+    on the host CPU (ATen LossCTC.cpp, what the reference runs at trainer.py:116-117 on a CPU box)."""
+    import multimodal_av_model_b200 as pkg
     from multimodal_av_model_b200 import _lib
     L = _lib.lib()
     flush = l2_flusher(device)
@@ -242,23 +325,39 @@ def bench_ctc(device, iters=10, Ts=(250, 1000)):
             _lib.check(L.avctc_ctc_backward(lp.data_ptr(), 0, lp.stride(0), lp.stride(1), T, B, V, tg.data_ptr(), tg.stride(0),
                                             None, il.data_ptr(), tl.data_ptr(), Lm, 0, 1, 1, nll.data_ptr(), go.data_ptr(), 0,
                                             grad.data_ptr(), ws.data_ptr(), wsb, st), "bwd")
+        x = lp.clone().requires_grad_()
+
+        def product():
+            x.grad = None
+            pkg.ctc_loss(x, tg, il, tl, blank=0, reduction="mean", zero_infinity=True).backward()
+        t_prod, _ = event_time(product, iters, 3, flush, device)
         t_all, t_min = event_time(lambda: (fwd(), bwd()), iters, 3, flush, device)
         t_f, _ = event_time(fwd, iters, 2, flush, device)
         t_b, _ = event_time(bwd, iters, 2, flush, device)
-        x = lp.clone().requires_grad_()
-
-        def torch_ref():
-            x.grad = None
-            torch.nn.functional.ctc_loss(x, tg, il, tl, blank=0, reduction="mean", zero_infinity=True).backward()
-        t_torch, _ = event_time(torch_ref, max(3, iters // 2), 2, flush, device)
         alg = 2 * T * B * V * 4
-        res[f"T{T}"] = dict(fwd_bwd_ms=t_all, scan_ms=t_f, grad_ms=t_b, gbs=alg / t_all / 1e6, utt_per_s=B / t_all * 1e3,
-                            grad_kernel_gbs=alg / t_b / 1e6, torch_cuda_ms=t_torch, speedup_vs_torch_cuda=t_torch / t_all,
-                            algorithmic_bytes=alg)
+        r = dict(product_ms=t_prod, gbs=alg / t_prod / 1e6, utt_per_s=B / t_prod * 1e3, abi_fwd_bwd_ms=t_all,
+                 abi_gbs=alg / t_all / 1e6, scan_ms=t_f, grad_ms=t_b, grad_kernel_gbs=alg / t_b / 1e6, algorithmic_bytes=alg)
+        if comparators:
+            def torch_ref():
+                x.grad = None
+                torch.nn.functional.ctc_loss(x, tg, il, tl, blank=0, reduction="mean", zero_infinity=True).backward()
+            t_torch, _ = event_time(torch_ref, max(3, iters // 2), 2, flush, device)
+            r.update(torch_cuda_ms=t_torch, speedup_vs_torch_cuda=t_torch / t_prod)
+            xc, tgc, ilc, tlc = lp.cpu().requires_grad_(), tg.cpu(), il.cpu(), tl.cpu()
+            threads = os.cpu_count() or 1
+            torch.set_num_threads(threads)
+
+            def cpu_ref():
+                xc.grad = None
+                torch.nn.functional.ctc_loss(xc, tgc, ilc, tlc, blank=0, reduction="mean", zero_infinity=True).backward()
+            t_cpu = cpu_time(cpu_ref, reps=3 if T <= 250 else 2)
+            r["cpu"] = {"ms": t_cpu, "gbs": alg / t_cpu / 1e6, "utt_per_s": B / t_cpu * 1e3, "cores": threads, "kind": "port",
+                        "sample": f"F.ctc_loss fwd+bwd on torch CPU (ATen LossCTC.cpp), the whole B={B} T={T} batch, fp32"}
+        res[f"T{T}"] = r
     return res
 
 
-def bench_beam(device, rank, world, iters=5, N=4096, T=150, beam=10):
+def bench_beam(device, rank, world, iters=5, N=4096, T=150, beam=10, comparators=True):
     """BASELINE config 5: N utterances sharded contiguously over ranks, no collective.
     ms = the two decode kernels through the C ABI (log-probs resident in HBM, ids left on the device);
     e2e = beam_search_batch() from pinned host log-probs to Python token lists."""
@@ -288,15 +387,41 @@ def bench_beam(device, rank, world, iters=5, N=4096, T=150, beam=10):
     for _ in range(2):
         pkg.beam_search_batch(lp_host, beam_width=beam, blank=BLANK)
     t_e2e = (time.perf_counter() - t0) / 2 * 1e3
-    return dict(utterances=N, shard=n, beam=beam, ms=t_k, utt_per_s_shard=n / t_k * 1e3, e2e_ms=t_e2e,
-                e2e_utt_per_s_shard=n / t_e2e * 1e3, gbs=n * T * VOCAB * 4 / t_k / 1e6,
-                hbm_frac=n * T * VOCAB * 4 / t_k / 1e6 / measured_peaks()["hbm"],
-                algorithmic_bytes=n * T * VOCAB * 4,
-                note="ms = decode kernels only (log-probs resident, ids left on device); e2e = beam_search_batch() on pinned host "
-                     "log-probs: chunked H2D overlapped with the decode kernels + D2H of ids + Python list construction")
+    out_d = dict(utterances=N, shard=n, beam=beam, ms=t_k, utt_per_s_shard=n / t_k * 1e3, e2e_ms=t_e2e,
+                 e2e_utt_per_s_shard=n / t_e2e * 1e3, gbs=n * T * VOCAB * 4 / t_k / 1e6,
+                 hbm_frac=n * T * VOCAB * 4 / t_k / 1e6 / measured_peaks()["hbm"],
+                 algorithmic_bytes=n * T * VOCAB * 4,
+                 note="ms = decode kernels only (log-probs resident in HBM, ids left on the device) = what evaluate() pays, its "
+                      "log-probs are device tensors; e2e = beam_search_batch() on pinned host log-probs: chunked H2D overlapped "
+                      "with the decode kernels + D2H of ids + Python list construction (PCIe-bound)")
+    if comparators and world == 1:
+        # (1) the same search written with stock torch CUDA ops, batched over utterances: one torch.topk over all rows, then
+        # T steps of [N, beam*beam] candidate scores -> torch.topk -> gather (float64 scores like the reference's Python floats)
+        def torch_cuda_beam():
+            vals, ids = torch.topk(lp, beam, dim=-1)                       # [n,T,beam]
+            score = torch.zeros(n, 1, dtype=torch.float64, device=device)
+            back = []
+            for t in range(T):
+                cand = (score[:, :, None] + vals[:, t, None, :].double()).reshape(n, -1)
+                score, pick = torch.topk(cand, min(beam, cand.shape[1]), dim=-1)
+                back.append(pick)
+            return score, back, ids
+        t_tc, _ = event_time(torch_cuda_beam, 2, 1, flush, device)
+        out_d.update(torch_cuda_ms=t_tc, speedup_vs_torch_cuda=t_tc / t_k,
+                     torch_cuda_note="batched stock-torch formulation (topk over all rows + T recurrence steps of topk/gather), "
+                                     "no path reconstruction; the reference's own per-utterance Python loop is the cpu leg")
+        # (2) the reference's simple_beam_search (beam_search.py:2-42) in a process pool over all host cores
+        from oracle import torch_port as tp
+        threads = os.cpu_count() or 1
+        sample = min(n, max(64, 4 * threads))
+        dt, _ = tp.beam_search_pool(lp_host[:sample], beam, BLANK, threads)
+        out_d["cpu"] = {"utt_per_s": sample / dt, "ms_per_utt_per_core": dt * 1e3 * threads / sample, "cores": threads,
+                        "kind": "port", "sample": f"simple_beam_search (Python loop + torch.topk per frame) on {sample} of the "
+                                                  f"{N} utterances, {threads} worker processes x 1 thread"}
+    return out_d
 
 
-def bench_fusion(device, peaks, iters=10):
+def bench_fusion(device, peaks, iters=10, comparators=True):
     """BASELINE config 3: projections + cross attention fwd/bwd, bf16, B=32, T_v=150, T_a=249."""
     import multimodal_av_model_b200 as pkg
     torch.manual_seed(0)
@@ -353,7 +478,80 @@ def bench_fusion(device, peaks, iters=10):
         out.update(graph_fwd_bwd_ms=t_g2, graph_tensor_frac_fwd_bwd=3 * flop_f / t_g2 / 1e9 / peaks["tf_burst"])
     except Exception as e:          # capture is a measurement aid, never a requirement
         out.update(graph_fwd_ms=None, graph_error=str(e)[:120])
+    if comparators:
+        out.update(fusion_comparators(fus, vis, aud, mask, r, flush, device, iters, flop_f, peaks))
     return out
+
+
+def fusion_comparators(fus, vis, aud, mask, r, flush, device, iters, flop_f, peaks):
+    """Config 3 on (1) the stock torch CUDA kernels (nn.Linear / nn.MultiheadAttention = cuBLAS + ATen softmax, bf16
+    autocast; the reference's formulation, fusion_module.py:40-63) and (2) the host CPU in fp32."""
+    from oracle import torch_port as tp
+    ref = tp.FusionPort(512, 1024, 512)
+    ref.load_state_dict(fus.state_dict())
+    ref.to(device)
+    a2 = aud.detach().clone().requires_grad_()
+
+    def t_fwd():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            ref.projection(vis, a2, mask)
+
+    def t_fwd_bwd():
+        ref.zero_grad(set_to_none=True); a2.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            f, _ = ref.projection(vis, a2, mask)
+        f.backward(r.to(f.dtype))
+    tf, _ = event_time(t_fwd, iters, 3, flush, device)
+    tfb, _ = event_time(t_fwd_bwd, iters, 3, flush, device)
+    out = dict(torch_cuda_fwd_ms=tf, torch_cuda_fwd_bwd_ms=tfb, torch_cuda_tensor_frac_fwd_bwd=3 * flop_f / tfb / 1e9 / peaks["tf_burst"])
+    ref.to("cpu")
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    vc, ac, mc, rc = vis.float().cpu(), aud.detach().float().cpu().requires_grad_(), mask.cpu(), r.float().cpu()
+
+    def cpu():
+        ref.zero_grad(set_to_none=True); ac.grad = None
+        f, _ = ref.projection(vc, ac, mc)
+        f.backward(rc)
+    t_cpu = cpu_time(cpu, reps=2)
+    out["cpu"] = {"fwd_bwd_ms": t_cpu, "tflops": 3 * flop_f / t_cpu / 1e9, "cores": threads, "kind": "port",
+                  "sample": "FusionPort.projection fwd+bwd (nn.Linear + nn.MultiheadAttention on torch CPU ops, fp32), whole B=32 batch"}
+    return out
+
+
+def bench_lstm(device, iters=10):
+    """temporal_model (2-layer BiLSTM 512->1024, fusion_module.py:21-27,64) fwd+bwd: the persistent sm_100a kernels against
+    cuDNN (torch.nn.LSTM, fp32 weights under bf16 autocast) on the same GPU, at the hot-path shape (2B=16 sequences, T=150)
+    and at config 3's batch (32)."""
+    import multimodal_av_model_b200 as pkg
+    from multimodal_av_model_b200.fusion_module import _BiLSTMFn
+    flush = l2_flusher(device)
+    torch.manual_seed(0)
+    ref = torch.nn.LSTM(512, 512, num_layers=2, batch_first=True, bidirectional=True).to(device)
+    res = {}
+    for B in (16, 32):
+        x = torch.randn(B, T_V, 512, device=device, dtype=torch.bfloat16, requires_grad=True)
+        r = torch.randn(B, T_V, 1024, device=device, dtype=torch.bfloat16)
+
+        def ours():
+            ref.zero_grad(set_to_none=True); x.grad = None
+            _BiLSTMFn.apply(x, *ref._flat_weights).backward(r)
+
+        def ours_fwd():
+            with torch.no_grad():
+                _BiLSTMFn.apply(x, *ref._flat_weights)
+
+        def cudnn():
+            ref.zero_grad(set_to_none=True); x.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y, _ = ref(x)
+            y.backward(r.to(y.dtype))
+        t, _ = event_time(ours, iters, 3, flush, device)
+        tf, _ = event_time(ours_fwd, iters, 3, flush, device)
+        tc, _ = event_time(cudnn, max(3, iters // 2), 2, flush, device)
+        res[f"B{B}"] = dict(fwd_ms=tf, fwd_bwd_ms=t, cudnn_fwd_bwd_ms=tc, speedup_vs_cudnn=tc / t,
+                            us_per_step_fwd=tf * 1e3 / (2 * T_V))
+    return res
 
 
 def bench_infonce(device, peaks, iters=10):
@@ -399,23 +597,25 @@ def bench_infonce(device, peaks, iters=10):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_train_sample(pairs, steps, warmup, threads):
-    """The reference's train step restated on torch CPU ops (oracle/torch_port.py + the PyTorch encoders)."""
+def cpu_train_sample(pairs, steps, warmup, threads, budget_s=300.0):
+    """The reference's train step (trainer.py:62-125) on the host CPU: its modules restated on stock torch / HF ops
+    (oracle/encoder_port.py: VisualEncoder + unmodified Wav2Vec2Model.forward; oracle/torch_port.py: fusion, CTC head,
+    nn.CTCLoss, InfoNCE), fp32 (torch.cuda.amp autocast/GradScaler are no-ops on CPU), Adam with the reference's four
+    parameter groups.  Nothing of the product package computes here; synthetic.make_batch only generates the inputs."""
+    from oracle import encoder_port as ep
     from oracle import torch_port as tp
-    from multimodal_av_model_b200.encoders import AudioEncoder, VisualEncoder, unfreeze_middle_layers, xlsr_large_config
     from multimodal_av_model_b200.synthetic import make_batch
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    vis = VisualEncoder()
-    for p in vis.parameters():
+    vis = ep.VisualPort()
+    for p in vis.parameters():                       # main.py:100-103
         p.requires_grad = False
-    aud = AudioEncoder(freeze=True, config=xlsr_large_config())
-    unfreeze_middle_layers(aud.model)
+    aud = ep.AudioPort()                             # main.py:105-106: only encoder.layers.6-9 train
     fus = tp.FusionPort(512, 1024, 512)
     dec = tp.DecoderPort(1024, VOCAB, BLANK)
     proj = torch.nn.Linear(1024, 128)
-    params = [p for m in (vis, aud, fus, dec) for p in m.parameters()]
-    opt = torch.optim.Adam([p for p in params if p.requires_grad], lr=1e-4)
+    opt = torch.optim.Adam([{"params": [p for p in aud.parameters() if p.requires_grad], "lr": 2e-5},
+                            {"params": fus.parameters(), "lr": 1e-4}, {"params": dec.parameters(), "lr": 1e-4}])
     for m in (vis, aud, fus, dec):
         m.train()
     batch = make_batch(pairs=pairs, seconds=SECONDS, t_v=T_V, vocab=VOCAB, seed=1234)
@@ -433,38 +633,53 @@ def cpu_train_sample(pairs, steps, warmup, threads):
         loss.backward()
         opt.step()
         return float(loss.detach())
-    for _ in range(warmup):
-        step()
+    # K timed steps after W warm-up steps as asked, unless that cannot end "within a few minutes" on this host: the first
+    # step is timed and, if (W-1+K) more would exceed `budget_s`, warm-up stops there and K shrinks to what fits (>= 1).
+    # The per-step workload (all `pairs`) is never reduced — the config stays the one the GPU arm runs.
+    done_warm = 0
+    if warmup > 0:
+        t0 = time.perf_counter(); step(); est = time.perf_counter() - t0
+        done_warm = 1
+        if (warmup - 1 + steps) * est > budget_s:
+            steps = max(1, min(steps, int(budget_s / est)))
+        else:
+            for _ in range(warmup - 1):
+                step()
+            done_warm = warmup
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return 2 * pairs * steps / dt, dt / steps
+    return 2 * pairs * steps / dt, dt / steps, steps, done_warm
 
 
 def train_config(world):
-    """The workload both arms run (BASELINE config 4); each arm adds how it runs it."""
+    """The workload BOTH arms run (BASELINE config 4) — the same dict on the `ours` and the `reference` line."""
     return {"workload": "config4: full AV-CTC + InfoNCE train step (encoders + fusion + BiLSTM + CTC head + CTC + InfoNCE + Adam)",
             "pairs_per_gpu": PAIRS_PER_GPU, "utterances_per_step": 2 * PAIRS_PER_GPU * world, "audio_s": SECONDS,
             "lip_frames": T_V, "t_enc": 249, "vocab": VOCAB, "blank": BLANK,
-            "encoders": "random-init ResNet-18 front-end + wav2vec2-large (XLSR layout)"}
+            "encoders": "random-init ResNet-18 front-end + wav2vec2-large (XLSR layout)",
+            "parallelism": f"dp{world}, utterance-sharded",
+            "l2": "per-step working set (1.3 GB of parameters + activations) exceeds the 126 MB L2; sub-benchmarks flush L2 "
+                  "with a 256 MB write between iterations"}
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the SAME config (8 pairs per step), K timed steps after W
+    warm-up steps exactly as asked, all host threads.  Under torchrun only rank 0 works."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    pairs = 2
-    steps = max(1, min(args.steps, 3))
-    warm = 1 if args.warmup > 0 else 0
-    val, sec = cpu_train_sample(pairs, steps, warm, threads)
+    world = max(1, args.gpus)
+    val, sec, steps, warm = cpu_train_sample(PAIRS_PER_GPU, args.steps, args.warmup, threads)
     line = {"impl": "reference", "metric": "train_utt_per_s", "value": val, "unit": "utt/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(train_config(1), implementation="torch CPU ops (oracle/torch_port.py + the PyTorch encoders), fp32",
-                           sample_pairs_per_step=pairs),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": train_config(world),
+            "implementation": "reference train step on torch CPU ops, fp32: oracle/encoder_port.py (unmodified "
+                              "Wav2Vec2Model.forward + ResNet-18 front end) + oracle/torch_port.py; one process, all host threads",
             "cpu_baseline": {"value": val, "unit": "utt/s", "cores": threads, "kind": "port",
-                             "sample": f"{steps} step(s) of {pairs} pairs (= {2 * pairs} utterances) of the config-4 step on torch CPU ops"},
+                             "sample": f"{steps} step(s) after {warm} warm-up of {PAIRS_PER_GPU} pairs "
+                                       f"(= {2 * PAIRS_PER_GPU} utterances) each: the full config-4 step, {sec:.1f} s/step"},
             "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -488,6 +703,28 @@ def emit(line):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+def source_hash(files=("ctc_loss.cu", "common.cuh")):
+    """sha256 (first 16 hex) of the kernel sources a profile belongs to — profiles/*.json carry it, so a DRAM-traffic
+    figure is only quoted while the kernels it was captured from are the ones being timed."""
+    h = hashlib.sha256()
+    for f in files:
+        with open(os.path.join(ROOT, "multimodal-av-model_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def ctc_traffic():
+    """(bytes per fwd+bwd launch pair, provenance) from profiles/ctc_traffic.json (written by
+    `tools/ncu_summary.py traffic` from one `ncu --set full` capture of tools/run_ctc_once.py), or (None, why)."""
+    path = os.path.join(ROOT, "profiles", "ctc_traffic.json")
+    if not os.path.exists(path):
+        return None, "no profiles/ctc_traffic.json"
+    d = json.load(open(path))
+    if d.get("source_hash") != source_hash():
+        return None, f"profiles/ctc_traffic.json was captured from other kernel sources ({d.get('source_hash')}), not quoted"
+    return d["traffic_bytes"], {"file": "profiles/ctc_traffic.json", "kernels": d.get("kernels"), "git_head": d.get("git_head")}
+
+
 def main():
     _guard_stdout()
     ap = argparse.ArgumentParser()
@@ -495,8 +732,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "ctc", "beam", "fusion", "infonce"])
+    ap.add_argument("--workload", default="train", choices=["train", "ctc", "beam", "fusion", "infonce", "lstm", "hot"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-comparators", action="store_true", help="skip the stock-torch CUDA / host CPU legs of the sub-benchmarks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
@@ -508,22 +746,23 @@ def main():
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     peaks = measured_peaks()
+    comparators = (world == 1) and not args.no_comparators
     line = {"metric": "train_utt_per_s", "unit": "utt/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": dict(train_config(world),
-                           implementation="PyTorch encoders + sm_100a fusion/BiLSTM/CTC head/CTC/InfoNCE kernels, bf16 autocast",
-                           parallelism=f"dp{world}, utterance-sharded",
-                           l2="per-step working set (1.3 GB of parameters + activations) exceeds the 126 MB L2; "
-                              "sub-benchmarks flush L2 with a 256 MB write between iterations")}
-    if args.workload == "train":
-        out, tr = bench_train(args, rank, local, world, device)
+            "config": train_config(world),
+            "implementation": "PyTorch encoders + sm_100a fusion/BiLSTM/CTC head/CTC/InfoNCE kernels, bf16 autocast"}
+    wl = args.workload
+    if wl in ("train", "hot"):
+        out, tr = bench_train(args, rank, local, world, device, hot_only=(wl == "hot"))
         line.update(out)
         del tr
         torch.cuda.empty_cache()
-    ctc = bench_ctc(device) if args.workload in ("train", "ctc") else None
-    beam = bench_beam(device, rank, world) if args.workload in ("train", "beam") else None
-    fusion = bench_fusion(device, peaks) if args.workload in ("train", "fusion") else None
-    if args.workload in ("train", "infonce"):
+    ctc = bench_ctc(device, comparators=comparators) if wl in ("train", "ctc") else None
+    beam = bench_beam(device, rank, world, comparators=comparators) if wl in ("train", "beam") else None
+    fusion = bench_fusion(device, peaks, comparators=comparators) if wl in ("train", "fusion") else None
+    if wl in ("train", "lstm"):
+        line["lstm"] = bench_lstm(device)
+    if wl in ("train", "infonce"):
         line["infonce"] = bench_infonce(device, peaks)
     if beam is not None:
         import torch.distributed as dist
@@ -536,39 +775,49 @@ def main():
     if ctc is not None:
         line["ctc"] = ctc
         top = ctc["T1000"]
-        # dram__bytes_read.sum + dram__bytes_write.sum of the two kernels from one ncu --set full capture of this config
-        # (profiles/r01_ctc_scan_grad_full_v3.txt: scan 264.42 + 68.57 MB, gradient 209.43 + 152.86 MB)
-        traffic = (332.99e6 + 362.28e6) if os.path.exists(os.path.join(ROOT, "profiles", "r01_ctc_scan_grad_full_v3.txt")) else None
+        traffic, prov = ctc_traffic()
         line["roofline"] = {"bound": "hbm", "kernel": "ctc_scan_ws_kernel + ctc_grad_lin_kernel (CTC fwd+bwd, config 2: B=64 T=1000 V=801 fp32)",
                             "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s", "frac": top["gbs"] / peaks["hbm"],
-                            "peak_src": peaks["src"] + " (burst copy bandwidth, MEASURED_PEAKS.json)", "traffic": traffic,
+                            "peak_src": peaks["src"] + " (burst copy bandwidth, MEASURED_PEAKS.json: the kernel pair is timed alone)",
+                            "traffic": traffic, "traffic_src": prov,
                             "algorithmic_bytes": top["algorithmic_bytes"],
-                            "grad_kernel_frac": top["grad_kernel_gbs"] / peaks["hbm"],
-                            "note": "achieved = 2*T*B*V*4 bytes / time of forward + backward enqueued back to back (one pair of CUDA "
-                                    "events around both); the scan is a 1000-step dependent recurrence over 128 CTAs (latency-bound), "
-                                    "the gradient pass streams and starts on each utterance as soon as its alpha/beta rows are "
-                                    "complete, so fwd_bwd_ms < scan_ms + grad_ms (each timed alone); traffic is the sum of the two "
-                                    "kernels' DRAM bytes from the round-1 ncu capture"}
+                            "frac_T250": ctc["T250"]["gbs"] / peaks["hbm"] if "T250" in ctc else None,
+                            "abi_frac": top["abi_gbs"] / peaks["hbm"], "grad_kernel_frac": top["grad_kernel_gbs"] / peaks["hbm"],
+                            "note": "achieved = 2*T*B*V*4 bytes / time of pkg.ctc_loss(x, ...).backward() (one pair of CUDA events "
+                                    "around the autograd call: scan + reduce + gradient pass enqueued back to back at forward time, "
+                                    "backward applies grad_out); the scan is a 1000-step dependent recurrence over 128 CTAs "
+                                    "(latency-bound), the gradient pass streams and starts on each utterance as soon as its alpha/beta "
+                                    "rows are complete, so the total is below scan_ms + grad_ms (each timed alone); abi_frac = the same "
+                                    "kernels through the C ABI with preallocated buffers; traffic = dram__bytes_read+write of both "
+                                    "kernels from the ncu --set full capture named in traffic_src (null when the kernel sources changed)"}
     if fusion is not None:
         line["fusion"] = fusion
-    if args.workload != "train":
+    if wl not in ("train",):
         line["metric"] = {"ctc": "ctc_fwd_bwd_gbs", "beam": "beam_decode_utt_per_s", "fusion": "fusion_tensor_frac",
-                          "infonce": "infonce_fwd_bwd_gbs"}[args.workload]
-        line["unit"] = {"ctc": "GB/s", "beam": "utt/s", "fusion": "fraction of bf16 tensor peak", "infonce": "GB/s"}[args.workload]
+                          "infonce": "infonce_fwd_bwd_gbs", "lstm": "bilstm_fwd_bwd_ms", "hot": "hot_path_utt_per_s"}[wl]
+        line["unit"] = {"ctc": "GB/s", "beam": "utt/s", "fusion": "fraction of bf16 tensor peak", "infonce": "GB/s", "lstm": "ms",
+                        "hot": "utt/s"}[wl]
         line["config"] = {"workload": {"ctc": "config2: CTC fwd+bwd micro-benchmark B=64 T=250/1000 V=801 L in [10,80] fp32",
                                        "beam": "config5: beam-10 decode of 4096 x [150,800] log-prob utterances",
                                        "fusion": "config3: fusion projections + cross attention fwd/bwd bf16 B=32 T_v=150 T_a=249",
-                                       "infonce": "config4 sizes: InfoNCE fwd+bwd on 8 x 249 rows of 1024 bf16 features"}[args.workload],
+                                       "infonce": "config4 sizes: InfoNCE fwd+bwd on 8 x 249 rows of 1024 bf16 features",
+                                       "lstm": "2-layer BiLSTM 512->1024 fwd+bwd, T=150, B=16/32, bf16",
+                                       "hot": "config4 from encoder features on (fusion+BiLSTM+head+CTC+InfoNCE fwd+bwd), 8 pairs"}[wl],
                           "l2": "256 MB write between timed iterations flushes L2"}
-        line["dtype"] = {"ctc": "f32", "beam": "f32 values, f64 scores", "fusion": "bf16", "infonce": "bf16 in, f32 math"}[args.workload]
+        line["dtype"] = {"ctc": "f32", "beam": "f32 values, f64 scores", "fusion": "bf16", "infonce": "bf16 in, f32 math",
+                         "lstm": "bf16", "hot": "bf16"}[wl]
         line["value"] = {"ctc": lambda: ctc["T1000"]["gbs"], "beam": lambda: beam["utt_per_s"], "fusion": lambda: fusion["tensor_frac_fwd_bwd"],
-                         "infonce": lambda: line["infonce"]["gbs"]}[args.workload]()
-    if rank == 0 and world == 1 and args.workload == "train" and not args.no_cpu_baseline:
+                         "infonce": lambda: line["infonce"]["gbs"], "lstm": lambda: line["lstm"]["B16"]["fwd_bwd_ms"],
+                         "hot": lambda: line["hot_path"]["value"]}[wl]()
+        if wl == "lstm":
+            line["higher_is_better"] = False
+    if rank == 0 and world == 1 and wl == "train" and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, sec = cpu_train_sample(2, 1, 1, threads)
+        v, sec, _, _ = cpu_train_sample(PAIRS_PER_GPU, 1, 1, threads)
         line["cpu_baseline"] = {"value": v, "unit": "utt/s", "cores": threads, "kind": "port",
-                                "sample": "1 step (after 1 warm-up) of 2 pairs (= 4 utterances) of the config-4 step on torch CPU ops "
-                                          f"(oracle/torch_port.py), {sec:.1f} s/step"}
+                                "sample": f"1 step (after 1 warm-up) of the same {PAIRS_PER_GPU} pairs (= {2 * PAIRS_PER_GPU} utterances): "
+                                          "the full config-4 step on torch CPU ops, fp32 (oracle/encoder_port.py + "
+                                          f"oracle/torch_port.py), {sec:.1f} s/step"}
     if rank == 0:
         emit(line)
     if world > 1:

@@ -101,6 +101,13 @@ AVCTC_API int avctc_ctc_backward(const void* log_probs, int dtype, int64_t strid
                        const float* nll, const float* grad_out, int64_t grad_out_stride,
                        void* grad, const void* workspace, size_t workspace_bytes, void* stream);
 
+/* grad[t][b][:] *= grad_out[b*grad_out_stride], in place (rows whose factor is exactly 1 are left alone).  The autograd
+ * host uses it to run the gradient pass at forward time: avctc_ctc_backward with a unit grad_out goes out directly behind
+ * avctc_ctc_forward (so it overlaps the scan, see above) and loss.backward() only applies the incoming factor — the
+ * chain rule step of torch's CtcLossBackward (/root/reference/model/trainer.py:121 `scaler.scale(loss_total).backward()`). */
+AVCTC_API int avctc_ctc_scale_grad(void* grad, int dtype, int T, int B, int V, const float* grad_out,
+                         int64_t grad_out_stride, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Beam-search decode — replaces simple_beam_search(log_probs[T,V], beam_width, blank)
  *   /root/reference/beam_search.py:2-42, called per utterance at model/trainer.py:230,237

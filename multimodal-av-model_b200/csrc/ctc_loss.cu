@@ -2008,6 +2008,23 @@ static int dispatch_grad_lin(const GradParams& gp, cudaStream_t st) {
 
 using namespace avctc;
 
+// grad[t][b][:] *= g[b * gstride] in place; rows whose factor is exactly 1 are not touched (a scalar factor of 1 — the
+// gradient of the loss with respect to itself — makes the whole launch a no-op after one 4-byte read per CTA)
+template <typename T>
+__global__ void __launch_bounds__(256) ctc_scale_grad_kernel(T* __restrict__ grad, long long rows, int B, int V,
+                                                             const float* __restrict__ g, long long gstride) {
+    if (gstride == 0 && g[0] == 1.f) return;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const float f = g[(row % B) * gstride];
+        if (f == 1.f) continue;
+        T* r = grad + row * V;
+        for (int c = threadIdx.x; c < V; c += blockDim.x) {
+            if constexpr (sizeof(T) == 4) r[c] = r[c] * f;
+            else r[c] = __float2bfloat16(__bfloat162float(r[c]) * f);
+        }
+    }
+}
+
 extern "C" size_t avctc_ctc_workspace_bytes(int T, int B, int max_target_len) {
     CtcPlan pl;
     if (T < 0 || B < 0 || max_target_len < 0) return 0;
@@ -2125,4 +2142,22 @@ extern "C" int avctc_ctc_backward(const void* log_probs, int dtype, int64_t stri
     gp.K = pl.Klog; gp.W = pl.Wlog;
     if (dtype == AVCTC_F32) return launch_grad<float>(gp, st);
     return launch_grad<__nv_bfloat16>(gp, st);
+}
+
+extern "C" int avctc_ctc_scale_grad(void* grad, int dtype, int T, int B, int V, const float* grad_out,
+                                    int64_t grad_out_stride, void* stream) {
+    if (T < 0 || B < 0 || V <= 0) return AVCTC_ERR_BAD_ARG;
+    if (T == 0 || B == 0) return AVCTC_OK;
+    if (!grad || !grad_out) return AVCTC_ERR_BAD_ARG;
+    if (dtype != AVCTC_F32 && dtype != AVCTC_BF16) return AVCTC_ERR_BAD_ARG;
+    const long long rows = (long long)T * B;
+    const int grid = (int)(rows < 148 * 8 ? rows : 148 * 8);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == AVCTC_F32)
+        ctc_scale_grad_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<float*>(grad), rows, B, V, grad_out,
+                                                           grad_out_stride);
+    else
+        ctc_scale_grad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(grad), rows, B, V,
+                                                                   grad_out, grad_out_stride);
+    return (int)cudaGetLastError();
 }

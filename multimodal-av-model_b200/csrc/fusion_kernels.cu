@@ -182,33 +182,27 @@ __global__ void resample_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int 
     } else if (Tp == Tv) {
         t_lo = t_hi = r;
     }
-    // the few (frame, weight) pairs that touch padded index r, found once per CTA
-    __shared__ int st_t[8];
-    __shared__ float st_w[8];
-    __shared__ int st_n;
-    if (threadIdx.x == 0) {
-        int n = 0;
-        for (int t = t_lo; t <= t_hi && n < 8; ++t) {
-            const LerpCoef c = lerp_coef(t, Tp, Tv);
-            float w = 0.f;
-            if (c.i0 == r) w += c.w0;
-            if (c.i1 == r && c.w1 != 0.f) w += c.w1;
-            if (w != 0.f) { st_t[n] = t; st_w[n] = w; ++n; }
-        }
-        st_n = n;
-    }
-    __syncthreads();
-    const int n = st_n;
+    // every output frame of [t_lo, t_hi] whose stencil touches padded index r contributes; the weight is recomputed per
+    // frame (uniform across the CTA), so any up-sampling ratio works — Tp == 1 has all Tv frames on index 0
+    auto weight = [&](int t) {
+        const LerpCoef c = lerp_coef(t, Tp, Tv);
+        float w = 0.f;
+        if (c.i0 == r) w += c.w0;
+        if (c.i1 == r && c.w1 != 0.f) w += c.w1;
+        return w;
+    };
     if ((D & 7) == 0) {
         for (int d = threadIdx.x * 8; d < D; d += blockDim.x * 8) {
             float acc[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-            for (int i = 0; i < n; ++i) {
+            for (int t = t_lo; t <= t_hi; ++t) {
+                const float w = weight(t);
+                if (w == 0.f) continue;
                 float x[8];
-                load8(dout + ((size_t)b * Tv + st_t[i]) * D, d, x);
+                load8(dout + ((size_t)b * Tv + t) * D, d, x);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] += st_w[i] * x[k];
+                for (int k = 0; k < 8; ++k) acc[k] += w * x[k];
             }
             if constexpr (sizeof(TOut) == 4) {
                 *reinterpret_cast<float4*>(drow + d) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -225,7 +219,10 @@ __global__ void resample_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int 
     }
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         float acc = 0.f;
-        for (int i = 0; i < n; ++i) acc += st_w[i] * __bfloat162float(dout[((size_t)b * Tv + st_t[i]) * D + d]);
+        for (int t = t_lo; t <= t_hi; ++t) {
+            const float w = weight(t);
+            if (w != 0.f) acc += w * __bfloat162float(dout[((size_t)b * Tv + t) * D + d]);
+        }
         put(drow + d, acc);
     }
 }

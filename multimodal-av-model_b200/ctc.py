@@ -29,11 +29,6 @@ class _CTCLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, log_probs, targets, input_lengths, target_lengths, blank, reduction, zero_infinity):
         _lib.require_cuda(log_probs, "log_probs")
-        if log_probs.dim() == 2:  # unbatched (T,V) like torch
-            log_probs = log_probs.unsqueeze(1)
-            targets = targets.unsqueeze(0) if targets.dim() == 1 else targets
-            input_lengths = torch.as_tensor(input_lengths).reshape(1)
-            target_lengths = torch.as_tensor(target_lengths).reshape(1)
         if log_probs.dim() != 3:
             raise RuntimeError("log_probs must be (T, B, V)")
         if log_probs.stride(2) != 1:
@@ -63,38 +58,61 @@ class _CTCLossFn(torch.autograd.Function):
             raise RuntimeError("CTC: target length not supported by the sm_100a kernels")
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
         st = _lib.stream_ptr(dev)
+        red = _lib.REDUCTION[reduction]
+        grad = None
         with torch.cuda.device(dev):
             _lib.check(L.avctc_ctc_forward(
                 log_probs.data_ptr(), _lib.dtype_enum(log_probs), log_probs.stride(0), log_probs.stride(1),
                 T, B, V, targets.data_ptr(), tstride, offsets.data_ptr() if offsets is not None else None,
                 input_lengths.data_ptr(), target_lengths.data_ptr(), lmax, int(blank), int(need_grad),
                 nll.data_ptr(), ws.data_ptr() if need_grad else None, ws_bytes, st), "avctc_ctc_forward")
-            red = _lib.REDUCTION[reduction]
             out = torch.empty(B if red == 0 else 1, dtype=torch.float32, device=dev)
             _lib.check(L.avctc_ctc_reduce(nll.data_ptr(), target_lengths.data_ptr(), B, red, int(zero_infinity),
                                           out.data_ptr(), st), "avctc_ctc_reduce")
-        ctx.save_for_backward(log_probs, targets, input_lengths, target_lengths, nll, ws)
-        ctx.cfg = (int(blank), red, int(zero_infinity), lmax, tstride, offsets, ws_bytes)
+            if need_grad:
+                # The gradient pass goes out NOW, directly behind the scan, with a unit grad_out: launched there it
+                # starts on each utterance as soon as that utterance's alpha/beta rows are complete, under the scans of
+                # the longer ones (csrc/ctc_loss.cu, "early" route).  backward() then only applies the incoming factor.
+                # The lattice workspace dies with this call instead of living until backward.
+                grad = torch.empty((T, B, V), dtype=log_probs.dtype, device=dev)
+                _lib.check(L.avctc_ctc_backward(
+                    log_probs.data_ptr(), _lib.dtype_enum(log_probs), log_probs.stride(0), log_probs.stride(1),
+                    T, B, V, targets.data_ptr(), tstride, offsets.data_ptr() if offsets is not None else None,
+                    input_lengths.data_ptr(), target_lengths.data_ptr(), lmax, int(blank), red, int(zero_infinity),
+                    nll.data_ptr(), _unit(dev).data_ptr(), 0, grad.data_ptr(), ws.data_ptr(), ws_bytes, st),
+                    "avctc_ctc_backward")
+        ctx.grad = grad
+        ctx.applied = None          # the factor already multiplied into ctx.grad (None = 1)
         loss = out if red == 0 else out.reshape(())
         return loss.to(log_probs.dtype) if log_probs.dtype != torch.float32 else loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        log_probs, targets, input_lengths, target_lengths, nll, ws = ctx.saved_tensors
-        blank, red, zero_inf, lmax, tstride, offsets, ws_bytes = ctx.cfg
-        dev = log_probs.device
-        T, B, V = log_probs.shape
+        grad = ctx.grad
+        if grad is None:
+            raise RuntimeError("CTC backward without a forward that required grad")
+        T, B, V = grad.shape
+        dev = grad.device
         go = grad_out.detach().to(torch.float32).contiguous()
+        if ctx.applied is not None:     # a second backward through a retained graph: undo the factor applied before
+            go = go / ctx.applied
         gstride = 0 if go.numel() == 1 else 1
-        grad = torch.empty((T, B, V), dtype=log_probs.dtype, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().avctc_ctc_backward(
-                log_probs.data_ptr(), _lib.dtype_enum(log_probs), log_probs.stride(0), log_probs.stride(1),
-                T, B, V, targets.data_ptr(), tstride, offsets.data_ptr() if offsets is not None else None,
-                input_lengths.data_ptr(), target_lengths.data_ptr(), lmax, blank, red, zero_inf,
-                nll.data_ptr(), go.data_ptr(), gstride, grad.data_ptr(), ws.data_ptr(), ws_bytes,
-                _lib.stream_ptr(dev)), "avctc_ctc_backward")
+            _lib.check(_lib.lib().avctc_ctc_scale_grad(grad.data_ptr(), _lib.dtype_enum(grad), T, B, V, go.data_ptr(),
+                                                       gstride, _lib.stream_ptr(dev)), "avctc_ctc_scale_grad")
+        ctx.applied = grad_out.detach().to(torch.float32).clone()
         return grad, None, None, None, None, None, None
+
+
+_UNIT = {}
+
+
+def _unit(dev):
+    """fp32 1.0 on `dev`, written once (long before any kernel that reads it is enqueued)."""
+    t = _UNIT.get(dev)
+    if t is None:
+        t = _UNIT[dev] = torch.ones(1, dtype=torch.float32, device=dev)
+    return t
 
 
 def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, reduction="mean", zero_infinity=False):
@@ -102,6 +120,12 @@ def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank=0, reducti
     if reduction not in _lib.REDUCTION:
         raise ValueError(f"{reduction} is not a valid value for reduction")
     unbatched = log_probs.dim() == 2
+    if unbatched:       # (T,V) like torch; the unsqueeze stays OUTSIDE the Function so autograd squeezes the gradient back
+        log_probs = log_probs.unsqueeze(1)
+        targets = torch.as_tensor(targets)
+        targets = targets.unsqueeze(0) if targets.dim() == 1 else targets
+        input_lengths = torch.as_tensor(input_lengths).reshape(1)
+        target_lengths = torch.as_tensor(target_lengths).reshape(1)
     out = _CTCLossFn.apply(log_probs, targets, input_lengths, target_lengths, blank, reduction, zero_infinity)
     if unbatched and reduction == "none":
         out = out.reshape(())

@@ -5,11 +5,15 @@ by batch item.  Every hot-path op is per-sample except the fusion resample (batc
 (mixes frames across the local batch), so an N-GPU step equals "N independent reference micro-batches with
 averaged gradients"  — that is what tests/test_ddp_cpu.py checks on gloo.
 
-GradBucketReducer: parameters are packed (reverse registration order = backward order) into flat fp32 buckets;
-a post-accumulate-grad hook copies each gradient into its bucket and, when a bucket is complete, launches an
-asynchronous all_reduce on a side stream so communication overlaps the rest of backward.  finish() waits,
-divides by world size and copies the averages back into .grad.  Parameters that received no gradient in a step
-(e.g. cross_attn_visual, never used by the reference) are skipped: their bucket slots stay zero on every rank.
+GradBucketReducer: parameters are packed (reverse registration order = backward order) into flat fp32 buckets and
+every `.grad` IS a view into its bucket, so autograd accumulates straight into the communication buffer: no
+per-parameter copy in, no copy back.  A post-accumulate-grad hook only counts; when a bucket is complete (and
+every earlier bucket has been launched — the collective order is the bucket index on every rank) an asynchronous
+all_reduce(SUM) goes out on a side stream under the rest of backward.  finish() launches what is left, waits, and
+scales all buckets with ONE foreach multiply by 1 / (number of ranks whose step succeeded) — that count travels
+in a spare slot of the last bucket, so a rank whose forward/backward raised contributes zeros and every rank
+still applies the same update (see finish()).  Parameters that received no gradient in a step (e.g.
+cross_attn_visual, never used by the reference) end the step with `.grad = None`, as in a single process.
 """
 from __future__ import annotations
 
@@ -66,13 +70,19 @@ def broadcast_buffers(module, src=0, group=None):
 
 
 class GradBucketReducer:
-    def __init__(self, params, bucket_bytes=64 << 20, group=None, overlap=True):
+    def __init__(self, params, bucket_bytes=24 << 20, group=None, overlap=True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
         self.overlap = overlap and self.world > 1
-        self.buckets = []          # list of dict(flat, items=[(param, offset, numel)], pending, work)
+        self.buckets = []          # dict(flat, items=[(param, offset, numel)], ready=set(), work)
         self._slot = {}
+        self._next = 0             # buckets [0, _next) have been launched this step
+        self._inactive = None      # parameters that got no gradient in the first finished step (outside the graph, e.g.
+                                   # cross_attn_visual): counted as ready from the start of later steps
+        self._late = None          # an "inactive" parameter received a gradient after its bucket had left
+        self._handles = []
+        self.stream = None
         if not self.params:
             return
         dev = self.params[0].device
@@ -85,21 +95,55 @@ class GradBucketReducer:
                 cur, cur_bytes = [], 0
         if cur:
             self._add_bucket(cur, dev)
+        # spare slot behind the last bucket: the number of ranks whose step succeeded
+        last = self.buckets[-1]
+        flat = torch.zeros(last["flat"].numel() + 1, dtype=torch.float32, device=dev)
+        last["flat"] = flat
+        self._ok = flat[-1:]
+        self._scale = torch.ones((), dtype=torch.float32, device=dev)
         self.stream = torch.cuda.Stream(device=dev) if (dev.type == "cuda" and self.overlap) else None
-        self._handles = []
-        if self.overlap:
-            for p in self.params:
-                self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        for p in self.params:
+            self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self.zero_grad()
 
     def _add_bucket(self, plist, dev):
         total = sum(p.numel() for p in plist)
-        b = dict(flat=torch.zeros(total, dtype=torch.float32, device=dev), items=[], pending=0, work=None, ready=set())
+        b = dict(flat=torch.zeros(total, dtype=torch.float32, device=dev), items=[], work=None, ready=set())
         off = 0
         for p in plist:
             b["items"].append((p, off, p.numel()))
-            self._slot[p] = (len(self.buckets), off)
+            self._slot[p] = len(self.buckets)
             off += p.numel()
         self.buckets.append(b)
+
+    # -------------------------------------------------------------------------------------------- step protocol
+    def reset(self):
+        """Forget a step that did not reach finish(): wait for collectives that are still in flight (every rank
+        launched them, so they complete), clear the per-step bookkeeping."""
+        for b in self.buckets:
+            if b["work"] is not None:
+                b["work"].wait()
+                b["work"] = None
+            b["ready"] = set()
+        self._next = 0
+        self._late = None
+
+    def _arm(self):
+        for b in self.buckets:
+            b["ready"] = {p for p, _, _ in b["items"] if p in self._inactive} if self._inactive else set()
+
+    def zero_grad(self):
+        """Start of a step (instead of optimizer.zero_grad()): one fill per bucket, and every parameter's .grad is
+        (again) the view into its bucket that autograd accumulates into."""
+        self.reset()
+        for b in self.buckets:
+            b["flat"].zero_()
+            flat = b["flat"]
+            for p, off, n in b["items"]:
+                g = p.grad
+                if g is None or g.data_ptr() != flat.data_ptr() + 4 * off:
+                    p.grad = flat[off:off + n].view_as(p)
+        self._arm()
 
     def _launch(self, b):
         if self.stream is not None:
@@ -109,38 +153,58 @@ class GradBucketReducer:
         else:
             b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
-    def _on_grad(self, p):
-        bi, off = self._slot[p]
-        b = self.buckets[bi]
-        b["flat"][off:off + p.numel()].copy_(p.grad.reshape(-1))
-        b["ready"].add(p)
-        if len(b["ready"]) == len(b["items"]) and b["work"] is None:
-            self._launch(b)
+    def _launch_ready(self):
+        last = len(self.buckets) - 1            # the last bucket carries the ok count: it leaves from finish()
+        while self._next < last and len(self.buckets[self._next]["ready"]) == len(self.buckets[self._next]["items"]):
+            self._launch(self.buckets[self._next])
+            self._next += 1
 
-    def finish(self):
-        """Call after backward(): completes every bucket and writes averaged gradients back."""
-        if self.world == 1:
+    def _on_grad(self, p):
+        bi = self._slot[p]
+        b = self.buckets[bi]
+        if self._inactive and p in self._inactive:
+            self._inactive.discard(p)
+            if bi < self._next:
+                self._late = p
+        b["ready"].add(p)
+        if self.overlap and self.world > 1:
+            self._launch_ready()
+
+    def finish(self, ok=True):
+        """Call after backward() — also when the step raised (ok=False): every rank launches every bucket exactly
+        once per step, in index order, whatever happened to its own step.  A failed rank contributes zeros for the
+        buckets that had not left yet and 0 to the ok count; gradients are divided by the ok count, so the ranks
+        whose step worked are averaged over themselves and ALL ranks (the failed one included) end up with the same
+        gradients and must apply the same optimizer step."""
+        if self.world == 1 or not self.buckets:
             return
-        for b in self.buckets:
-            if b["work"] is None:                 # hooks disabled, or some params got no gradient this step
-                for p, off, n in b["items"]:
-                    if p not in b["ready"]:
-                        if p.grad is not None:
-                            b["flat"][off:off + n].copy_(p.grad.reshape(-1))
-                        else:
-                            b["flat"][off:off + n].zero_()
-                self._launch(b)
+        self._ok.fill_(1.0 if ok else 0.0)
+        while self._next < len(self.buckets):
+            b = self.buckets[self._next]
+            if not ok:
+                b["flat"][:sum(n for _, _, n in b["items"])].zero_()
+            self._launch(b)
+            self._next += 1
         for b in self.buckets:
             b["work"].wait()
+            b["work"] = None
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
-        inv = 1.0 / self.world
+        torch.reciprocal(self._ok.clamp(min=1.0).reshape(()), out=self._scale)
+        torch._foreach_mul_([b["flat"] for b in self.buckets], self._scale)
+        if ok and self._inactive is None:
+            self._inactive = {p for b in self.buckets for p, _, _ in b["items"] if p not in b["ready"]}
+        elif ok:
+            self._inactive |= {p for b in self.buckets for p, _, _ in b["items"] if p not in b["ready"]}
+        for p in (self._inactive or ()):        # parameters outside the graph keep .grad = None (Adam skips them)
+            p.grad = None
+        late, self._late = self._late, None
         for b in self.buckets:
-            for p, off, n in b["items"]:
-                if p.grad is not None:
-                    p.grad.copy_((b["flat"][off:off + n] * inv).view_as(p.grad))
-            b["work"] = None
             b["ready"] = set()
+        self._next = 0
+        if late is not None:
+            raise RuntimeError("a parameter that had received no gradient in earlier steps received one after its bucket "
+                               "had been reduced; this step's gradients are incomplete (the next step is correct)")
 
     def grad_bytes(self):
         return sum(b["flat"].numel() * 4 for b in self.buckets)

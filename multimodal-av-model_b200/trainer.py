@@ -237,10 +237,9 @@ class MultimodalTrainer:
         total = (ctc[0] + ctc[1]) / 2 + self.lambda_ * (con[0] + con[1]) / 2
         return total, ctc[0], ctc[1], con[0], con[1]
 
-    def train_step(self, batch):
-        """One optimisation step on one collated batch, or on a StagedBatch from stage() (the body of the reference's
-        loop, trainer.py:64-125).  Returns the detached total loss (device tensor; no host sync)."""
-        self.optimizer.zero_grad()
+    def _forward_backward(self, batch):
+        if isinstance(batch, Exception):          # a staging error (train_epoch._stage_next) fails THIS step, inside the
+            raise batch                           # step protocol, so that under DDP the peers are not left waiting
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=str(self.device).startswith("cuda")):
             d = self.stage(batch)
             kw = d["enc_kw"]
@@ -259,9 +258,29 @@ class MultimodalTrainer:
                 vis = [self.visual_encoder(d["lips"][0]()), self.visual_encoder(d["lips"][1]())]
             total, c1, c2, k1, k2 = self.hot_path_loss(vis, aud, mid, d["masks"], d["texts"], d["lens"])
         total.backward()
+        return total, c1, c2, k1, k2
+
+    def train_step(self, batch):
+        """One optimisation step on one collated batch, or on a StagedBatch from stage() (the body of the reference's
+        loop, trainer.py:64-125).  Returns the detached total loss (device tensor; no host sync)."""
         if self._reducer is not None:
-            self._reducer.finish()
+            self._reducer.zero_grad()           # .grad = zeroed views into the all-reduce buckets
+        else:
+            self.optimizer.zero_grad()
+        err = None
+        try:
+            total, c1, c2, k1, k2 = self._forward_backward(batch)
+        except Exception as e:
+            if self._reducer is None:
+                raise
+            err = e
+        if self._reducer is not None:
+            # every rank reduces every bucket and applies the same update, also when ITS step raised (it then contributes
+            # zeros and is left out of the average, ddp.GradBucketReducer.finish); the error surfaces afterwards
+            self._reducer.finish(ok=err is None)
         self.optimizer.step()
+        if err is not None:
+            raise err
         self._last_parts = (c1.detach(), c2.detach(), k1.detach(), k2.detach())
         return total.detach()
 
@@ -294,8 +313,6 @@ class MultimodalTrainer:
             batch_idx += 1
             loss = None
             try:
-                if isinstance(cur, Exception):
-                    raise cur
                 loss = self.train_step(cur)
             except Exception as e:                      # same policy as trainer.py:162-164
                 print(f"Error at batch {batch_idx}: {e}", flush=True)
@@ -350,7 +367,12 @@ class MultimodalTrainer:
                         lps.append(lp)
                 total_loss += (losses[0].item() + losses[1].item()) / 2
                 B = lps[0].shape[0]
-                ids = beam_search_batch(torch.cat(lps, 0), beam_width=self.beam_width, blank=blank)   # all 2B at once
+                if lps[0].shape[1:] == lps[1].shape[1:]:
+                    ids = beam_search_batch(torch.cat(lps, 0), beam_width=self.beam_width, blank=blank)   # all 2B at once
+                else:       # collate_fn pads lip1 and lip2 separately (dataset/collate_fn.py:18-23): T_v1 != T_v2 is the
+                    ids = []   # normal case on real data; each speaker then decodes exactly its own padded T (trainer.py:230,237)
+                    for lp_s in lps:
+                        ids.extend(beam_search_batch(lp_s, beam_width=self.beam_width, blank=blank))
                 lens_h = [d["lens"][0].cpu().tolist(), d["lens"][1].cpu().tolist()]
                 texts_h = [d["texts"][0].cpu(), d["texts"][1].cpu()]
                 for i in range(B):

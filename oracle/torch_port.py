@@ -131,3 +131,29 @@ def hot_path_losses(fusion, decoder, projection_layer, feats, blank, lambda_=0.1
         lp = decoder(fused)
         ctc = ctc + crit(lp.transpose(0, 1), f["text"], il, f["text_len"])
     return ctc / 2 + lambda_ * con / 2
+
+
+def _beam_pool_init():
+    torch.set_num_threads(1)
+
+
+def _beam_pool_job(args):
+    lp, beam, blank = args                                  # numpy [T,V] (plain pickling; no shared-memory handles)
+    return simple_beam_search(torch.from_numpy(lp), beam, blank)
+
+
+def beam_search_pool(log_probs, beam_width, blank, workers):
+    """simple_beam_search over a batch [N,T,V] in a pool of `workers` single-threaded processes (the reference decodes one
+    utterance at a time in Python, trainer.py:229-242; a pool over the host cores is the best a CPU box can do with it).
+    Returns (seconds of decode wall time excluding pool start-up, token lists)."""
+    import multiprocessing as mp
+    import time
+    lp = log_probs.detach().float().cpu().contiguous()
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers, initializer=_beam_pool_init) as pool:
+        pool.map(_beam_pool_job, [(lp[0][:2].numpy().copy(), beam_width, blank)] * workers)   # start-up + imports, untimed
+        jobs = [(lp[i].numpy(), beam_width, blank) for i in range(lp.shape[0])]
+        t0 = time.perf_counter()
+        out = pool.map(_beam_pool_job, jobs, chunksize=max(1, len(jobs) // (4 * workers)))
+        dt = time.perf_counter() - t0
+    return dt, out

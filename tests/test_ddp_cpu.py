@@ -28,11 +28,15 @@ def _worker(rank, world, port, overlap, q):
     g = torch.Generator().manual_seed(100)
     x_all = torch.randn(8, 6, generator=g); y_all = torch.randn(8, 3, generator=g)
     lo, hi = ddp.shard_range(8, r, w)
-    for step in range(2):
-        model.zero_grad()
+    for step in range(3):
+        red.zero_grad()
         loss = ((model(x_all[lo:hi]) - y_all[lo:hi]) ** 2).mean()
         loss.backward()
         red.finish()
+        # .grad lives inside the communication buckets (no copy in, no copy back)
+        assert all(any(p.grad.data_ptr() >= b["flat"].data_ptr() and
+                       p.grad.data_ptr() < b["flat"].data_ptr() + 4 * b["flat"].numel() for b in red.buckets)
+                   for p in model.parameters())
     grads = [p.grad.clone() for p in model.parameters()]
     # single-process truth: average of the two shard gradients
     ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
@@ -111,3 +115,58 @@ def test_broadcast_buffers_aligns_running_statistics_only():
     assert all(same for _, same, _, _, _ in res), res
     assert res[0][2] is True and res[1][2] is False          # rank 0 kept its statistics, rank 1 adopted them
     assert all(w_ok for _, _, _, w_ok, _ in res) and all(n == 3 for *_, n in res)
+
+
+def _failure_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from multimodal_av_model_b200 import ddp
+    r, _, w = ddp.init_distributed("gloo")
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    red = ddp.GradBucketReducer(list(model.parameters()), bucket_bytes=64)
+    g = torch.Generator().manual_seed(100)
+    x_all = torch.randn(8, 6, generator=g); y_all = torch.randn(8, 3, generator=g)
+    lo, hi = ddp.shard_range(8, r, w)
+    out = {}
+    for step, fail_rank in enumerate((None, 1, None)):
+        red.zero_grad()
+        ok = True
+        try:
+            h = model[1](model[0](x_all[lo:hi]))
+            if fail_rank == rank:
+                raise RuntimeError("synthetic failure between forward and backward")
+            ((model[2](h) - y_all[lo:hi]) ** 2).mean().backward()
+        except RuntimeError:
+            ok = False
+        red.finish(ok=ok)
+        out[step] = [p.grad.clone() for p in model.parameters()]
+    # truth: step 1 = rank 0's own gradient on every rank (the failed rank is left out of the average);
+    # step 2 = the plain average again (no stale bucket state survived the failed step)
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    per_rank = []
+    for rr in range(w):
+        a, b = ddp.shard_range(8, rr, w)
+        ref.zero_grad()
+        ((ref(x_all[a:b]) - y_all[a:b]) ** 2).mean().backward()
+        per_rank.append([p.grad.clone() for p in ref.parameters()])
+    avg = [(a + b) / 2 for a, b in zip(*per_rank)]
+    ok1 = all(torch.allclose(a, b, atol=1e-6) for a, b in zip(out[1], per_rank[0]))
+    ok02 = all(torch.allclose(a, b, atol=1e-6) for s_ in (0, 2) for a, b in zip(out[s_], avg))
+    q.put((rank, bool(ok1), bool(ok02)))
+    dist.destroy_process_group()
+
+
+def test_failed_rank_is_left_out_and_every_rank_gets_the_same_gradients():
+    """a step that raises on one rank must neither desynchronise the collectives nor leak stale
+    bucket state into the next step."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_failure_worker, args=(r, 2, 29631, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(a and b for _, a, b in res), res

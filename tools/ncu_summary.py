@@ -4,6 +4,7 @@ or a launch list csv from `ncu --metrics gpu__time_duration.sum --csv --log-file
 
     python tools/ncu_summary.py rep  gpurun_out/x.ncu-rep  > profiles/r01_x_full.txt
     python tools/ncu_summary.py list gpurun_out/launches.csv > profiles/r01_x_launches.txt
+    python tools/ncu_summary.py traffic gpurun_out/ctc.ncu-rep profiles/ctc_traffic.json   # what bench.py's roofline.traffic reads
 """
 import collections
 import csv
@@ -74,5 +75,40 @@ def launches(path):
         print(f"{t:12.1f} {100 * t / tot:6.1f}% {n:6d} {t / n:10.2f}  {k[:140]}")
 
 
+def traffic(path, out_path):
+    """DRAM bytes (read + write) of the LAST launch of the CTC scan and gradient kernels in a --set full report, with the
+    hash of the kernel sources they were built from: bench.py quotes the figure only while that hash matches."""
+    import json
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    kn = hdr.index("Kernel Name")
+    sc = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tsc = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+    ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+    last = {}
+    for r in data:
+        name = r[kn].split("(")[0].split("<")[0]
+        if not name.startswith(("ctc_scan", "ctc_grad")):
+            continue
+        rd, wr = float(r[ir].replace(",", "")) * sc[units[ir]], float(r[iw].replace(",", "")) * sc[units[iw]]
+        if rd + wr < 1e6:            # the guarded log-domain twins exit at once: not part of the traffic
+            continue
+        last[name] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "time_us": float(r[it].replace(",", "")) * tsc[units[it]]}
+    head = subprocess.run(["git", "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True).stdout.strip()
+    d = {"what": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none, config 2 "
+                 "(B=64 T=1000 V=801 fp32), one CTC forward+backward", "report": os.path.basename(path),
+         "source_hash": bench.source_hash(), "git_head": head, "kernels": last,
+         "traffic_bytes": sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in last.values())}
+    json.dump(d, open(out_path, "w"), indent=1)
+    print(json.dumps(d, indent=1))
+
+
 if __name__ == "__main__":
-    {"rep": rep, "list": launches}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3])
+    else:
+        {"rep": rep, "list": launches}[sys.argv[1]](sys.argv[2])
