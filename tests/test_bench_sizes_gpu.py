@@ -61,10 +61,10 @@ def test_fusion_projection_config3_full_size_vs_torch_port(record_property):
         elif not k.startswith("temporal_model"):
             errs[k] = relerr(p.grad, q.grad)
     print("config-3 bf16 errors (max-norm relative):", {k: round(v, 5) for k, v in errs.items()})
-    assert errs["fused"] < 1e-2, errs                 # measured 4e-3
+    assert errs["fused"] < 1e-2, errs                 # measured on B200: 3.9e-3
     assert rms_relerr(f, f_ref) < 5e-3
     for k, v in errs.items():
-        assert v < 2e-2, (k, v, errs)                 # measured <= 8e-3 for every gradient
+        assert v < 1.5e-2, (k, v, errs)               # measured: 1.6e-3 ... 7.7e-3 (d_audio) over all gradients
 
 
 def test_bilstm_config3_full_size_vs_torch():
@@ -87,9 +87,9 @@ def test_bilstm_config3_full_size_vs_torch():
     for name, p, g in zip(ref._flat_weights_names, ref._flat_weights, g_ref):
         errs[name] = relerr(p.grad, g)
     print("BiLSTM (32,150,512) bf16 errors:", {k: round(v, 5) for k, v in errs.items()})
-    assert errs["y"] < 1e-2, errs
+    assert errs["y"] < 1e-2, errs                     # measured on B200: 4.7e-3
     for k, v in errs.items():
-        assert v < 2e-2, (k, v)
+        assert v < 1e-2, (k, v)                       # measured: 1.8e-3 ... 5.1e-3
 
 
 class _Enc(torch.nn.Module):
@@ -131,7 +131,7 @@ def test_hot_path_step_config4_size_vs_torch_port():
         errs[f"d_audio{s}"] = relerr(fd["audio"][s].grad, feats[s]["audio"].grad)
     print("config-4 hot-path gradient errors:", {k: round(v, 4) for k, v in errs.items()})
     for k, v in errs.items():
-        assert v < 3e-2, (k, v)
+        assert v < 2e-2, (k, v)                       # measured on B200: <= 5.2e-3 (parameters), 8.6e-3 (d_audio)
 
 
 def test_ctc_bf16_config2_full_size():

@@ -41,6 +41,10 @@ def test_fusion_and_head_match_reference_fixture(name):
     lp = dec(fused)
     (lp * torch.from_numpy(c["r"]).cuda()).sum().backward()
     assert il.cpu().tolist() == c["input_lengths"].tolist()          # exact
+    print(name, "fused", round(relerr(fused, torch.from_numpy(c["fused"])), 5), "lp", round((lp.cpu() - torch.from_numpy(c["log_probs"])).abs().max().item(), 5),
+          "d_audio", round(relerr(aud.grad, torch.from_numpy(c["grad_audio"])), 5), "d_visual", round(relerr(vis.grad, torch.from_numpy(c["grad_visual"])), 5),
+          "params", round(max(relerr(p.grad, torch.from_numpy(c[f"dec_grad/{k[4:]}"] if k.startswith("dec.") else c[f"grad/{k}"]))
+                              for k, p in list(fus.named_parameters()) + [("dec." + k, p) for k, p in dec.named_parameters()] if p.grad is not None), 5))
     assert relerr(fused, torch.from_numpy(c["fused"])) < 2e-2
     assert (lp.cpu() - torch.from_numpy(c["log_probs"])).abs().max().item() < 3e-2
     assert relerr(aud.grad, torch.from_numpy(c["grad_audio"])) < 5e-2
@@ -155,6 +159,8 @@ def test_fused_path_odd_shapes_full_module_vs_torch_port(B, Tv, Ta, E, H):
     y, il = ours(v2, a2, mask=mask.cuda())
     (y * r.cuda()).sum().backward()
     assert il.cpu().tolist() == il_ref.tolist()
+    print((B, Tv, Ta, E, H), "y", round(relerr(y, y_ref), 5), "d_audio", round(relerr(a2.grad, a1.grad), 5), "d_visual", round(relerr(v2.grad, v1.grad), 5),
+          "params", round(max(relerr(p.grad, q.grad) for (k, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()) if q.grad is not None), 5))
     assert relerr(y, y_ref) < 3e-2
     assert relerr(a2.grad, a1.grad) < 6e-2
     assert relerr(v2.grad, v1.grad) < 6e-2

@@ -9,6 +9,7 @@ or a launch list csv from `ncu --metrics gpu__time_duration.sum --csv --log-file
 import collections
 import csv
 import io
+import re
 import subprocess
 import sys
 
@@ -91,9 +92,10 @@ def traffic(path, out_path):
     ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
     last = {}
     for r in data:
-        name = r[kn].split("(")[0].split("<")[0]
-        if not name.startswith(("ctc_scan", "ctc_grad")):
+        m = re.search(r"(ctc_scan\w*|ctc_grad\w*)", r[kn])
+        if not m:
             continue
+        name = m.group(1)
         rd, wr = float(r[ir].replace(",", "")) * sc[units[ir]], float(r[iw].replace(",", "")) * sc[units[iw]]
         if rd + wr < 1e6:            # the guarded log-domain twins exit at once: not part of the traffic
             continue
