@@ -101,6 +101,16 @@ AVCTC_API int avctc_ctc_backward(const void* log_probs, int dtype, int64_t strid
                        const float* nll, const float* grad_out, int64_t grad_out_stride,
                        void* grad, const void* workspace, size_t workspace_bytes, void* stream);
 
+/* avctc_ctc_forward(need_grad=1) + avctc_ctc_reduce + avctc_ctc_backward enqueued back to back by one call (same
+ * arguments, same results): the form in which the gradient pass overlaps the scan. */
+AVCTC_API int avctc_ctc_forward_backward(const void* log_probs, int dtype, int64_t stride_t, int64_t stride_b,
+                               int T, int B, int V,
+                               const int64_t* targets, int64_t target_stride, const int64_t* target_offsets,
+                               const int64_t* input_lengths, const int64_t* target_lengths,
+                               int max_target_len, int blank, int reduction, int zero_infinity,
+                               float* nll, float* loss, const float* grad_out, int64_t grad_out_stride,
+                               void* grad, void* workspace, size_t workspace_bytes, void* stream);
+
 /* grad[t][b][:] *= grad_out[b*grad_out_stride], in place (rows whose factor is exactly 1 are left alone).  The autograd
  * host uses it to run the gradient pass at forward time: avctc_ctc_backward with a unit grad_out goes out directly behind
  * avctc_ctc_forward (so it overlaps the scan, see above) and loss.backward() only applies the incoming factor — the
@@ -185,30 +195,51 @@ AVCTC_API int avctc_log_softmax_backward(const void* Y, const void* dY, int dtyp
                                long long ldx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Attention core (tcgen05 + TMEM, scores never leave the SM) — replaces, inside nn.MultiheadAttention
+ *   /root/reference/model/fusion_module.py:61 -> torch/nn/functional.py:6630-6652,
+ * bmm(q / sqrt(hd), k^T) -> softmax over all T keys (no mask) -> bmm(P, v), and its autograd.
+ * q: bf16 [B,T,E] (the projected queries, head h in columns [h*128, h*128+128)); kv: bf16 [B,T,2E] (keys | values).
+ * o: bf16 [B,T,E] (heads already merged); lse2: fp32 [B*H,T] = log2 sum_j exp(s_ij / sqrt(hd)) (kept for backward).
+ * backward: dout bf16 [B,T,E] plus the forward's o and lse2 -> dq bf16 [B,T,E], dkv bf16 [B,T,2E] (dk | dv).
+ * Requires E == 128*H and T <= 192 (AVCTC_ERR_UNSUPPORTED otherwise); pointers 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+AVCTC_API int avctc_attention_forward(const void* q, const void* kv, void* o, float* lse2, int B, int T, int H, int E,
+                            void* stream);
+AVCTC_API int avctc_attention_backward(const void* q, const void* kv, const void* dout, const void* o, const float* lse2,
+                             void* dq, void* dkv, int B, int T, int H, int E, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused fusion path — CrossAttentionFusion.forward up to and including fusion_proj, and its backward,
  *   /root/reference/model/fusion_module.py:40-63 (resample, visual_proj, audio_proj, cross_attn_audio, fusion_proj)
- * as ONE host call each: the call enqueues the weight casts, the resample, the tcgen05 GEMMs, the softmax and the bias
- * column sums on `stream`.  Requires fused_dim/num_heads to be a multiple of 64 and Dv, Da multiples of 8.
+ * as ONE host call each: the call enqueues the resample, the (grouped) tcgen05 GEMMs, the fused attention kernel
+ * (csrc/attention.cu: Q.K^T -> softmax -> P.V with the scores in tensor memory; T <= 192 and head_dim 128, other shapes
+ * run it as GEMM + softmax + GEMM) and the bias column sums on `stream`.  Requires fused_dim/num_heads to be a multiple
+ * of 64 and Dv, Da multiples of 8.
  * visual: bf16 [B*T,Dv]; audio: fp32/bf16 [B,Ta,Da]; mask int64 [B,Ta]; weights and biases are the fp32 nn.Module
- * parameters (w_in/b_in = MultiheadAttention.in_proj_weight/bias [3E,E]/[3E]).  out: fp32 [B*T,E].
- * `saved` (which=0 bytes) carries the bf16 weights and activations from forward to backward; `scratch` (which=1 for
- * forward, which=2 for backward) is free after the call's kernels ran.  backward writes fp32 parameter gradients and,
- * when the pointers are non-NULL, d_visual (bf16 [B*T,Dv]) and d_audio ([B,Ta,Da], fp32 or bf16).  grads_zeroed != 0
- * promises that all ten gradient tensors were zeroed by the caller (e.g. views of one zero-filled buffer): the library
- * then skips its own per-tensor memsets.
+ * parameters (w_in/b_in = MultiheadAttention.in_proj_weight/bias [3E,E]/[3E]).  out: [B*T,E] fp32 or bf16 (out_dtype).
+ * `wbf16` (which=3 bytes) holds the bf16 copies of the five weight matrices; the caller keeps it across calls and sets
+ * refresh_weights != 0 whenever a weight changed since the buffer was last filled (first call, optimizer step) — the
+ * library then re-casts them first.  backward must see the buffer as forward left it.
+ * `saved` (which=0 bytes) carries the activations from forward to backward; `scratch` (which=1 for forward, which=2
+ * for backward) is free after the call's kernels ran.  backward writes fp32 parameter gradients and, when the pointers
+ * are non-NULL, d_visual (bf16 [B*T,Dv]) and d_audio ([B,Ta,Da], fp32 or bf16).  grads_zeroed != 0 promises that all
+ * ten gradient tensors were zeroed by the caller (e.g. views of one zero-filled buffer): the library then skips its
+ * own per-tensor memsets.
  * ---------------------------------------------------------------------------------------------- */
 AVCTC_API size_t avctc_fusion_workspace_bytes(int B, int T, int Ta, int Dv, int Da, int E, int H, int which);
 AVCTC_API int avctc_fusion_forward(const void* visual_bf16, const void* audio, int audio_dtype, const int64_t* mask,
                          const float* w_vp, const float* b_vp, const float* w_ap, const float* b_ap,
                          const float* w_in, const float* b_in, const float* w_o, const float* b_o,
                          const float* w_f, const float* b_f, int B, int T, int Ta, int Dv, int Da, int E, int H,
-                         float* out, int64_t* mask_out, int64_t* input_lengths, void* saved, size_t saved_bytes,
+                         void* out, int out_dtype, int64_t* mask_out, int64_t* input_lengths,
+                         void* wbf16, size_t wbf16_bytes, int refresh_weights, void* saved, size_t saved_bytes,
                          void* scratch, size_t scratch_bytes, void* stream);
 AVCTC_API int avctc_fusion_backward(const void* df, int df_dtype, const void* visual_bf16, int B, int T, int Ta, int Dv,
                           int Da, int E, int H, float* g_wvp, float* g_bvp, float* g_wap, float* g_bap,
                           float* g_win, float* g_bin, float* g_wo, float* g_bo, float* g_wf, float* g_bf,
-                          void* d_visual_bf16, void* d_audio, int d_audio_dtype, const void* saved,
-                          size_t saved_bytes, void* scratch, size_t scratch_bytes, int grads_zeroed, void* stream);
+                          void* d_visual_bf16, void* d_audio, int d_audio_dtype, const void* wbf16, size_t wbf16_bytes,
+                          const void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes, int grads_zeroed,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * temporal_model — nn.LSTM(E, E, num_layers=2, batch_first=True, bidirectional=True), zero initial state,

@@ -29,6 +29,8 @@ SIGNATURES = {
     "avctc_ctc_reduce": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "avctc_ctc_backward": (_i, [_vp, _i, _i64, _i64, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i,
                                 _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "avctc_ctc_forward_backward": (_i, [_vp, _i, _i64, _i64, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i,
+                                        _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "avctc_ctc_scale_grad": (_i, [_vp, _i, _i, _i, _i, _vp, _i64, _vp]),
     "avctc_beam_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "avctc_beam_search": (_i, [_vp, _i64, _i64, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -42,9 +44,13 @@ SIGNATURES = {
     "avctc_colsum": (_i, [_vp, _i, ctypes.c_longlong, _i, ctypes.c_longlong, _vp, _i, _vp]),
     "avctc_log_softmax_forward": (_i, [_vp, _i, _vp, _i, ctypes.c_longlong, _i, _vp]),
     "avctc_log_softmax_backward": (_i, [_vp, _vp, _i, _vp, ctypes.c_longlong, _i, ctypes.c_longlong, _vp]),
+    "avctc_attention_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "avctc_attention_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "avctc_fusion_workspace_bytes": (_sz, [_i] * 8),
-    "avctc_fusion_forward": (_i, [_vp, _vp, _i, _vp] + [_vp] * 10 + [_i] * 7 + [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
-    "avctc_fusion_backward": (_i, [_vp, _i, _vp] + [_i] * 7 + [_vp] * 10 + [_vp, _vp, _i, _vp, _sz, _vp, _sz, _i, _vp]),
+    "avctc_fusion_forward": (_i, [_vp, _vp, _i, _vp] + [_vp] * 10 + [_i] * 7 + [_vp, _i, _vp, _vp, _vp, _sz, _i, _vp, _sz,
+                                  _vp, _sz, _vp]),
+    "avctc_fusion_backward": (_i, [_vp, _i, _vp] + [_i] * 7 + [_vp] * 10 + [_vp, _vp, _i, _vp, _sz, _vp, _sz, _vp, _sz, _i,
+                                   _vp]),
     "avctc_bilstm_workspace_bytes": (_sz, [_i] * 5),
     "avctc_bilstm_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp, _sz, _i, _vp]),
     "avctc_bilstm_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
@@ -66,11 +72,11 @@ class GemmOperand(ctypes.Structure):
 
 # kernels launched by each entry point (bench.py reports "gpu_launches" from this table); CTC forward / backward with a
 # workspace = the probability-domain kernel + its guarded log-domain twin (which exits at once unless the range guard tripped)
-KERNELS = {"avctc_ctc_forward": 2, "avctc_ctc_reduce": 1, "avctc_ctc_backward": 2, "avctc_ctc_scale_grad": 1, "avctc_beam_search": 2,
+KERNELS = {"avctc_ctc_forward": 2, "avctc_ctc_reduce": 1, "avctc_ctc_backward": 2, "avctc_ctc_forward_backward": 5, "avctc_ctc_scale_grad": 1, "avctc_beam_search": 2,
            "avctc_gemm_bf16": 1, "avctc_resample_forward": 2, "avctc_resample_backward": 1, "avctc_softmax_forward": 1,
            "avctc_softmax_backward": 1, "avctc_colsum": 1, "avctc_log_softmax_forward": 1,
            "avctc_log_softmax_backward": 1, "avctc_infonce_forward": 4, "avctc_infonce_backward": 2,
-           "avctc_fusion_forward": 12, "avctc_fusion_backward": 24,
+           "avctc_attention_forward": 1, "avctc_attention_backward": 1, "avctc_fusion_forward": 7, "avctc_fusion_backward": 8,
            "avctc_bilstm_forward": 7, "avctc_bilstm_backward": 20}
 launch_count = 0
 

@@ -2161,3 +2161,22 @@ extern "C" int avctc_ctc_scale_grad(void* grad, int dtype, int T, int B, int V, 
                                                                    grad_out, grad_out_stride);
     return (int)cudaGetLastError();
 }
+
+// forward + reduce + backward(unit or given grad_out) as ONE host call: what the autograd host enqueues at forward time
+extern "C" int avctc_ctc_forward_backward(const void* log_probs, int dtype, int64_t stride_t, int64_t stride_b, int T, int B,
+                                          int V, const int64_t* targets, int64_t target_stride,
+                                          const int64_t* target_offsets, const int64_t* input_lengths,
+                                          const int64_t* target_lengths, int max_target_len, int blank, int reduction,
+                                          int zero_infinity, float* nll, float* loss, const float* grad_out,
+                                          int64_t grad_out_stride, void* grad, void* workspace, size_t workspace_bytes,
+                                          void* stream) {
+    int rc = avctc_ctc_forward(log_probs, dtype, stride_t, stride_b, T, B, V, targets, target_stride, target_offsets,
+                               input_lengths, target_lengths, max_target_len, blank, 1, nll, workspace, workspace_bytes,
+                               stream);
+    if (rc) return rc;
+    rc = avctc_ctc_reduce(nll, target_lengths, B, reduction, zero_infinity, loss, stream);
+    if (rc) return rc;
+    return avctc_ctc_backward(log_probs, dtype, stride_t, stride_b, T, B, V, targets, target_stride, target_offsets,
+                              input_lengths, target_lengths, max_target_len, blank, reduction, zero_infinity, nll, grad_out,
+                              grad_out_stride, grad, workspace, workspace_bytes, stream);
+}

@@ -17,7 +17,12 @@
 // quarter, each taking half of the columns: a lone warp per SM sub-partition issues too slowly to drain the tile).
 #include <cuda.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
+#include "gemm_internal.h"
+#include "tcgen05.cuh"
 
 namespace avctc {
 
@@ -46,6 +51,18 @@ struct GemmParams {
     int dbg;                             // record phase timestamps of CTA (0,0,0) into g_gemm_dbg
 };
 
+// Several independent GEMMs in ONE launch ("grouped"): the flat grid is cut into per-job ranges of CTAs.  The steps of the
+// fusion path that do not depend on each other (e.g. a layer's dgrad and its wgrad, or the two input projections) share
+// a launch, so the SMs see 2-4x more tiles per wave and the chain has fewer launch + prologue + drain latencies.
+constexpr int kMaxJobs = 6;
+struct GemmGroup {
+    int njobs;
+    int cta_end[kMaxJobs];          // exclusive prefix of CTAs per job
+    int gx[kMaxJobs], gy[kMaxJobs]; // M tiles, N tiles of the job (z = the rest)
+    GemmParams p[kMaxJobs];
+    CUtensorMap maps[2 * kMaxJobs]; // A, B of job j at [2j], [2j+1]
+};
+
 __device__ long long g_gemm_dbg[16];
 __device__ long long g_gemm_dbg2[2 * 2048 + 2];   // per-CTA start/end timestamps (debug)
 __device__ __forceinline__ long long gtime() {
@@ -53,54 +70,7 @@ __device__ __forceinline__ long long gtime() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-#define GEMM_DBG(slot) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_gemm_dbg[slot] = gtime(); } while (0)
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
-        "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
+#define GEMM_DBG(slot) do { if (p.dbg && blockIdx.x == 0) g_gemm_dbg[slot] = gtime(); } while (0)
 
 // UMMA shared-memory descriptor, 128-byte swizzle (cute/arch/mma_sm100_desc.hpp bit layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SWIZZLE_128B)
@@ -114,8 +84,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int mn_major) {
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 2)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const GemmParams p) {
+gemm_bf16_kernel(const __grid_constant__ GemmGroup grp) {
+    int job = 0;
+    while (job + 1 < grp.njobs && (int)blockIdx.x >= grp.cta_end[job]) ++job;
+    const GemmParams p = grp.p[job];
+    const CUtensorMap* map_a = &grp.maps[2 * job];
+    const CUtensorMap* map_b = map_a + 1;
+    const int cta_local = blockIdx.x - (job ? grp.cta_end[job - 1] : 0);
+    const int bx = cta_local % grp.gx[job], by = (cta_local / grp.gx[job]) % grp.gy[job];
+    const int bz = cta_local / (grp.gx[job] * grp.gy[job]);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;             // SWIZZLE_128B tiles need 1024-byte alignment
@@ -130,10 +107,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) GEMM_DBG(0);
-    const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const int cta_lin = blockIdx.x;
     if (p.dbg && threadIdx.x == 0 && cta_lin < 2048) g_gemm_dbg2[2 * cta_lin] = gtime();
-    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
-    const int z = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+    const int m0 = bx * kBM, n0 = by * kBN;
+    const int z = bz / p.splits, split = bz % p.splits;
     const int zo = z / p.inner_count, zi = z % p.inner_count;
     const int total_kb = (p.K + kBK - 1) / kBK;
     const int kb_per = (total_kb + p.splits - 1) / p.splits;
@@ -164,7 +141,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int ak = zo * p.a.k_outer + zi * p.a.k_inner, ar = zo * p.a.r_outer + zi * p.a.r_inner + m0;
             const int az = zo * p.a.z_outer + zi * p.a.z_inner;
             const int bk = zo * p.b.k_outer + zi * p.b.k_inner, br = zo * p.b.r_outer + zi * p.b.r_inner + n0;
-            const int bz = zo * p.b.z_outer + zi * p.b.z_inner;
+            const int bzc = zo * p.b.z_outer + zi * p.b.z_inner;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kStages;
                 mbar_wait(empty(s), ((kb / kStages) & 1) ^ 1);
@@ -172,16 +149,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const uint32_t da = sA + s * kTileBytes, db = sB + s * kTileBytes;
                 const int ko = (kb0 + kb) * kBK;
                 if (p.a.mn_major) {   // tensor dims {rows, K, z}: two 64-wide row blocks of 64 k-rows each
-                    tma_load_3d(da, &map_a, full(s), ar, ak + ko, az);
-                    tma_load_3d(da + kTileBytes / 2, &map_a, full(s), ar + 64, ak + ko, az);
+                    tma_load_3d(da, map_a, full(s), ar, ak + ko, az);
+                    tma_load_3d(da + kTileBytes / 2, map_a, full(s), ar + 64, ak + ko, az);
                 } else {              // tensor dims {K, rows, z}
-                    tma_load_3d(da, &map_a, full(s), ak + ko, ar, az);
+                    tma_load_3d(da, map_a, full(s), ak + ko, ar, az);
                 }
                 if (p.b.mn_major) {
-                    tma_load_3d(db, &map_b, full(s), br, bk + ko, bz);
-                    tma_load_3d(db + kTileBytes / 2, &map_b, full(s), br + 64, bk + ko, bz);
+                    tma_load_3d(db, map_b, full(s), br, bk + ko, bzc);
+                    tma_load_3d(db + kTileBytes / 2, map_b, full(s), br + 64, bk + ko, bzc);
                 } else {
-                    tma_load_3d(db, &map_b, full(s), bk + ko, br, bz);
+                    tma_load_3d(db, map_b, full(s), bk + ko, br, bzc);
                 }
             }
         }
@@ -332,11 +309,41 @@ static int get_encode() {
     return 0;
 }
 
-// 3-D bf16 tensor: dim0 (contiguous) x dim1 (stride ld elements) x dim2 (stride zstride elements)
-static int make_map(CUtensorMap* m, const void* ptr, long long dim0, long long dim1, long long dim2, long long ld,
-                    long long zstride, int box0, int box1) {
+}  // namespace avctc
+
+using namespace avctc;
+
+namespace {
+struct MapKey {
+    const void* ptr; long long d0, d1, d2, ld, zs; int b0, b1;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && ld == o.ld && zs == o.zs && b0 == o.b0 && b1 == o.b1;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        for (long long v : {k.d0, k.d1, k.d2, k.ld, k.zs, (long long)k.b0, (long long)k.b1})
+            h = h * 1099511628211ull ^ (size_t)v;
+        return h;
+    }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+}  // namespace
+
+int avctc_tensor_map(CUtensorMap* m, const void* ptr, long long dim0, long long dim1, long long dim2, long long ld,
+                     long long zstride, int box0, int box1) {
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16 || (dim2 > 1 && (zstride * 2) % 16))
         return AVCTC_ERR_ALIGNMENT;
+    int rc = get_encode();
+    if (rc) return rc;
+    const MapKey key{ptr, dim0, dim1, dim2, ld, zstride, box0, box1};
+    {
+        std::lock_guard<std::mutex> lk(g_map_mu);
+        auto it = g_map_cache.find(key);
+        if (it != g_map_cache.end()) { *m = it->second; return 0; }
+    }
     cuuint64_t dims[3] = {(cuuint64_t)dim0, (cuuint64_t)dim1, (cuuint64_t)(dim2 > 0 ? dim2 : 1)};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(dim2 > 1 ? zstride : ld * dim1) * 2};
     cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1};
@@ -344,18 +351,12 @@ static int make_map(CUtensorMap* m, const void* ptr, long long dim0, long long d
     CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : AVCTC_ERR_BAD_ARG;
+    if (r != CUDA_SUCCESS) return AVCTC_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    if (g_map_cache.size() > 8192) g_map_cache.clear();
+    g_map_cache.emplace(key, *m);
+    return 0;
 }
-
-}  // namespace avctc
-
-using namespace avctc;
-
-// Internal launcher shared with fusion_path.cu.  splits > 1: split-K over blockIdx.z with fp32 red.add into a C that
-// this function zeroes first (fp32 output, no accumulate, batch C slices must be disjoint).
-int avctc_gemm_launch(const avctc_gemm_operand* a, const avctc_gemm_operand* b, int M, int N, int K, int batch,
-                      int inner_count, void* C, int out_dtype, long long ldc, long long c_outer, long long c_inner,
-                      const float* bias, int bias_mode, float alpha, int accumulate, int splits, void* stream);
 
 // debug only (not part of the public header): phase timestamps (ns) of CTA (0,0,0) of the last launch with gemm_dbg=1
 extern "C" __attribute__((visibility("default"))) int avctc_debug_gemm_timestamps(long long* host_out16) {
@@ -377,35 +378,49 @@ extern "C" int avctc_gemm_bf16(const avctc_gemm_operand* a, const avctc_gemm_ope
 int avctc_gemm_launch(const avctc_gemm_operand* a, const avctc_gemm_operand* b, int M, int N, int K, int batch,
                       int inner_count, void* C, int out_dtype, long long ldc, long long c_outer, long long c_inner,
                       const float* bias, int bias_mode, float alpha, int accumulate, int splits, void* stream) {
-    if (!a || !b || !C || M <= 0 || N <= 0 || K <= 0 || batch <= 0 || inner_count <= 0) return AVCTC_ERR_BAD_ARG;
-    if (out_dtype != AVCTC_F32 && out_dtype != AVCTC_BF16) return AVCTC_ERR_BAD_ARG;
-    if (accumulate && out_dtype != AVCTC_F32) return AVCTC_ERR_BAD_ARG;
-    if (bias_mode < 0 || bias_mode > 2 || (bias_mode && !bias)) return AVCTC_ERR_BAD_ARG;
-    int rc = get_encode();
-    if (rc) return rc;
-    CUtensorMap ma, mb;
-    const avctc_gemm_operand* ops[2] = {a, b};
-    CUtensorMap* maps[2] = {&ma, &mb};
-    GemmParams p;
-    OperandSpec* specs[2] = {&p.a, &p.b};
-    for (int i = 0; i < 2; ++i) {
-        const avctc_gemm_operand* o = ops[i];
-        if (!o->ptr) return AVCTC_ERR_BAD_ARG;
-        // K-major: tensor is rows x K -> TMA dims {K, rows, z}, box {64 k, 128 rows}
-        // MN-major: tensor is K x rows -> TMA dims {rows, K, z}, box {64 rows, 64 k}
-        rc = o->mn_major ? make_map(maps[i], o->ptr, o->rows, o->kdim, o->zdim, o->ld, o->zstride, 64, kBK)
-                         : make_map(maps[i], o->ptr, o->kdim, o->rows, o->zdim, o->ld, o->zstride, kBK, kBM);
-        if (rc) return rc;
-        specs[i]->k_outer = o->k_outer; specs[i]->k_inner = o->k_inner;
-        specs[i]->r_outer = o->r_outer; specs[i]->r_inner = o->r_inner;
-        specs[i]->z_outer = o->z_outer; specs[i]->z_inner = o->z_inner;
-        specs[i]->mn_major = o->mn_major ? 1 : 0;
-    }
-    p.M = M; p.N = N; p.K = K; p.batch = batch; p.inner_count = inner_count;
-    p.C = C; p.ldc = ldc; p.c_outer = c_outer; p.c_inner = c_inner; p.out_dtype = out_dtype;
-    p.bias = bias; p.bias_mode = bias_mode; p.alpha = alpha; p.accumulate = accumulate;
-    {
-        const int total_kb = (K + kBK - 1) / kBK;
+    if (!a || !b) return AVCTC_ERR_BAD_ARG;
+    AvctcGemmJob j;
+    j.a = *a; j.b = *b; j.M = M; j.N = N; j.K = K; j.batch = batch; j.inner_count = inner_count;
+    j.C = C; j.out_dtype = out_dtype; j.ldc = ldc; j.c_outer = c_outer; j.c_inner = c_inner;
+    j.bias = bias; j.bias_mode = bias_mode; j.alpha = alpha; j.accumulate = accumulate; j.splits = splits;
+    return avctc_gemm_launch_group(&j, 1, stream);
+}
+
+int avctc_gemm_launch_group(const AvctcGemmJob* jobs, int njobs, void* stream) {
+    if (!jobs || njobs < 1 || njobs > kMaxJobs) return AVCTC_ERR_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    GemmGroup g;
+    g.njobs = njobs;
+    int total = 0;
+    const int dbg = avctc_tuning_get("gemm_dbg", 0);
+    for (int ji = 0; ji < njobs; ++ji) {
+        const AvctcGemmJob& J = jobs[ji];
+        if (!J.C || J.M <= 0 || J.N <= 0 || J.K <= 0 || J.batch <= 0 || J.inner_count <= 0) return AVCTC_ERR_BAD_ARG;
+        if (J.out_dtype != AVCTC_F32 && J.out_dtype != AVCTC_BF16) return AVCTC_ERR_BAD_ARG;
+        if (J.accumulate && J.out_dtype != AVCTC_F32) return AVCTC_ERR_BAD_ARG;
+        if (J.bias_mode < 0 || J.bias_mode > 2 || (J.bias_mode && !J.bias)) return AVCTC_ERR_BAD_ARG;
+        GemmParams& p = g.p[ji];
+        const avctc_gemm_operand* ops[2] = {&J.a, &J.b};
+        OperandSpec* specs[2] = {&p.a, &p.b};
+        for (int i = 0; i < 2; ++i) {
+            const avctc_gemm_operand* o = ops[i];
+            if (!o->ptr) return AVCTC_ERR_BAD_ARG;
+            // K-major: tensor is rows x K -> TMA dims {K, rows, z}, box {64 k, 128 rows}
+            // MN-major: tensor is K x rows -> TMA dims {rows, K, z}, box {64 rows, 64 k}
+            const int rc = o->mn_major
+                ? avctc_tensor_map(&g.maps[2 * ji + i], o->ptr, o->rows, o->kdim, o->zdim, o->ld, o->zstride, 64, kBK)
+                : avctc_tensor_map(&g.maps[2 * ji + i], o->ptr, o->kdim, o->rows, o->zdim, o->ld, o->zstride, kBK, kBM);
+            if (rc) return rc;
+            specs[i]->k_outer = o->k_outer; specs[i]->k_inner = o->k_inner;
+            specs[i]->r_outer = o->r_outer; specs[i]->r_inner = o->r_inner;
+            specs[i]->z_outer = o->z_outer; specs[i]->z_inner = o->z_inner;
+            specs[i]->mn_major = o->mn_major ? 1 : 0;
+        }
+        p.M = J.M; p.N = J.N; p.K = J.K; p.batch = J.batch; p.inner_count = J.inner_count;
+        p.C = J.C; p.ldc = J.ldc; p.c_outer = J.c_outer; p.c_inner = J.c_inner; p.out_dtype = J.out_dtype;
+        p.bias = J.bias; p.bias_mode = J.bias_mode; p.alpha = J.alpha; p.accumulate = J.accumulate;
+        int splits = J.splits;
+        const int total_kb = (J.K + kBK - 1) / kBK;
         const bool prezeroed = splits < 0;      // negative: |splits|-way split-K into a C the caller already zeroed
         if (prezeroed) splits = -splits;
         if (splits < 1) splits = 1;
@@ -413,19 +428,24 @@ int avctc_gemm_launch(const avctc_gemm_operand* a, const avctc_gemm_operand* b, 
         const int kb_per = (total_kb + splits - 1) / splits;
         splits = (total_kb + kb_per - 1) / kb_per;            // every split owns at least one k-block
         if (splits > 1) {
-            if (out_dtype != AVCTC_F32 || accumulate || batch != 1) return AVCTC_ERR_BAD_ARG;
-            if (!prezeroed) AVCTC_CUDA_RETURN(cudaMemset2DAsync(C, sizeof(float) * (size_t)ldc, 0, sizeof(float) * (size_t)N, (size_t)M,
-                                                reinterpret_cast<cudaStream_t>(stream)));
+            if (J.out_dtype != AVCTC_F32 || J.accumulate || J.batch != 1) return AVCTC_ERR_BAD_ARG;
+            if (!prezeroed)
+                AVCTC_CUDA_RETURN(cudaMemset2DAsync(J.C, sizeof(float) * (size_t)J.ldc, 0, sizeof(float) * (size_t)J.N,
+                                                    (size_t)J.M, st));
         }
         p.splits = splits;
-        p.dbg = avctc_tuning_get("gemm_dbg", 0);
+        p.dbg = dbg;
+        g.gx[ji] = (J.M + kBM - 1) / kBM;
+        g.gy[ji] = (J.N + kBN - 1) / kBN;
+        total += g.gx[ji] * g.gy[ji] * J.batch * splits;
+        g.cta_end[ji] = total;
     }
+    for (int ji = njobs; ji < kMaxJobs; ++ji) { g.cta_end[ji] = total; g.gx[ji] = g.gy[ji] = 1; }
     const size_t smem = 2 * kStages * kTileBytes + (2 * kStages + 1) * 8 + 32 + kBN * sizeof(float) + 1024;
     static bool configured = false;
     if (!configured) {
         AVCTC_CUDA_RETURN(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid((M + kBM - 1) / kBM, (N + kBN - 1) / kBN, batch * p.splits);
-    return (int)avctc_launch_pdl(gemm_bf16_kernel, grid, dim3(kGemmThreads), smem, reinterpret_cast<cudaStream_t>(stream), ma, mb, p);
+    return (int)avctc_launch_pdl(gemm_bf16_kernel, dim3(total), dim3(kGemmThreads), smem, st, g);
 }

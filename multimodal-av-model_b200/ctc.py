@@ -56,31 +56,31 @@ class _CTCLossFn(torch.autograd.Function):
         ws_bytes = int(L.avctc_ctc_workspace_bytes(T, B, lmax)) if need_grad else 0
         if need_grad and ws_bytes == 0:
             raise RuntimeError("CTC: target length not supported by the sm_100a kernels")
-        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if need_grad else None
         st = _lib.stream_ptr(dev)
         red = _lib.REDUCTION[reduction]
         grad = None
+        out = torch.empty(B if red == 0 else 1, dtype=torch.float32, device=dev)
+        off_ptr = offsets.data_ptr() if offsets is not None else None
         with torch.cuda.device(dev):
-            _lib.check(L.avctc_ctc_forward(
-                log_probs.data_ptr(), _lib.dtype_enum(log_probs), log_probs.stride(0), log_probs.stride(1),
-                T, B, V, targets.data_ptr(), tstride, offsets.data_ptr() if offsets is not None else None,
-                input_lengths.data_ptr(), target_lengths.data_ptr(), lmax, int(blank), int(need_grad),
-                nll.data_ptr(), ws.data_ptr() if need_grad else None, ws_bytes, st), "avctc_ctc_forward")
-            out = torch.empty(B if red == 0 else 1, dtype=torch.float32, device=dev)
-            _lib.check(L.avctc_ctc_reduce(nll.data_ptr(), target_lengths.data_ptr(), B, red, int(zero_infinity),
-                                          out.data_ptr(), st), "avctc_ctc_reduce")
             if need_grad:
                 # The gradient pass goes out NOW, directly behind the scan, with a unit grad_out: launched there it
                 # starts on each utterance as soon as that utterance's alpha/beta rows are complete, under the scans of
                 # the longer ones (csrc/ctc_loss.cu, "early" route).  backward() then only applies the incoming factor.
                 # The lattice workspace dies with this call instead of living until backward.
                 grad = torch.empty((T, B, V), dtype=log_probs.dtype, device=dev)
-                _lib.check(L.avctc_ctc_backward(
+                _lib.check(L.avctc_ctc_forward_backward(
                     log_probs.data_ptr(), _lib.dtype_enum(log_probs), log_probs.stride(0), log_probs.stride(1),
-                    T, B, V, targets.data_ptr(), tstride, offsets.data_ptr() if offsets is not None else None,
-                    input_lengths.data_ptr(), target_lengths.data_ptr(), lmax, int(blank), red, int(zero_infinity),
-                    nll.data_ptr(), _unit(dev).data_ptr(), 0, grad.data_ptr(), ws.data_ptr(), ws_bytes, st),
-                    "avctc_ctc_backward")
+                    T, B, V, targets.data_ptr(), tstride, off_ptr, input_lengths.data_ptr(), target_lengths.data_ptr(),
+                    lmax, int(blank), red, int(zero_infinity), nll.data_ptr(), out.data_ptr(), _unit(dev).data_ptr(), 0,
+                    grad.data_ptr(), ws.data_ptr(), ws_bytes, st), "avctc_ctc_forward_backward")
+            else:
+                _lib.check(L.avctc_ctc_forward(
+                    log_probs.data_ptr(), _lib.dtype_enum(log_probs), log_probs.stride(0), log_probs.stride(1),
+                    T, B, V, targets.data_ptr(), tstride, off_ptr, input_lengths.data_ptr(), target_lengths.data_ptr(),
+                    lmax, int(blank), 0, nll.data_ptr(), None, 0, st), "avctc_ctc_forward")
+                _lib.check(L.avctc_ctc_reduce(nll.data_ptr(), target_lengths.data_ptr(), B, red, int(zero_infinity),
+                                              out.data_ptr(), st), "avctc_ctc_reduce")
         ctx.grad = grad
         ctx.applied = None          # the factor already multiplied into ctx.grad (None = 1)
         loss = out if red == 0 else out.reshape(())

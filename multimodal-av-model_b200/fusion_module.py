@@ -12,8 +12,10 @@ What runs where:
   * visual_proj, audio_proj, the MultiheadAttention in/out projections, Q.K^T, P.V, fusion_proj
     (fusion_module.py:57-63) forward AND backward: avctc_gemm_bf16 = tcgen05.mma + TMEM + TMA, bf16 operands,
     fp32 accumulation, transposed operands read in place (no transpose copies); softmax in fp32
-  * temporal_model (2-layer BiLSTM, fusion_module.py:64): torch.nn.LSTM / cuDNN, as SURVEY.md §7 scopes it
-    (row N1 of §8f is the follow-up)
+  * the attention core (scores -> softmax -> P.V and its backward): ONE tcgen05 kernel per direction, scores in tensor
+    memory only (csrc/attention.cu; T <= 192, head_dim 128 — other shapes run GEMM + softmax + GEMM)
+  * temporal_model (2-layer BiLSTM, fusion_module.py:64): persistent sm_100a kernels (csrc/lstm.cu) for hidden 256/512;
+    other shapes use torch.nn.LSTM / cuDNN
 `cross_attn_visual` exists but is never used, exactly like the reference (its parameters get no gradient).
 """
 from __future__ import annotations
@@ -224,12 +226,18 @@ class _FusionCoreFnPy(torch.autograd.Function):
         return (d_visual, d_audio, None, None, g_wvp, g_bvp, g_wap, g_bap, g_win, g_bin, g_wo, g_bo, g_wf, g_bf)
 
 
+def _weights_key(params):
+    return tuple((p.data_ptr(), p._version) for p in params)
+
+
 class _FusionCoreFn(torch.autograd.Function):
     """Same computation through avctc_fusion_forward / avctc_fusion_backward: ONE host call enqueues every kernel of the
-    step (weight casts, resample, 6 projection GEMMs, Q.K^T, softmax, P.V forward; 21 GEMMs + glue backward)."""
+    step (resample, grouped projection GEMMs, the fused tcgen05 attention kernel forward; grouped dgrad/wgrad GEMMs, the
+    fused attention backward, bias column sums backward).  `cache` is the module's dict holding the persistent bf16
+    copies of the five weight matrices and the (data_ptr, version) key they were made from."""
 
     @staticmethod
-    def forward(ctx, visual, audio, mask, num_heads, w_vp, b_vp, w_ap, b_ap, w_in, b_in, w_o, b_o, w_f, b_f):
+    def forward(ctx, visual, audio, mask, num_heads, cache, w_vp, b_vp, w_ap, b_ap, w_in, b_in, w_o, b_o, w_f, b_f):
         _lib.require_cuda(visual, "visual_feat")
         _lib.require_cuda(audio, "audio_feat")
         if mask is None:
@@ -248,29 +256,46 @@ class _FusionCoreFn(torch.autograd.Function):
         mask_c = mask.to(device=dev, dtype=torch.long).contiguous()
         xv = _bf16(visual.detach().reshape(B * T, Dv)).contiguous()
         ws = [_f32c(t) for t in (w_vp, b_vp, w_ap, b_ap, w_in, b_in, w_o, b_o, w_f, b_f)]
+        mats = (w_vp, w_ap, w_in, w_o, w_f)
         saved_bytes = _ws_bytes("avctc_fusion_workspace_bytes", B, T, Ta, Dv, Da, E, H, 0)
         scratch_bytes = _ws_bytes("avctc_fusion_workspace_bytes", B, T, Ta, Dv, Da, E, H, 1)
+        w_bytes = _ws_bytes("avctc_fusion_workspace_bytes", B, T, Ta, Dv, Da, E, H, 3)
         if saved_bytes == 0:
             raise RuntimeError("fusion dims not supported by the fused path")
+        # bf16 weight copies: one persistent buffer per module and device, re-cast only when a parameter changed
+        key = _weights_key(mats)
+        wbuf = cache.get("buf")
+        refresh = wbuf is None or wbuf.device != dev or wbuf.numel() != w_bytes or cache.get("key") != key
+        if wbuf is None or wbuf.device != dev or wbuf.numel() != w_bytes:
+            wbuf = cache["buf"] = torch.empty(w_bytes, dtype=torch.uint8, device=dev)
+        cache["key"] = key
         saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev)
         scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
-        out = torch.empty((B, T, E), dtype=torch.float32, device=dev)
+        # nn.Linear under autocast returns the autocast dtype; plain fp32 modules return fp32
+        out_dtype = _BF16 if (visual.dtype == _BF16 or torch.is_autocast_enabled()) else torch.float32
+        out = torch.empty((B, T, E), dtype=out_dtype, device=dev)
         mask_out = torch.empty((B, T), dtype=torch.long, device=dev)
         input_lengths = torch.empty(B, dtype=torch.long, device=dev)
         with torch.cuda.device(dev):
             _lib.check(L.avctc_fusion_forward(xv.data_ptr(), audio_c.data_ptr(), _lib.dtype_enum(audio_c), mask_c.data_ptr(),
                                               *[t.data_ptr() for t in ws], B, T, Ta, Dv, Da, E, H, out.data_ptr(),
-                                              mask_out.data_ptr(), input_lengths.data_ptr(), saved.data_ptr(), saved_bytes,
+                                              _lib.dtype_enum(out), mask_out.data_ptr(), input_lengths.data_ptr(),
+                                              wbuf.data_ptr(), w_bytes, int(refresh), saved.data_ptr(), saved_bytes,
                                               scratch.data_ptr(), scratch_bytes, st), "avctc_fusion_forward")
         ctx.save_for_backward(xv, saved)
-        ctx.dims = (B, T, Ta, Dv, Da, E, H, saved_bytes, audio.dtype, visual.dtype)
+        ctx.dims = (B, T, Ta, Dv, Da, E, H, saved_bytes, w_bytes, audio.dtype, visual.dtype)
+        ctx.weights = (mats, key, wbuf)
         ctx.mark_non_differentiable(mask_out, input_lengths)
         return out, mask_out, input_lengths
 
     @staticmethod
     def backward(ctx, df, _dm, _dl):
         xv, saved = ctx.saved_tensors
-        B, T, Ta, Dv, Da, E, H, saved_bytes, audio_dtype, visual_dtype = ctx.dims
+        B, T, Ta, Dv, Da, E, H, saved_bytes, w_bytes, audio_dtype, visual_dtype = ctx.dims
+        mats, key, wbuf = ctx.weights
+        if _weights_key(mats) != key:        # what autograd's saved-tensor version check says for nn.Linear's weight
+            raise RuntimeError("one of the variables needed for gradient computation has been modified by an inplace "
+                               "operation: a CrossAttentionFusion weight changed between forward and backward")
         dev = df.device
         L = _lib.lib()
         dfc = df.detach()
@@ -297,13 +322,13 @@ class _FusionCoreFn(torch.autograd.Function):
                                                d_visual.data_ptr() if d_visual is not None else None,
                                                d_audio.data_ptr() if d_audio is not None else None,
                                                _lib.dtype_enum(d_audio) if d_audio is not None else 0,
-                                               saved.data_ptr(), saved_bytes, scratch.data_ptr(), scratch_bytes, 1,
-                                               _lib.stream_ptr(dev)), "avctc_fusion_backward")
+                                               wbuf.data_ptr(), w_bytes, saved.data_ptr(), saved_bytes, scratch.data_ptr(),
+                                               scratch_bytes, 1, _lib.stream_ptr(dev)), "avctc_fusion_backward")
         if d_visual is not None:
             d_visual = d_visual.to(visual_dtype)
         if d_audio is not None:
             d_audio = d_audio.to(audio_dtype)
-        return (d_visual, d_audio, None, None, *g)
+        return (d_visual, d_audio, None, None, None, *g)
 
 
 class _BiLSTMFn(torch.autograd.Function):
@@ -370,6 +395,7 @@ class CrossAttentionFusion(nn.Module):
         self.temporal_model = nn.LSTM(input_size=fused_dim, hidden_size=fused_dim, num_layers=2, batch_first=True,
                                       bidirectional=True)
         self.num_heads = num_heads
+        self._wcache = {}            # persistent bf16 copies of the weight matrices (see _FusionCoreFn)
 
     def fused_projection(self, visual_feat, audio_feat, mask):
         """Everything up to and including fusion_proj (fusion_module.py:40-63): (fused[B,T,E] fp32, mask[B,T], lengths)."""
@@ -377,12 +403,12 @@ class CrossAttentionFusion(nn.Module):
         E = self.fusion_proj.weight.shape[0]
         fused = (E % self.num_heads == 0 and (E // self.num_heads) % 64 == 0 and visual_feat.shape[-1] % 8 == 0
                  and audio_feat.shape[-1] % 8 == 0)
-        fn = _FusionCoreFn if fused else _FusionCoreFnPy
-        return fn.apply(visual_feat, audio_feat, mask, self.num_heads,
-                                   self.visual_proj.weight, self.visual_proj.bias,
-                                   self.audio_proj.weight, self.audio_proj.bias,
-                                   at.in_proj_weight, at.in_proj_bias, at.out_proj.weight, at.out_proj.bias,
-                                   self.fusion_proj.weight, self.fusion_proj.bias)
+        params = (self.visual_proj.weight, self.visual_proj.bias, self.audio_proj.weight, self.audio_proj.bias,
+                  at.in_proj_weight, at.in_proj_bias, at.out_proj.weight, at.out_proj.bias,
+                  self.fusion_proj.weight, self.fusion_proj.bias)
+        if fused:
+            return _FusionCoreFn.apply(visual_feat, audio_feat, mask, self.num_heads, self._wcache, *params)
+        return _FusionCoreFnPy.apply(visual_feat, audio_feat, mask, self.num_heads, *params)
 
     def forward(self, visual_feat, audio_feat, mask=None):
         fused, _mask_rs, input_lengths = self.fused_projection(visual_feat, audio_feat, mask)
