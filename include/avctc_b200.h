@@ -195,6 +195,22 @@ AVCTC_API int avctc_log_softmax_backward(const void* Y, const void* dY, int dtyp
                                long long ldx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * CTC head — CTCDecoder.forward, /root/reference/model/decoder.py:24-25: log_softmax(x . W^T + b) as ONE kernel
+ * (csrc/ctc_head.cu): a thread-block cluster owns 128 rows x all V classes, the fp32 logits stay in tensor memory and
+ * the per-row softmax statistics are exchanged through distributed shared memory, so the log-probs are the only
+ * [M,V] tensor that touches HBM.  passes = 2 additionally applies the second F.log_softmax of evaluate()
+ * (/root/reference/model/trainer.py:212,221) in the same kernel.
+ * x: bf16 [M,K]; w: bf16 [V,K] (nn.Linear weight); bias: fp32 [V]; log_probs: fp32 [M,V].  V <= 1024, K % 8 == 0.
+ * backward: dlog_probs fp32 [M,V] (+ the forward's log_probs) -> g_w fp32 [V,K], g_b fp32 [V] and, if non-NULL,
+ * dx bf16 [M,K]; dz is caller-owned bf16 scratch of M * round_up(V, 8) elements.
+ * ---------------------------------------------------------------------------------------------- */
+AVCTC_API int avctc_ctc_head_forward(const void* x_bf16, const void* w_bf16, const float* bias, int M, int V, int K,
+                           float* log_probs, int passes, void* stream);
+AVCTC_API int avctc_ctc_head_backward(const float* log_probs, const float* dlog_probs, const void* x_bf16,
+                            const void* w_bf16, int M, int V, int K, void* dz_bf16, float* g_w, float* g_b,
+                            void* dx_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Attention core (tcgen05 + TMEM, scores never leave the SM) — replaces, inside nn.MultiheadAttention
  *   /root/reference/model/fusion_module.py:61 -> torch/nn/functional.py:6630-6652,
  * bmm(q / sqrt(hd), k^T) -> softmax over all T keys (no mask) -> bmm(P, v), and its autograd.

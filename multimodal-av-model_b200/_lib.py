@@ -44,6 +44,8 @@ SIGNATURES = {
     "avctc_colsum": (_i, [_vp, _i, ctypes.c_longlong, _i, ctypes.c_longlong, _vp, _i, _vp]),
     "avctc_log_softmax_forward": (_i, [_vp, _i, _vp, _i, ctypes.c_longlong, _i, _vp]),
     "avctc_log_softmax_backward": (_i, [_vp, _vp, _i, _vp, ctypes.c_longlong, _i, ctypes.c_longlong, _vp]),
+    "avctc_ctc_head_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "avctc_ctc_head_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "avctc_attention_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "avctc_attention_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "avctc_fusion_workspace_bytes": (_sz, [_i] * 8),
@@ -76,7 +78,9 @@ KERNELS = {"avctc_ctc_forward": 2, "avctc_ctc_reduce": 1, "avctc_ctc_backward": 
            "avctc_gemm_bf16": 1, "avctc_resample_forward": 2, "avctc_resample_backward": 1, "avctc_softmax_forward": 1,
            "avctc_softmax_backward": 1, "avctc_colsum": 1, "avctc_log_softmax_forward": 1,
            "avctc_log_softmax_backward": 1, "avctc_infonce_forward": 4, "avctc_infonce_backward": 2,
-           "avctc_attention_forward": 1, "avctc_attention_backward": 1, "avctc_fusion_forward": 7, "avctc_fusion_backward": 8,
+           "avctc_ctc_head_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "avctc_ctc_head_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "avctc_ctc_head_forward": 1, "avctc_ctc_head_backward": 3, "avctc_attention_forward": 1, "avctc_attention_backward": 1, "avctc_fusion_forward": 7, "avctc_fusion_backward": 8,
            "avctc_bilstm_forward": 7, "avctc_bilstm_backward": 20}
 launch_count = 0
 

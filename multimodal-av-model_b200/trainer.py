@@ -362,7 +362,10 @@ class MultimodalTrainer:
                         t_enc = aud.shape[1]
                         mask_ds = F.interpolate(d["masks"][s].unsqueeze(1).float(), size=t_enc, mode="nearest").squeeze(1).long()
                         fused, il = self.fusion_module(vis, aud, mask_ds)
-                        lp = _log_softmax_again(self.decoder1(fused))
+                        if hasattr(self.decoder1, "log_probs"):       # both normalisations inside the head kernel
+                            lp = self.decoder1.log_probs(fused, passes=2)
+                        else:
+                            lp = _log_softmax_again(self.decoder1(fused))
                         losses.append(self.ctc_loss(lp.transpose(0, 1), d["texts"][s], il, d["lens"][s]))
                         lps.append(lp)
                 total_loss += (losses[0].item() + losses[1].item()) / 2

@@ -5,7 +5,7 @@ import bench
 from torch.profiler import profile, ProfilerActivity
 dev = torch.device("cuda:0")
 what = sys.argv[1] if len(sys.argv) > 1 else "hot"
-tr = bench.build_models(dev)
+tr = bench.build_models(dev, encoders=(what != "hot"))
 from multimodal_av_model_b200.synthetic import make_features, make_batch
 f = make_features(pairs=8, t_v=150, t_enc=249, seed=1234, dtype=torch.bfloat16)
 fd = {k: [t.to(dev) for t in v] for k, v in f.items()}
