@@ -53,16 +53,16 @@ class _CTCHeadFn(torch.autograd.Function):
                     _lib.check(L.avctc_log_softmax_forward(logits.data_ptr(), _lib.F32, lp.data_ptr(), _lib.F32, M, V,
                                                            _lib.stream_ptr(dev)), "avctc_log_softmax_forward")
                     logits = lp
-        if passes != 1 and any(ctx.needs_input_grad[:3]):
-            raise RuntimeError("the doubly normalised head (passes=2) is the evaluation path: no backward")
         ctx.save_for_backward(xb, wb, lp)
-        ctx.shp = (shp, x.dtype, fused)
+        ctx.shp = (shp, x.dtype, fused, int(passes))
         return lp.view(*shp[:-1], V)
 
     @staticmethod
     def backward(ctx, dlp):
         xb, wb, lp = ctx.saved_tensors
-        shp, xdtype, fused = ctx.shp
+        shp, xdtype, fused, passes = ctx.shp
+        if passes != 1:
+            raise RuntimeError("the doubly normalised head (passes=2) is the evaluation path: no backward")
         dev = dlp.device
         M, D = xb.shape
         V = wb.shape[0]
