@@ -114,6 +114,19 @@ class VisualEncoder(nn.Module):
         return F.max_pool2d(y, pool.kernel_size[1:], pool.stride[1:], pool.padding[1:])
 
     def forward(self, x):
+        # main.py:100-103 freezes every parameter of this encoder: for a fixed clip shape its forward is a fixed kernel
+        # sequence whose output needs no gradient -> replayed from a CUDA graph (graphed.py), ~170 launches -> 1
+        if x.is_cuda and x.shape[1] == 1:
+            self._channels_last()
+        seg = getattr(self, "_graph_seg", None)
+        if seg is None:
+            from .graphed import GraphedSegment
+            seg = self._graph_seg = GraphedSegment(self._forward_impl, list(self.parameters()), list(self.buffers()))
+        if seg.usable(x):
+            return seg(x)
+        return self._forward_impl(x)
+
+    def _forward_impl(self, x):
         b, t = x.shape[0], x.shape[2]
         conv = self.frontend3D[0]
         if (x.is_cuda and x.shape[1] == 1 and conv.stride[0] == 1 and conv.dilation == (1, 1, 1)
@@ -201,6 +214,15 @@ class AudioEncoder(nn.Module):
             _install_feature_cache(fe)
         fe(x)
 
+    def _layer_segment(self, layer):
+        seg = getattr(layer, "_avctc_graph_seg", None)
+        if seg is None:
+            from .graphed import GraphedSegment
+            seg = GraphedSegment(lambda h, m: layer(h, attention_mask=m, output_attentions=False)[0],
+                                 list(layer.parameters()), max_entries=4)
+            object.__setattr__(layer, "_avctc_graph_seg", seg)
+        return seg
+
     def _forward_sync_free(self, x, attention_mask, host_lengths):
         from transformers.models.wav2vec2.modeling_wav2vec2 import _compute_mask_indices
         m = self.model
@@ -252,7 +274,11 @@ class AudioEncoder(nn.Module):
             draw = torch.rand([])                                                 # LayerDrop: host draw, as upstream
             skip = enc.training and bool(draw < cfg.layerdrop)
             if not skip:
-                hidden = layer(hidden, attention_mask=mask4d, output_attentions=False)[0]
+                seg = self._layer_segment(layer)
+                if seg.usable(hidden, mask4d):      # frozen layer, no gradient flows through it yet (layers 0-5 in
+                    hidden = seg(hidden, mask4d)    # training, every frozen layer under no_grad): one graph launch
+                else:
+                    hidden = layer(hidden, attention_mask=mask4d, output_attentions=False)[0]
         if stable:
             hidden = enc.layer_norm(hidden)
         all_hidden = all_hidden + (hidden,)
@@ -272,8 +298,10 @@ def _install_feature_cache(fe):
     unchanged input tensor is reused instead of recomputed: identical values, one conv stack pass per step instead of
     two.  Installed as an instance-level forward wrapper, so module structure and state_dict keys do not change."""
     import weakref
+    from .graphed import GraphedSegment
     inner = fe.forward
     state = {"ref": None, "key": None, "out": None}
+    seg = GraphedSegment(inner, list(fe.parameters()))      # seven conv + norm + GELU layers: one graph launch
 
     def cached_forward(input_values):
         frozen = not any(p.requires_grad for p in fe.parameters()) and not getattr(fe, "_requires_grad", False)
@@ -287,7 +315,7 @@ def _install_feature_cache(fe):
         same = state["ref"] is not None and state["ref"]() is input_values and state["key"] == key
         if not same:
             with torch.no_grad():
-                state["out"] = inner(input_values)
+                state["out"] = seg(input_values) if seg.usable(input_values) else inner(input_values)
             state["ref"], state["key"] = weakref.ref(input_values), key
         return state["out"]
 

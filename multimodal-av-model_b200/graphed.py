@@ -1,0 +1,89 @@
+"""CUDA-graph replay of the frozen, gradient-free segments of the producer encoders.
+
+The full training step is bound by the HOST's enqueue time, not by the GPU (~1500 small PyTorch launches
+per step in the two encoders, which main.py:100-106 freezes except wav2vec2 layers 6-9).  A frozen segment whose output
+needs no gradient is a fixed kernel sequence for a fixed input shape: it is captured once per (shape, dtype, autocast,
+train/eval, parameter versions) and replayed with ONE launch afterwards — same kernels, same arithmetic, same in-place
+side effects (BatchNorm running statistics advance on every replay exactly as in eager mode; dropout inside a captured
+segment draws from the CUDA generator through PyTorch's graph-safe Philox offsets).
+
+No new kernels and no change of results: this is scheduling only.  `_lib.set_py_tuning("enc_graphs", 0)` turns it off.
+"""
+from __future__ import annotations
+
+import collections
+
+import torch
+
+from . import _lib
+
+_lib._PY_TUNING.setdefault("enc_graphs", 1)
+
+
+def _sig(t):
+    return None if t is None else (tuple(t.shape), t.dtype, tuple(t.stride()))
+
+
+class GraphedSegment:
+    """fn(*tensors) -> tensor, captured per input signature.  `params` are the parameters fn reads (all must be frozen),
+    `buffers` the buffers it updates in place (restored after the capture warm-up so warm-up runs leave no trace)."""
+
+    def __init__(self, fn, params, buffers=(), max_entries=6, warmup=2):
+        self.fn = fn
+        self.params = list(params)
+        self.buffers = list(buffers)
+        self.max_entries = max_entries
+        self.warmup = warmup
+        self.cache = collections.OrderedDict()
+        self.replays = 0
+        self.captures = 0
+
+    def usable(self, *inputs):
+        if not _lib.tuning_enabled("enc_graphs"):
+            return False
+        ts = [t for t in inputs if t is not None]
+        if not ts or not all(t.is_cuda for t in ts) or torch.cuda.is_current_stream_capturing():
+            return False
+        if torch.is_grad_enabled() and any(t.requires_grad for t in ts):
+            return False
+        return not any(p.requires_grad for p in self.params)
+
+    def __call__(self, *inputs):
+        dev = next(t for t in inputs if t is not None).device
+        key = (tuple(_sig(t) for t in inputs), torch.is_autocast_enabled(),
+               torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else None,
+               sum(p._version for p in self.params), tuple(p.data_ptr() for p in self.params[:4]))
+        ent = self.cache.get(key)
+        if ent is None:
+            ent = self._capture(inputs, dev)
+            self.cache[key] = ent
+            while len(self.cache) > self.max_entries:
+                self.cache.popitem(last=False)
+        else:
+            self.cache.move_to_end(key)
+        static_in, graph, static_out = ent
+        for s, t in zip(static_in, inputs):
+            if s is not None:
+                s.copy_(t, non_blocking=True)
+        graph.replay()
+        self.replays += 1
+        return static_out.clone()             # the next replay overwrites the static output
+
+    def _capture(self, inputs, dev):
+        static_in = [None if t is None else t.detach().clone() for t in inputs]
+        saved = [b.detach().clone() for b in self.buffers]
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.no_grad():
+            with torch.cuda.stream(side):
+                for _ in range(self.warmup):          # lazy initialisation (cuDNN heuristics, cast caches) outside the capture
+                    self.fn(*static_in)
+            cur.wait_stream(side)
+            for b, s in zip(self.buffers, saved):     # warm-up runs must not advance the running statistics
+                b.copy_(s)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self.fn(*static_in)
+        self.captures += 1
+        return static_in, graph, static_out
