@@ -104,6 +104,7 @@ class MultimodalTrainer:
         self.verbose = True
         self.beam_width = 5                       # trainer.py:230,237
         self.batch_speakers = True                # BiLSTM + CTC head over both speakers at once (hot_path_loss)
+        self.overlap_contrastive = True           # InfoNCE on a side stream, under the BiLSTM kernels (hot_path_loss)
         self.gpu_heavy_first = False              # train_step enqueue order (see there); measured slower on B200, kept as a switch
         self.prefetch_batches = True              # train_epoch: stage batch i+1 while step i runs on the GPU
         self.loss_log = None                      # pinned fp32 ring: per-step total loss of the current epoch (async D2H)
@@ -203,6 +204,15 @@ class MultimodalTrainer:
         self.loss_log[self.loss_log_count % self._LOSS_LOG_CAP].copy_(loss.detach().float(), non_blocking=True)
         self.loss_log_count += 1
 
+    def _side_stream(self, ref):
+        """Stream for work that is independent of the main chain (None on CPU tensors or when switched off)."""
+        if not ref.is_cuda or not self.overlap_contrastive or torch.cuda.is_current_stream_capturing():
+            return None
+        st = getattr(self, "_aux_stream", None)
+        if st is None or st.device != ref.device:
+            st = self._aux_stream = torch.cuda.Stream(device=ref.device)
+        return st
+
     def _ensure_projection(self, D):
         if self.projection_layer is None:           # trainer.py:105-106: created lazily, once per epoch
             self.projection_layer = nn.Linear(D, 128).to(self.device)
@@ -216,7 +226,23 @@ class MultimodalTrainer:
             t_enc = audio_feats[s].shape[1]
             mask_ds.append(F.interpolate(masks[s].unsqueeze(1).float(), size=t_enc, mode="nearest").squeeze(1).long())
             self._ensure_projection(audio_feats[s].shape[2])
-            con.append(contrastive_loss_with_mask(middle_feats[s], mask_ds[s].reshape(-1), projection_layer=self.projection_layer))
+        # The two contrastive losses depend on nothing the fusion -> BiLSTM -> head -> CTC chain produces, and that chain
+        # is dominated by the persistent BiLSTM kernels, which occupy 64 of the 148 SMs: the InfoNCE kernels (forward
+        # here, backward through autograd, which replays an op on the stream its forward ran on) go to a side stream
+        # and run on the idle SMs underneath it.  Same kernels, same values.
+        side = self._side_stream(middle_feats[0])
+        if side is not None:
+            main = torch.cuda.current_stream(middle_feats[0].device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for s in range(2):
+                    middle_feats[s].record_stream(side); mask_ds[s].record_stream(side)
+                    con.append(contrastive_loss_with_mask(middle_feats[s], mask_ds[s].reshape(-1),
+                                                          projection_layer=self.projection_layer))
+        else:
+            for s in range(2):
+                con.append(contrastive_loss_with_mask(middle_feats[s], mask_ds[s].reshape(-1),
+                                                      projection_layer=self.projection_layer))
         if self.batch_speakers and hasattr(self.fusion_module, "forward_pair"):
             # the recurrent model and the CTC head see both speakers as one batch of 2B sequences (same values, half
             # the sequential steps); everything whose result depends on the batch it is computed in stays per speaker
@@ -234,6 +260,10 @@ class MultimodalTrainer:
         for s in range(2):
             ctc.append(self.ctc_loss(log_probs[s].transpose(0, 1), texts[s], in_lens[s], lens[s]))
         self._last_log_probs = log_probs[0]
+        if side is not None:
+            main.wait_stream(side)
+            for c in con:
+                c.record_stream(main)
         total = (ctc[0] + ctc[1]) / 2 + self.lambda_ * (con[0] + con[1]) / 2
         return total, ctc[0], ctc[1], con[0], con[1]
 

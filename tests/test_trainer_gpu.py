@@ -163,3 +163,39 @@ def test_batching_both_speakers_through_the_bilstm_changes_no_value():
         assert (a[1][n] - b[1][n]).abs().max() <= 2e-3 * scale, n
     for x, y in zip(a[2], b[2]):
         assert (x.float() - y.float()).abs().max() <= 2e-2 * (x.float().abs().max() + 1e-12)
+
+
+def test_contrastive_on_side_stream_changes_no_value():
+    """hot_path_loss runs the two InfoNCE losses on a side stream under the BiLSTM kernels (overlap_contrastive): same
+    losses and gradients as the single-stream order, over several back-to-back steps (allocator reuse across streams)."""
+    pkg = _pkg()
+    from multimodal_av_model_b200.synthetic import CharTokenizer, make_features
+    torch.manual_seed(0)
+    fus = pkg.CrossAttentionFusion(512, 1024, 512)
+    dec = pkg.CTCDecoder(1024, 800, blank_id=3)
+    tr = pkg.MultimodalTrainer(_Enc(), _Enc(), fus, dec, CharTokenizer(800), device="cuda")
+    f = make_features(pairs=4, t_v=60, t_enc=99, seed=9, n_samples=32000, dtype=torch.bfloat16)
+    out = {}
+    for mode in (False, True):
+        tr.overlap_contrastive = mode
+        runs = []
+        for rep in range(3):
+            fd = {k: [t.cuda() for t in v] for k, v in f.items()}
+            for k in ("audio", "middle"):
+                fd[k] = [t.requires_grad_() for t in fd[k]]
+            for m in (fus, dec):
+                m.zero_grad(set_to_none=True)
+            if tr.projection_layer is not None:
+                tr.projection_layer.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                parts = tr.hot_path_loss(fd["visual"], fd["audio"], fd["middle"], fd["masks"], fd["texts"], fd["lens"])
+            parts[0].backward()
+            torch.cuda.synchronize()
+            runs.append(([float(x.detach()) for x in parts], [t.grad.clone() for t in fd["middle"]],
+                         tr.projection_layer.weight.grad.clone()))
+        out[mode] = runs
+    for a, b in zip(out[False], out[True]):
+        assert np.allclose(a[0], b[0], rtol=1e-6, atol=1e-7), (a[0], b[0])
+        for x, y in zip(a[1], b[1]):
+            assert torch.equal(x, y)                                  # the InfoNCE backward is bit-reproducible
+        assert (a[2] - b[2]).abs().max() <= 1e-5 * (a[2].abs().max() + 1e-12)      # split-K atomics order only
