@@ -65,6 +65,28 @@ class _InfoNCEFn(torch.autograd.Function):
         return dy.to(ydtype), None, None, None, None
 
 
+_MAX_FUSED_DIM = 256        # the fused kernel keeps a 64-row tile of features in shared memory: feature dim <= 256
+
+
+def _wide_feature_loss(flat_feat, flat_mask):
+    """Feature dim > 256 — only reachable with projection_layer=None on the raw 1024-dim wav2vec2 features, which the
+    reference's trainer never does (trainer.py:105-109 always projects to 128).  Kept working, on the GPU, with the
+    reference's own formulation on torch CUDA ops (contrastive.py:13-44; it syncs on the boolean indexing like the
+    reference does) instead of refusing the call; the sm_100a kernel covers every dimension the path actually uses."""
+    import torch.nn.functional as F
+    _lib.require_cuda(flat_feat, "features")
+    keep = flat_mask != 3
+    z = F.normalize(flat_feat[keep].float(), dim=1)
+    m = flat_mask[keep]
+    weak, strong, neg = z[m == 1], z[m == 2], z[m == 0]
+    loss = torch.zeros((), device=flat_feat.device, requires_grad=True)
+    if len(weak) > 0 and len(strong) > 0:
+        loss = loss + WEIGHT_POS_ALIGN * (-F.log_softmax(weak @ strong.T / TEMPERATURE, dim=1)).mean()
+    if len(weak) > 0 and len(neg) > 0:
+        loss = loss + WEIGHT_NEG_SUPPRESS * (-F.log_softmax(weak @ neg.T / TEMPERATURE, dim=1)).mean()
+    return loss
+
+
 def contrastive_loss_with_mask(middle_feat, flat_mask, projection_layer=None):
     B, T_enc, D = middle_feat.shape
     flat_feat = middle_feat.reshape(B * T_enc, D)
@@ -76,6 +98,8 @@ def contrastive_loss_with_mask(middle_feat, flat_mask, projection_layer=None):
             flat_feat = LinearFn.apply(flat_feat, projection_layer.weight, projection_layer.bias)
         else:
             flat_feat = projection_layer(flat_feat)
+    if flat_feat.shape[-1] > _MAX_FUSED_DIM:
+        return _wide_feature_loss(flat_feat, flat_mask)
     loss = _InfoNCEFn.apply(flat_feat, flat_mask, TEMPERATURE, WEIGHT_POS_ALIGN, WEIGHT_NEG_SUPPRESS)
     # the reference starts from a fresh requires-grad zero (contrastive.py:28), so the result always requires grad
     return loss + torch.zeros((), device=loss.device, requires_grad=True)

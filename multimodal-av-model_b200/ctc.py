@@ -82,25 +82,24 @@ class _CTCLossFn(torch.autograd.Function):
                 _lib.check(L.avctc_ctc_reduce(nll.data_ptr(), target_lengths.data_ptr(), B, red, int(zero_infinity),
                                               out.data_ptr(), st), "avctc_ctc_reduce")
         ctx.grad = grad
-        ctx.applied = None          # the factor already multiplied into ctx.grad (None = 1)
         loss = out if red == 0 else out.reshape(())
         return loss.to(log_probs.dtype) if log_probs.dtype != torch.float32 else loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        grad = ctx.grad
+        grad, ctx.grad = ctx.grad, None
         if grad is None:
-            raise RuntimeError("CTC backward without a forward that required grad")
+            # The gradient was computed at forward time and handed to autograd by the first backward WITHOUT keeping a
+            # reference (a second owner would make AccumulateGrad clone the [T,B,V] tensor: +50 % HBM traffic).
+            raise RuntimeError("CTC loss: backward through this graph a second time is not supported (the gradient "
+                               "computed at forward time was consumed by the first backward); call the loss again")
         T, B, V = grad.shape
         dev = grad.device
         go = grad_out.detach().to(torch.float32).contiguous()
-        if ctx.applied is not None:     # a second backward through a retained graph: undo the factor applied before
-            go = go / ctx.applied
         gstride = 0 if go.numel() == 1 else 1
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().avctc_ctc_scale_grad(grad.data_ptr(), _lib.dtype_enum(grad), T, B, V, go.data_ptr(),
                                                        gstride, _lib.stream_ptr(dev)), "avctc_ctc_scale_grad")
-        ctx.applied = grad_out.detach().to(torch.float32).clone()
         return grad, None, None, None, None, None, None
 
 

@@ -91,3 +91,19 @@ def test_infonce_no_projection_kernel_only_parity():
     loss.backward()
     assert abs(loss.item() - loss_ref) <= 1e-4 * abs(loss_ref)
     assert rel(x.grad.cpu().numpy(), dmid_ref) < 1e-4
+
+
+def test_contrastive_without_projection_on_wide_features():
+    """projection_layer=None on 1024-dim features (the reference's default argument; its trainer never uses it): the call
+    works and equals the reference formulation (round-1 advisor finding: it used to raise UNSUPPORTED)."""
+    import multimodal_av_model_b200 as pkg
+    from oracle import torch_port as tp
+    torch.manual_seed(0)
+    feat = torch.randn(2, 40, 1024)
+    mask = torch.randint(0, 4, (80,))
+    ref = tp.contrastive_loss_with_mask(feat.clone().requires_grad_(), mask)
+    x = feat.cuda().requires_grad_()
+    out = pkg.contrastive_loss_with_mask(x, mask.cuda())
+    out.backward()
+    assert abs(out.item() - ref.item()) < 1e-4 * abs(ref.item())
+    assert x.grad is not None and torch.isfinite(x.grad).all()
