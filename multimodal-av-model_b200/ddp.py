@@ -12,8 +12,11 @@ every earlier bucket has been launched — the collective order is the bucket in
 all_reduce(SUM) goes out on a side stream under the rest of backward.  finish() launches what is left, waits, and
 scales all buckets with ONE foreach multiply by 1 / (number of ranks whose step succeeded) — that count travels
 in a spare slot of the last bucket, so a rank whose forward/backward raised contributes zeros and every rank
-still applies the same update (see finish()).  Parameters that received no gradient in a step (e.g.
-cross_attn_visual, never used by the reference) end the step with `.grad = None`, as in a single process.
+still applies the same update (see finish()).  Parameters that are outside every step's graph by construction
+(cross_attn_visual, never used by the reference) are declared `never_used`: no slot, `.grad` stays None, as in a
+single process.  A parameter that happens to get no gradient in ONE step (wav2vec2's LayerDrop skips a trainable layer
+with probability 0.1 per call) contributes zeros to the sum, as under torch's DistributedDataParallel; its bucket, and
+the ones behind it in launch order, then leave from finish() instead of from the hooks.
 """
 from __future__ import annotations
 
@@ -70,17 +73,19 @@ def broadcast_buffers(module, src=0, group=None):
 
 
 class GradBucketReducer:
-    def __init__(self, params, bucket_bytes=24 << 20, group=None, overlap=True):
+    def __init__(self, params, bucket_bytes=None, group=None, overlap=True, never_used=()):
+        if bucket_bytes is None:
+            bucket_bytes = int(os.environ.get("AVCTC_BUCKET_MB", "24")) << 20
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.params = [p for p in params if p.requires_grad]
+        # `never_used`: parameters that are outside every step's graph by construction (cross_attn_visual, which the
+        # reference builds and never calls, fusion_module.py:14,61): they get no slot, their .grad stays None
+        skip = {id(p) for p in never_used}
+        self.params = [p for p in params if p.requires_grad and id(p) not in skip]
         self.overlap = overlap and self.world > 1
         self.buckets = []          # dict(flat, items=[(param, offset, numel)], ready=set(), work)
         self._slot = {}
         self._next = 0             # buckets [0, _next) have been launched this step
-        self._inactive = None      # parameters that got no gradient in the first finished step (outside the graph, e.g.
-                                   # cross_attn_visual): counted as ready from the start of later steps
-        self._late = None          # an "inactive" parameter received a gradient after its bucket had left
         self._handles = []
         self.stream = None
         if not self.params:
@@ -126,11 +131,6 @@ class GradBucketReducer:
                 b["work"] = None
             b["ready"] = set()
         self._next = 0
-        self._late = None
-
-    def _arm(self):
-        for b in self.buckets:
-            b["ready"] = {p for p, _, _ in b["items"] if p in self._inactive} if self._inactive else set()
 
     def zero_grad(self):
         """Start of a step (instead of optimizer.zero_grad()): one fill per bucket, and every parameter's .grad is
@@ -143,7 +143,6 @@ class GradBucketReducer:
                 g = p.grad
                 if g is None or g.data_ptr() != flat.data_ptr() + 4 * off:
                     p.grad = flat[off:off + n].view_as(p)
-        self._arm()
 
     def _launch(self, b):
         if self.stream is not None:
@@ -160,12 +159,7 @@ class GradBucketReducer:
             self._next += 1
 
     def _on_grad(self, p):
-        bi = self._slot[p]
-        b = self.buckets[bi]
-        if self._inactive and p in self._inactive:
-            self._inactive.discard(p)
-            if bi < self._next:
-                self._late = p
+        b = self.buckets[self._slot[p]]
         b["ready"].add(p)
         if self.overlap and self.world > 1:
             self._launch_ready()
@@ -192,19 +186,9 @@ class GradBucketReducer:
             torch.cuda.current_stream().wait_stream(self.stream)
         torch.reciprocal(self._ok.clamp(min=1.0).reshape(()), out=self._scale)
         torch._foreach_mul_([b["flat"] for b in self.buckets], self._scale)
-        if ok and self._inactive is None:
-            self._inactive = {p for b in self.buckets for p, _, _ in b["items"] if p not in b["ready"]}
-        elif ok:
-            self._inactive |= {p for b in self.buckets for p, _, _ in b["items"] if p not in b["ready"]}
-        for p in (self._inactive or ()):        # parameters outside the graph keep .grad = None (Adam skips them)
-            p.grad = None
-        late, self._late = self._late, None
         for b in self.buckets:
             b["ready"] = set()
         self._next = 0
-        if late is not None:
-            raise RuntimeError("a parameter that had received no gradient in earlier steps received one after its bucket "
-                               "had been reduced; this step's gradients are incomplete (the next step is correct)")
 
     def grad_bytes(self):
         return sum(b["flat"].numel() * 4 for b in self.buckets)

@@ -397,6 +397,11 @@ class CrossAttentionFusion(nn.Module):
         self.num_heads = num_heads
         self._wcache = {}            # persistent bf16 copies of the weight matrices (see _FusionCoreFn)
 
+    def never_used_parameters(self):
+        """cross_attn_visual is constructed (fusion_module.py:14) and never called (:61 uses cross_attn_audio only): its
+        parameters are outside every graph.  The data-parallel reducer leaves them out of its buckets."""
+        return list(self.cross_attn_visual.parameters())
+
     def fused_projection(self, visual_feat, audio_feat, mask):
         """Everything up to and including fusion_proj (fusion_module.py:40-63): (fused[B,T,E] fp32, mask[B,T], lengths)."""
         at = self.cross_attn_audio

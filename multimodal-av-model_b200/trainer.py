@@ -115,7 +115,8 @@ class MultimodalTrainer:
         if self.world_size > 1:
             for m in (self.visual_encoder, self.audio_encoder, self.fusion_module, self.decoder1):
                 broadcast_module(m)
-            self._reducer = GradBucketReducer(self.parameters)
+            never = list(getattr(self.fusion_module, "never_used_parameters", lambda: [])())
+            self._reducer = GradBucketReducer(self.parameters, never_used=never)
 
     # ------------------------------------------------------------------------------------------ helpers
     def crop_or_pad_feat(self, feat, target_len):

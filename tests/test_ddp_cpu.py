@@ -24,7 +24,7 @@ def _worker(rank, world, port, overlap, q):
                 p.add_(1.0)                                 # diverge on purpose; broadcast must repair it
     ddp.broadcast_module(model)
     params = list(model.parameters()) + list(unused.parameters())
-    red = ddp.GradBucketReducer(params, bucket_bytes=64, overlap=overlap)
+    red = ddp.GradBucketReducer(params, bucket_bytes=64, overlap=overlap, never_used=list(unused.parameters()))
     g = torch.Generator().manual_seed(100)
     x_all = torch.randn(8, 6, generator=g); y_all = torch.randn(8, 3, generator=g)
     lo, hi = ddp.shard_range(8, r, w)
@@ -170,3 +170,44 @@ def test_failed_rank_is_left_out_and_every_rank_gets_the_same_gradients():
     for p in procs:
         p.join(timeout=60)
     assert all(a and b for _, a, b in res), res
+
+
+def _layerdrop_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from multimodal_av_model_b200 import ddp
+    r, _, w = ddp.init_distributed("gloo")
+    torch.manual_seed(0)
+    a, skipped, c = torch.nn.Linear(6, 6), torch.nn.Linear(6, 6), torch.nn.Linear(6, 3)
+    params = list(a.parameters()) + list(skipped.parameters()) + list(c.parameters())
+    red = ddp.GradBucketReducer(params, bucket_bytes=64)
+    g = torch.Generator().manual_seed(100)
+    x_all = torch.randn(8, 6, generator=g)
+    lo, hi = ddp.shard_range(8, r, w)
+    res = []
+    for step, use in enumerate((False, True, False, True)):      # wav2vec2 LayerDrop: a trainable layer is skipped in some steps
+        red.zero_grad()
+        h = a(x_all[lo:hi])
+        if use:
+            h = skipped(h)
+        c(h).pow(2).mean().backward()
+        red.finish()
+        gs = skipped.weight.grad
+        res.append(None if gs is None else float(gs.abs().sum()))
+    ok = res[0] == 0.0 and res[2] == 0.0 and res[1] > 0 and res[3] > 0 and abs(res[1] - res[3]) < 1e-6
+    q.put((rank, bool(ok), res))
+    dist.destroy_process_group()
+
+
+def test_parameter_without_gradient_in_some_steps():
+    """Round 2: LayerDrop leaves a trainable layer without a gradient in some steps; the reducer neither raises nor
+    desynchronises, the skipped layer's reduced gradient is zero in that step (torch DDP semantics) and right afterwards."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_layerdrop_worker, args=(r, 2, 29651, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res

@@ -1,11 +1,11 @@
 #!/bin/bash
-# 8 GPUs: 2-rank NCCL parity test, DDP step profile (exposed all-reduce), bench at N=8
+# 8 GPUs: DDP step profile (exposed all-reduce) for bucket sizes / NCCL protocols, then bench at N=8 and N=1 on the same box
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_ddp_gpu.py -q -x -s > gpurun_out/r2n8_ddp_test.log 2>&1; echo "ddp test rc=$?" | tee -a gpurun_out/r2n8_ddp_test.log
-tail -n 4 gpurun_out/r2n8_ddp_test.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29555 tools/profile_ddp.py > gpurun_out/r2n8_profile.txt 2> gpurun_out/r2n8_profile.err; echo "profile rc=$?"
-head -n 14 gpurun_out/r2n8_profile.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29556 bench.py --gpus 8 --steps 10 --warmup 4 > gpurun_out/r2n8_bench.json 2> gpurun_out/r2n8_bench.err; echo "bench8 rc=$?"
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
+AVCTC_BUCKETS=24,48,12 timeout 600 $TR --master-port 29555 tools/profile_ddp.py > gpurun_out/r2n8_profile.txt 2> gpurun_out/r2n8_profile.err; echo "profile rc=$?"
+NCCL_PROTO=Simple AVCTC_NO_PROFILE=1 AVCTC_BUCKETS=24,48 timeout 600 $TR --master-port 29557 tools/profile_ddp.py >> gpurun_out/r2n8_profile.txt 2>> gpurun_out/r2n8_profile.err; echo "profile simple rc=$?"
+grep "^world" gpurun_out/r2n8_profile.txt
+timeout 900 $TR --master-port 29556 bench.py --gpus 8 --steps 10 --warmup 4 > gpurun_out/r2n8_bench.json 2> gpurun_out/r2n8_bench.err; echo "bench8 rc=$?"
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/r2n8_bench.json'))

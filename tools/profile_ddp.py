@@ -16,36 +16,54 @@ dev = torch.device("cuda", local)
 torch.cuda.set_device(dev)
 tr = bench.build_models(dev)
 batch = {k: v.to(dev) for k, v in make_batch(pairs=bench.PAIRS_PER_GPU, seconds=bench.SECONDS, t_v=bench.T_V, seed=1234 + rank).items()}
-red = tr._reducer
-marks = []
-if red is not None:
-    orig = red.finish
-    def finish(ok=True):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()                      # behind backward's last kernel on the main stream
-        orig(ok)
-        b.record()
-        marks.append((a, b))
-    red.finish = finish
-for _ in range(4):
-    tr.train_step(batch)
-torch.cuda.synchronize(); marks.clear()
-if world > 1:
-    dist.barrier()
-t0 = time.perf_counter()
-n = 10
-for _ in range(n):
-    tr.train_step(batch)
-torch.cuda.synchronize()
-dt = (time.perf_counter() - t0) / n * 1e3
-exposed = sum(a.elapsed_time(b) for a, b in marks) / max(len(marks), 1)
-t = torch.tensor([dt, exposed], device=dev)
-if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-if rank == 0:
-    nb = len(red.buckets) if red is not None else 0
-    print(f"world {world}: {float(t[0]):.2f} ms/step (max over ranks); exposed after backward (finish(): tail buckets + wait + scale) "
-          f"{float(t[1]):.3f} ms; {nb} buckets, {red.grad_bytes() / 1e6 if red else 0:.1f} MB of gradients per step")
+from multimodal_av_model_b200.ddp import GradBucketReducer
+never = tr.fusion_module.never_used_parameters()
+
+
+def measure(bucket_mb, n=10):
+    """Step time (max over ranks) and the part of the reduction exposed behind backward, for one bucket size."""
+    if tr._reducer is not None:
+        tr._reducer.close()
+    red = tr._reducer = GradBucketReducer(tr.parameters, bucket_bytes=bucket_mb << 20, never_used=never) if world > 1 else None
+    marks = []
+    if red is not None:
+        orig = red.finish
+        def finish(ok=True):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()                      # behind backward's last kernel on the main stream
+            orig(ok)
+            b.record()
+            marks.append((a, b))
+        red.finish = finish
+    for _ in range(4):
+        tr.train_step(batch)
+    torch.cuda.synchronize(); marks.clear()
+    if world > 1:
+        dist.barrier()
+    a0, b0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(n):
+        tr.train_step(batch)
+    b0.record()
+    torch.cuda.synchronize()
+    dt = a0.elapsed_time(b0) / n
+    exposed = sum(a.elapsed_time(b) for a, b in marks) / max(len(marks), 1)
+    t = torch.tensor([dt, exposed], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        nb = len(red.buckets) if red is not None else 0
+        print(f"world {world} NCCL_PROTO={os.environ.get('NCCL_PROTO', 'default')} bucket {bucket_mb} MB: {float(t[0]):.2f} ms/step "
+              f"(CUDA events, max over ranks); exposed behind backward (finish(): tail buckets + wait + scale) {float(t[1]):.3f} ms; "
+              f"{nb} buckets, {red.grad_bytes() / 1e6 if red else 0:.1f} MB of gradients per step", flush=True)
+
+
+for mb in [int(x) for x in os.environ.get("AVCTC_BUCKETS", "24").split(",")]:
+    measure(mb)
+if os.environ.get("AVCTC_NO_PROFILE"):
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    sys.exit(0)
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     tr.train_step(batch)
