@@ -53,7 +53,8 @@ AVCTC_API const char* avctc_status_string(int status);
  * globaltimer stamps in the workspace's flag block: debug / tests), "ctc_grad_warps", "beam_fast" (1 = threshold top-k fast path), "beam_two_phase" (1 = top-k for all rows first),
  * "beam_pf" (1 = L2 prefetch of the next row), "pdl" (1 = programmatic dependent launch for the GEMM / softmax / CTC
  * kernel chains), "lstm_tag" (BiLSTM step exchange: 0 counter barrier, 1 sentinel polling in the forward pass when
- * B <= 8, 2 forward always, 3 forward and backward), "gemm_dbg" (per-CTA timestamps).  Unknown keys return
+ * B <= 8, 2 forward always, 3 forward and backward), "lstm_groups" (batch groups of the BiLSTM kernels: 0 auto, n = n
+ * groups), "gemm_dbg" (per-CTA timestamps).  Unknown keys return
  * AVCTC_ERR_BAD_ARG. */
 AVCTC_API int avctc_set_tuning(const char* key, int value);
 
@@ -260,13 +261,14 @@ AVCTC_API int avctc_fusion_backward(const void* df, int df_dtype, const void* vi
 /* ------------------------------------------------------------------------------------------------
  * temporal_model — nn.LSTM(E, E, num_layers=2, batch_first=True, bidirectional=True), zero initial state,
  *   /root/reference/model/fusion_module.py:21-27, called at :64 over all padded frames
- * as persistent cooperative kernels (csrc/lstm.cu).  H in {256, 512}, B <= 32, In % 8 == 0.
+ * as persistent cooperative kernels (csrc/lstm.cu).  H in {256, 512}, B <= 64 (H = 512) / 128 (H = 256), In % 8 == 0;
+ * calls with more than 8 sequences run as independent batch groups side by side in one launch.
  * x: bf16 [B,T,In]; params / grads: HOST arrays of 16 DEVICE fp32 pointers in nn.LSTM's flat parameter order
  * (weight_ih_l0 [4H,In], weight_hh_l0 [4H,H], bias_ih_l0 [4H], bias_hh_l0 [4H], the same four "_reverse", then the
  * four + four of layer 1 with In = 2H); gate order i,f,g,o.  y: bf16 [B,T,2H].  `saved` (which=0) carries weights in
  * bf16, gates and cell states from forward to backward (written only when need_grad); scratch which=1 forward,
  * which=2 backward.  backward: dy bf16 [B,T,2H] -> 16 parameter gradients and, if non-NULL, dx bf16 [B,T,In].
- * The kernels use a cooperative launch (2*H/16 CTAs must be co-resident).
+ * The kernels use a cooperative launch (groups * 2*H/16 <= 128 CTAs must be co-resident).
  * ---------------------------------------------------------------------------------------------- */
 AVCTC_API size_t avctc_bilstm_workspace_bytes(int B, int T, int In, int H, int which);
 AVCTC_API int avctc_bilstm_forward(const void* x_bf16, int B, int T, int In, int H, const float* const* params,

@@ -97,7 +97,9 @@ struct LstmFwdParams {
     float* gates;                // [2][T][B][4][H] post-activation i,f,g,o, or nullptr
     float* cst;                  // [2][T][B][H] cell state, or nullptr
     unsigned* bar;               // [2] step counters, zeroed by the host
-    int B, T;
+    int B, T;                    // B = sequences of the whole call (array strides)
+    int Bg;                      // sequences per batch group: blockIdx.y handles sequences [Bg*blockIdx.y, +Bg) on its own
+                                 // set of 2*H/16 CTAs with its own step counters (sequences are independent)
     int tagged;                  // 1: y was filled with the 0xFFFF sentinel by the host; exchange by polling the data
 };
 
@@ -117,7 +119,10 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(const LstmFwd
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const int gate = warp & 3, khalf = warp >> 2;
-    const int B = p.B, T = p.T;
+    const int T = p.T, BS = p.B;                         // BS: batch stride of the [.,T,B,.] arrays
+    const int b0 = blockIdx.y * p.Bg;                     // my batch group
+    const int B = min(p.Bg, p.B - b0);
+    const unsigned* const bar = p.bar + 2 * blockIdx.y;
 
     // W_hh rows of my gate and units, my K half: A fragments for the whole sequence
     uint32_t afrag[KS][4];
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(const LstmFwd
             const int e = tid + kLstmThreads * i, u = e & 15, b = e >> 4;
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-                xnext[i][g] = (b < B && step < T) ? __ldg(p.xproj + ((size_t)b * T + tt) * 8 * H + (size_t)d * 4 * H + g * H + u0 + u) : 0.f;
+                xnext[i][g] = (b < B && step < T) ? __ldg(p.xproj + ((size_t)(b0 + b) * T + tt) * 8 * H + (size_t)d * 4 * H + g * H + u0 + u) : 0.f;
         }
     };
     load_x(0);
@@ -165,14 +170,14 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(const LstmFwd
             if (p.tagged) {                                              // h_{t-1}: poll the data itself
                 poll_load_chunks(tid, B * (H / 8), kLstmThreads,
                     [&](int c) { const int b = c / (H / 8), q = c % (H / 8);
-                                 return reinterpret_cast<const uint4*>(p.y + ((size_t)b * T + tprev) * 2 * H + (size_t)d * H) + q; },
+                                 return reinterpret_cast<const uint4*>(p.y + ((size_t)(b0 + b) * T + tprev) * 2 * H + (size_t)d * H) + q; },
                     [&](int c) { const int b = c / (H / 8), q = c % (H / 8); return reinterpret_cast<uint4*>(hs + b * HS + q * 8); });
             } else {
-                if (tid == 0) step_barrier_wait(p.bar + d, (unsigned)NC * s);
+                if (tid == 0) step_barrier_wait(bar + d, (unsigned)NC * s);
                 __syncthreads();
                 for (int c = tid; c < B * (H / 8); c += kLstmThreads) {    // h_{t-1}: L2 loads (written by other SMs)
                     const int b = c / (H / 8), q = c % (H / 8);
-                    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p.y + ((size_t)b * T + tprev) * 2 * H + (size_t)d * H) + q);
+                    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p.y + ((size_t)(b0 + b) * T + tprev) * 2 * H + (size_t)d * H) + q);
                     *reinterpret_cast<uint4*>(hs + b * HS + q * 8) = v;
                 }
             }
@@ -224,13 +229,13 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(const LstmFwd
                 const float h = og * tanh_fast(c);
                 hprev_reg[i] = hcur_reg[i];                     // the h_{t-1} of my own unit that this step consumed
                 hcur_reg[i] = __float2bfloat16(h);
-                p.y[((size_t)b * T + t) * 2 * H + (size_t)d * H + u0 + u] = hcur_reg[i];
+                p.y[((size_t)(b0 + b) * T + t) * 2 * H + (size_t)d * H + u0 + u] = hcur_reg[i];
                 sv[i][0] = ig; sv[i][1] = fg; sv[i][2] = gg; sv[i][3] = og;
             }
         }
         if (!p.tagged) {
             __syncthreads();
-            if (tid == 0) { __threadfence(); atomicAdd(p.bar + d, 1u); }
+            if (tid == 0) { __threadfence(); atomicAdd(const_cast<unsigned*>(bar) + d, 1u); }
         }
         // everything only the backward pass needs is stored AFTER the arrive: the fence above must not wait for it
         if (p.gates) {
@@ -238,10 +243,10 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_fwd_kernel(const LstmFwd
             for (int i = 0; i < PP; ++i) {
                 const int e = tid + kLstmThreads * i, u = e & 15, b = e >> 4;
                 if (b < B) {
-                    float* gp = p.gates + (((size_t)d * T + t) * B + b) * 4 * H + u0 + u;
+                    float* gp = p.gates + (((size_t)d * T + t) * BS + b0 + b) * 4 * H + u0 + u;
                     gp[0] = sv[i][0]; gp[H] = sv[i][1]; gp[2 * H] = sv[i][2]; gp[3 * H] = sv[i][3];
-                    p.cst[(((size_t)d * T + t) * B + b) * H + u0 + u] = creg[i];
-                    p.hprev[((size_t)b * T + t) * 2 * H + (size_t)d * H + u0 + u] = hprev_reg[i];
+                    p.cst[(((size_t)d * T + t) * BS + b0 + b) * H + u0 + u] = creg[i];
+                    p.hprev[((size_t)(b0 + b) * T + t) * 2 * H + (size_t)d * H + u0 + u] = hprev_reg[i];
                 }
             }
         }
@@ -255,7 +260,7 @@ struct LstmBwdParams {
     const float* cst;            // [2][T][B][H]
     __nv_bfloat16* dG;           // [B*T][8H] gate pre-activation gradients (output; also the exchange buffer)
     unsigned* bar;               // [2]
-    int B, T;
+    int B, T, Bg;                // as in LstmFwdParams
     int tagged;                  // 1: dG was filled with the 0xFFFF sentinel by the host; exchange by polling the data
 };
 
@@ -273,7 +278,10 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(const LstmBwd
     const int u0 = cta * kLstmUnits;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
-    const int B = p.B, T = p.T;
+    const int T = p.T, BS = p.B;
+    const int b0 = blockIdx.y * p.Bg;
+    const int B = min(p.Bg, p.B - b0);
+    unsigned* const bar = p.bar + 2 * blockIdx.y;
 
     // A = W_hh^T rows (my 16 units) x K = 4H gate rows, my K slice
     uint32_t afrag[KS][4];
@@ -305,11 +313,11 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(const LstmBwd
 #pragma unroll
             for (int k = 0; k < 7; ++k) nx[i][k] = 0.f;
             if (b < B && step < T) {
-                const size_t gi = (((size_t)d * T + tt) * B + b) * 4 * H + u0 + u;
+                const size_t gi = (((size_t)d * T + tt) * BS + b0 + b) * 4 * H + u0 + u;
                 nx[i][0] = p.gates[gi]; nx[i][1] = p.gates[gi + H]; nx[i][2] = p.gates[gi + 2 * H]; nx[i][3] = p.gates[gi + 3 * H];
-                nx[i][4] = p.cst[(((size_t)d * T + tt) * B + b) * H + u0 + u];
-                nx[i][5] = (tp >= 0 && tp < T) ? p.cst[(((size_t)d * T + tp) * B + b) * H + u0 + u] : 0.f;
-                nx[i][6] = __bfloat162float(p.dy[((size_t)b * T + tt) * 2 * H + (size_t)d * H + u0 + u]);
+                nx[i][4] = p.cst[(((size_t)d * T + tt) * BS + b0 + b) * H + u0 + u];
+                nx[i][5] = (tp >= 0 && tp < T) ? p.cst[(((size_t)d * T + tp) * BS + b0 + b) * H + u0 + u] : 0.f;
+                nx[i][6] = __bfloat162float(p.dy[((size_t)(b0 + b) * T + tt) * 2 * H + (size_t)d * H + u0 + u]);
             }
         }
     };
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(const LstmBwd
                 const float d_f = dc * cp * fg * (1.f - fg);
                 const float d_g = dc * ig * (1.f - gg * gg);
                 dc_carry[i] = dc * fg;
-                __nv_bfloat16* go = p.dG + ((size_t)b * T + t) * 8 * H + (size_t)d * 4 * H + u0 + u;
+                __nv_bfloat16* go = p.dG + ((size_t)(b0 + b) * T + t) * 8 * H + (size_t)d * 4 * H + u0 + u;
                 go[0] = __float2bfloat16(d_i); go[H] = __float2bfloat16(d_f);
                 go[2 * H] = __float2bfloat16(d_g); go[3 * H] = __float2bfloat16(d_o);
             }
@@ -346,19 +354,19 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(const LstmBwd
         if (p.tagged) {                                                    // all gate gradients of step t: poll the data
             poll_load_chunks(tid, B * (4 * H / 8), kLstmThreads,
                 [&](int c) { const int b = c / (4 * H / 8), q = c % (4 * H / 8);
-                             return reinterpret_cast<const uint4*>(p.dG + ((size_t)b * T + t) * 8 * H + (size_t)d * 4 * H) + q; },
+                             return reinterpret_cast<const uint4*>(p.dG + ((size_t)(b0 + b) * T + t) * 8 * H + (size_t)d * 4 * H) + q; },
                 [&](int c) { const int b = c / (4 * H / 8), q = c % (4 * H / 8); return reinterpret_cast<uint4*>(dgs + b * GS + q * 8); });
         } else {
             __syncthreads();
             if (tid == 0) {
                 __threadfence();
-                atomicAdd(p.bar + d, 1u);
-                step_barrier_wait(p.bar + d, (unsigned)NC * (s + 1));
+                atomicAdd(bar + d, 1u);
+                step_barrier_wait(bar + d, (unsigned)NC * (s + 1));
             }
             __syncthreads();
             for (int c = tid; c < B * (4 * H / 8); c += kLstmThreads) {   // all gate gradients of step t, every unit
                 const int b = c / (4 * H / 8), q = c % (4 * H / 8);
-                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p.dG + ((size_t)b * T + t) * 8 * H + (size_t)d * 4 * H) + q);
+                const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p.dG + ((size_t)(b0 + b) * T + t) * 8 * H + (size_t)d * 4 * H) + q);
                 *reinterpret_cast<uint4*>(dgs + b * GS + q * 8) = v;
             }
         }
@@ -449,12 +457,27 @@ __global__ void lstm_copy2_kernel(const float* src, int n, float* d0, float* d1)
     if (i < n) { const float v = src[i]; d0[i] = v; d1[i] = v; }
 }
 
-struct LDims { int B, T, In, H, NB; long long BT; };
+struct LDims { int B, T, In, H, NB, G, Bg; long long BT; };
+// Batch groups: the sequences of a call are independent, and one group of 2*H/16 CTAs (64 for H = 512) leaves more than
+// half of the 148 SMs idle while its per-step cost grows with the batch (h / gate-gradient exchange, MMA N tiles).  A call
+// with more than 8 sequences is therefore split into G groups that run side by side in ONE cooperative launch, each on
+// its own CTAs with its own step counters: 16 sequences run as 2 x 8 at the step time of 8 (knob "lstm_groups": 0 auto,
+// 1 = one group as in round 1).
 static bool ldims(int B, int T, int In, int H, LDims* d) {
-    if (B <= 0 || T <= 0 || In <= 0 || B > 32) return false;
+    if (B <= 0 || T <= 0 || In <= 0) return false;
     if (H != 512 && H != 256) return false;
     if (In % 8) return false;
-    d->B = B; d->T = T; d->In = In; d->H = H; d->NB = B <= 8 ? 1 : (B <= 16 ? 2 : 4); d->BT = (long long)B * T;
+    const int max_groups = 128 / (2 * H / kLstmUnits);          // co-resident CTAs: one per SM, 148 SMs
+    int G = 1;
+    const int knob = avctc_tuning_get("lstm_groups", 0);
+    if (knob > 0) G = knob;
+    else if (B > 8) G = max_groups < 2 ? 1 : (B > 32 && max_groups >= 4 ? 4 : 2);
+    if (G > max_groups) G = max_groups;
+    if (G > B) G = B;
+    const int Bg = (B + G - 1) / G;
+    if (Bg > 32) return false;
+    d->B = B; d->T = T; d->In = In; d->H = H; d->G = (B + Bg - 1) / Bg; d->Bg = Bg;
+    d->NB = Bg <= 8 ? 1 : (Bg <= 16 ? 2 : 4); d->BT = (long long)B * T;
     return true;
 }
 struct LCarver {
@@ -510,7 +533,7 @@ static avctc_gemm_operand lop(const void* ptr, long long rows, long long kdim, l
 }
 
 template <int H, int NB>
-static int launch_fwd(const LstmFwdParams& p, cudaStream_t st) {
+static int launch_fwd(const LstmFwdParams& p, int groups, cudaStream_t st) {
     const size_t smem = (size_t)8 * NB * (H + 8) * 2 + (size_t)2 * 4 * 16 * 8 * NB * 4;
     static bool cfg = false;
     if (!cfg && smem > 48 * 1024) {
@@ -518,11 +541,11 @@ static int launch_fwd(const LstmFwdParams& p, cudaStream_t st) {
         cfg = true;
     }
     void* args[] = {const_cast<LstmFwdParams*>(&p)};
-    return (int)cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_fwd_kernel<H, NB>), dim3(2 * H / kLstmUnits),
-                                            dim3(kLstmThreads), args, smem, st);
+    return (int)cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_fwd_kernel<H, NB>),
+                                            dim3(2 * H / kLstmUnits, groups), dim3(kLstmThreads), args, smem, st);
 }
 template <int H, int NB>
-static int launch_bwd(const LstmBwdParams& p, cudaStream_t st) {
+static int launch_bwd(const LstmBwdParams& p, int groups, cudaStream_t st) {
     const size_t smem = (size_t)8 * NB * (4 * H + 8) * 2 + (size_t)8 * 16 * 8 * NB * 4;
     static bool cfg = false;
     if (!cfg && smem > 48 * 1024) {
@@ -530,16 +553,16 @@ static int launch_bwd(const LstmBwdParams& p, cudaStream_t st) {
         cfg = true;
     }
     void* args[] = {const_cast<LstmBwdParams*>(&p)};
-    return (int)cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_bwd_kernel<H, NB>), dim3(2 * H / kLstmUnits),
-                                            dim3(kLstmThreads), args, smem, st);
+    return (int)cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_bwd_kernel<H, NB>),
+                                            dim3(2 * H / kLstmUnits, groups), dim3(kLstmThreads), args, smem, st);
 }
-static int dispatch_fwd(int H, int NB, const LstmFwdParams& p, cudaStream_t st) {
-    if (H == 512) { if (NB == 1) return launch_fwd<512, 1>(p, st); if (NB == 2) return launch_fwd<512, 2>(p, st); return launch_fwd<512, 4>(p, st); }
-    if (NB == 1) return launch_fwd<256, 1>(p, st); if (NB == 2) return launch_fwd<256, 2>(p, st); return launch_fwd<256, 4>(p, st);
+static int dispatch_fwd(int H, int NB, int G, const LstmFwdParams& p, cudaStream_t st) {
+    if (H == 512) { if (NB == 1) return launch_fwd<512, 1>(p, G, st); if (NB == 2) return launch_fwd<512, 2>(p, G, st); return launch_fwd<512, 4>(p, G, st); }
+    if (NB == 1) return launch_fwd<256, 1>(p, G, st); if (NB == 2) return launch_fwd<256, 2>(p, G, st); return launch_fwd<256, 4>(p, G, st);
 }
-static int dispatch_bwd(int H, int NB, const LstmBwdParams& p, cudaStream_t st) {
-    if (H == 512) { if (NB == 1) return launch_bwd<512, 1>(p, st); if (NB == 2) return launch_bwd<512, 2>(p, st); return launch_bwd<512, 4>(p, st); }
-    if (NB == 1) return launch_bwd<256, 1>(p, st); if (NB == 2) return launch_bwd<256, 2>(p, st); return launch_bwd<256, 4>(p, st);
+static int dispatch_bwd(int H, int NB, int G, const LstmBwdParams& p, cudaStream_t st) {
+    if (H == 512) { if (NB == 1) return launch_bwd<512, 1>(p, G, st); if (NB == 2) return launch_bwd<512, 2>(p, G, st); return launch_bwd<512, 4>(p, G, st); }
+    if (NB == 1) return launch_bwd<256, 1>(p, G, st); if (NB == 2) return launch_bwd<256, 2>(p, G, st); return launch_bwd<256, 4>(p, G, st);
 }
 
 #define LSTM_TRY(expr) do { const int rc_ = (expr); if (rc_) return rc_; } while (0)
@@ -600,14 +623,14 @@ extern "C" int avctc_bilstm_forward(const void* x_bf16, int B, int T, int In, in
         fp.hprev = need_grad ? s.l[l].hprev : nullptr;
         fp.gates = need_grad ? s.l[l].gates : nullptr;
         fp.cst = need_grad ? s.l[l].cst : nullptr;
-        fp.bar = w.bar; fp.B = B; fp.T = T;
+        fp.bar = w.bar; fp.B = B; fp.T = T; fp.Bg = d.Bg;
         // measured (tools/exp_lstm_tag.py, B200): forward 766 -> 546 us at B=8, no gain at B=16 (more chunks to poll per
         // step); backward is slower with it at every batch size (every CTA polls all B x 4H gate gradients).
         // knob lstm_tag: 0 off, 1 forward when B <= 8 (default), 2 forward always, 3 forward and backward.
         const int tagk = avctc_tuning_get("lstm_tag", 1);
-        fp.tagged = (tagk >= 2 || (tagk == 1 && B <= 8)) ? 1 : 0;
+        fp.tagged = (tagk >= 2 || (tagk == 1 && d.Bg <= 8)) ? 1 : 0;
         if (fp.tagged) AVCTC_CUDA_RETURN(cudaMemsetAsync(fp.y, 0xFF, (size_t)d.BT * 2 * H * sizeof(__nv_bfloat16), st));
-        LSTM_TRY(dispatch_fwd(H, d.NB, fp, st));
+        LSTM_TRY(dispatch_fwd(H, d.NB, d.G, fp, st));
         xin = fp.y;
     }
     return AVCTC_OK;
@@ -632,10 +655,10 @@ extern "C" int avctc_bilstm_backward(const void* dy_bf16, const void* x_bf16, in
         AVCTC_CUDA_RETURN(cudaMemsetAsync(w.bar, 0, 64 * sizeof(unsigned), st));
         LstmBwdParams bp;
         bp.dy = dy; bp.whh = s.l[l].whh; bp.gates = s.l[l].gates; bp.cst = s.l[l].cst; bp.dG = w.dG; bp.bar = w.bar;
-        bp.B = B; bp.T = T;
+        bp.B = B; bp.T = T; bp.Bg = d.Bg;
         bp.tagged = avctc_tuning_get("lstm_tag", 1) >= 3 ? 1 : 0;
         if (bp.tagged) AVCTC_CUDA_RETURN(cudaMemsetAsync(w.dG, 0xFF, (size_t)d.BT * 8 * H * sizeof(__nv_bfloat16), st));
-        LSTM_TRY(dispatch_bwd(H, d.NB, bp, st));
+        LSTM_TRY(dispatch_bwd(H, d.NB, d.G, bp, st));
         for (int dir = 0; dir < 2; ++dir) {
             // dW_ih[dir] [4H,In] = dG[:, dir*4H:+4H]^T . x ; dW_hh[dir] [4H,H] = dG_dir^T . hprev[:, dir*H:+H]
             const avctc_gemm_operand A = lop(w.dG + (size_t)dir * 4 * H, 4 * H, d.BT, 8 * H, true);

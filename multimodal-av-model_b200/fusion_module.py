@@ -430,22 +430,29 @@ class CrossAttentionFusion(nn.Module):
         for s in range(2):
             fs, _m, il = self.fused_projection(visual_feats[s], audio_feats[s], masks[s])
             f.append(fs); lens.append(il)
-        if f[0].shape[1:] != f[1].shape[1:] or f[0].shape[0] + f[1].shape[0] > 32:
+        if f[0].shape[1:] != f[1].shape[1:] or f[0].shape[0] + f[1].shape[0] > 64:
             return (self.temporal(f[0]), self.temporal(f[1])), tuple(lens)
         y = self.temporal(torch.cat(f, dim=0))
         b0 = f[0].shape[0]
         return (y[:b0], y[b0:]), tuple(lens)
 
     def temporal(self, fused):
-        """temporal_model over all padded frames (fusion_module.py:64).  The reference's configuration (hidden 512,
-        also 256; batch <= 32) runs on the persistent kernels of csrc/lstm.cu; other shapes use nn.LSTM (cuDNN)."""
+        """temporal_model over all padded frames (fusion_module.py:64).  The reference's configuration (hidden 512, also
+        256; up to 64 sequences) runs on the persistent kernels of csrc/lstm.cu; other shapes use nn.LSTM (cuDNN) and
+        say so once."""
         lstm = self.temporal_model
         B, _, In = fused.shape
-        if (fused.is_cuda and lstm.hidden_size in (256, 512) and B <= 32 and In % 8 == 0 and lstm.num_layers == 2
+        max_b = 64 if lstm.hidden_size == 512 else 128
+        if (fused.is_cuda and lstm.hidden_size in (256, 512) and B <= max_b and In % 8 == 0 and lstm.num_layers == 2
                 and lstm.bidirectional and _lib.tuning_enabled("lstm_custom")):
             y = _BiLSTMFn.apply(fused, *lstm._flat_weights)
             if fused.dtype == torch.float32 and not torch.is_autocast_enabled():
                 y = y.float()
             return y
+        if fused.is_cuda and _lib.tuning_enabled("lstm_custom") and not getattr(self, "_warned_cudnn", False):
+            import warnings
+            warnings.warn(f"CrossAttentionFusion.temporal_model: shape (batch {B}, hidden {lstm.hidden_size}, input {In}) is "
+                          "outside the sm_100a BiLSTM kernels (hidden 256/512, batch <= 64/128); running torch.nn.LSTM (cuDNN)")
+            self._warned_cudnn = True
         fused_seq, _ = lstm(fused)
         return fused_seq

@@ -18,7 +18,8 @@ def relerr(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
 
 
-@pytest.mark.parametrize("B,T,H", [(8, 150, 512), (3, 17, 512), (16, 40, 256), (32, 25, 512), (1, 1, 512)])
+@pytest.mark.parametrize("B,T,H", [(8, 150, 512), (3, 17, 512), (16, 40, 256), (32, 25, 512), (1, 1, 512), (16, 60, 512),
+                                   (12, 33, 512), (48, 20, 512), (64, 9, 256), (9, 21, 512)])
 def test_bilstm_forward_backward_vs_torch(B, T, H):
     pkg = _pkg()
     from multimodal_av_model_b200.fusion_module import _BiLSTMFn
@@ -85,3 +86,32 @@ def test_bilstm_exchange_modes_are_bitwise_identical(B, T, H):
         assert torch.equal(res[0][0], res[mode][0]) and torch.equal(res[0][1], res[mode][1]), mode   # y, dx
         for a, b in zip(res[0][2:], res[mode][2:]):      # weight gradients: split-K fp32 atomics, order not fixed
             assert (a - b).abs().max() <= 1e-4 * (a.abs().max() + 1e-12), mode
+
+
+@pytest.mark.parametrize("B,T,H", [(16, 50, 512), (11, 30, 512), (24, 20, 256)])
+def test_bilstm_batch_groups_change_no_value(B, T, H):
+    """Calls with more than 8 sequences run as independent batch groups side by side in one cooperative launch
+    (csrc/lstm.cu, knob lstm_groups).  A sequence's arithmetic does not depend on the group it runs in: outputs and
+    input gradients are bit-identical to the single-group launch of round 1."""
+    pkg = _pkg()
+    from multimodal_av_model_b200.fusion_module import _BiLSTMFn
+    torch.manual_seed(B * 7 + T)
+    ref = torch.nn.LSTM(H, H, num_layers=2, batch_first=True, bidirectional=True).cuda()
+    x = torch.randn(B, T, H, device="cuda")
+    r = torch.randn(B, T, 2 * H, device="cuda")
+    res = {}
+    try:
+        for groups in (1, 0, 2):
+            pkg._lib.set_tuning("lstm_groups", groups)
+            for p in ref.parameters():
+                p.grad = None
+            xi = x.clone().requires_grad_()
+            y = _BiLSTMFn.apply(xi, *ref._flat_weights)
+            (y.float() * r).sum().backward()
+            res[groups] = [y.detach().clone(), xi.grad.clone()] + [p.grad.clone() for p in ref._flat_weights]
+    finally:
+        pkg._lib.set_tuning("lstm_groups", 0)
+    for groups in (0, 2):
+        assert torch.equal(res[1][0], res[groups][0]) and torch.equal(res[1][1], res[groups][1]), groups
+        for a, b in zip(res[1][2:], res[groups][2:]):
+            assert (a - b).abs().max() <= 1e-4 * (a.abs().max() + 1e-12), groups
