@@ -1,7 +1,8 @@
 """GPU: CrossAttentionFusion / CTCDecoder (tcgen05 GEMMs + glue kernels) against the reference fixtures
 (small dims) and the torch-CPU restatement (config-3 dims).  Tolerance (north_star): bf16 — operands are
 rounded to bf16 and accumulated in fp32, so activations agree to ~1e-2 relative of their scale; integer
-outputs (input_lengths, resampled mask) are exact."""
+outputs (input_lengths, resampled mask) are exact.  Bounds are the errors MEASURED on B200 with ~2x head-room
+(north_star: rel 1e-2 on O(1) activations; gradients of tiny fixtures sit slightly above that in max-norm)."""
 import numpy as np
 import pytest
 import torch
@@ -45,16 +46,18 @@ def test_fusion_and_head_match_reference_fixture(name):
           "d_audio", round(relerr(aud.grad, torch.from_numpy(c["grad_audio"])), 5), "d_visual", round(relerr(vis.grad, torch.from_numpy(c["grad_visual"])), 5),
           "params", round(max(relerr(p.grad, torch.from_numpy(c[f"dec_grad/{k[4:]}"] if k.startswith("dec.") else c[f"grad/{k}"]))
                               for k, p in list(fus.named_parameters()) + [("dec." + k, p) for k, p in dec.named_parameters()] if p.grad is not None), 5))
-    assert relerr(fused, torch.from_numpy(c["fused"])) < 2e-2
-    assert (lp.cpu() - torch.from_numpy(c["log_probs"])).abs().max().item() < 3e-2
-    assert relerr(aud.grad, torch.from_numpy(c["grad_audio"])) < 5e-2
-    assert relerr(vis.grad, torch.from_numpy(c["grad_visual"])) < 5e-2
+    # measured on B200 (round 2): fused 1.5e-4 / 4.1e-4, log-probs 4e-4, d_audio 1.2e-2 / 8.4e-3, d_visual 7.5e-3 / 8.7e-3,
+    # parameter gradients <= 1.15e-2 — bounds = measured with ~2x head-room
+    assert relerr(fused, torch.from_numpy(c["fused"])) < 5e-3
+    assert (lp.cpu() - torch.from_numpy(c["log_probs"])).abs().max().item() < 5e-3
+    assert relerr(aud.grad, torch.from_numpy(c["grad_audio"])) < 2.5e-2
+    assert relerr(vis.grad, torch.from_numpy(c["grad_visual"])) < 2e-2
     for k, p in list(fus.named_parameters()) + [("dec." + k, p) for k, p in dec.named_parameters()]:
         g = c[f"dec_grad/{k[4:]}"] if k.startswith("dec.") else c[f"grad/{k}"]
         if g.size == 0:
             assert p.grad is None, k                                     # cross_attn_visual stays unused
         else:
-            assert relerr(p.grad, torch.from_numpy(g)) < 5e-2, k
+            assert relerr(p.grad, torch.from_numpy(g)) < 2.5e-2, k
 
 
 def config3_inputs(B=32, Tv=150, Ta=249, seed=0):
@@ -86,14 +89,14 @@ def test_fusion_projection_config3_vs_torch_port():
     (f * r.cuda()).sum().backward()
     assert torch.equal(m.cpu(), m_ref)
     assert il.cpu().tolist() == (m_ref != 0).sum(1).tolist()
-    assert relerr(f, f_ref) < 2e-2
-    assert relerr(a2.grad, a1.grad) < 5e-2
-    assert relerr(v2.grad, v1.grad) < 5e-2
+    assert relerr(f, f_ref) < 1e-2                       # measured 4e-3 (B=32: tests/test_bench_sizes_gpu.py)
+    assert relerr(a2.grad, a1.grad) < 2e-2
+    assert relerr(v2.grad, v1.grad) < 2e-2
     for (k, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
         if q.grad is None:
             assert p.grad is None
         elif not k.startswith("temporal_model"):
-            assert relerr(p.grad, q.grad) < 5e-2, k
+            assert relerr(p.grad, q.grad) < 2e-2, k
 
 
 def test_resample_edge_cases():
@@ -161,14 +164,15 @@ def test_fused_path_odd_shapes_full_module_vs_torch_port(B, Tv, Ta, E, H):
     assert il.cpu().tolist() == il_ref.tolist()
     print((B, Tv, Ta, E, H), "y", round(relerr(y, y_ref), 5), "d_audio", round(relerr(a2.grad, a1.grad), 5), "d_visual", round(relerr(v2.grad, v1.grad), 5),
           "params", round(max(relerr(p.grad, q.grad) for (k, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()) if q.grad is not None), 5))
-    assert relerr(y, y_ref) < 3e-2
-    assert relerr(a2.grad, a1.grad) < 6e-2
-    assert relerr(v2.grad, v1.grad) < 6e-2
+    # measured on B200 (round 2): y <= 4e-3, d_audio <= 1.03e-2, d_visual <= 6.8e-3, parameter gradients <= 9.8e-3
+    assert relerr(y, y_ref) < 1e-2
+    assert relerr(a2.grad, a1.grad) < 2.5e-2
+    assert relerr(v2.grad, v1.grad) < 2e-2
     for (k, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
         if q.grad is None:
             assert p.grad is None, k
         else:
-            assert relerr(p.grad, q.grad) < 6e-2, k
+            assert relerr(p.grad, q.grad) < 2.5e-2, k
 
 
 @pytest.mark.parametrize("Tv2", [40, 33])
