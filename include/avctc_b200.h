@@ -54,7 +54,7 @@ AVCTC_API const char* avctc_status_string(int status);
  * "beam_pf" (1 = L2 prefetch of the next row), "pdl" (1 = programmatic dependent launch for the GEMM / softmax / CTC
  * kernel chains), "lstm_tag" (BiLSTM step exchange: 0 counter barrier, 1 sentinel polling in the forward pass when
  * B <= 8, 2 forward always, 3 forward and backward), "lstm_groups" (batch groups of the BiLSTM kernels: 0 auto, n = n
- * groups), "beam_chunks" (frame-chunk pipeline of the two-phase beam decode: 0 auto, 1 off, n = n chunks), "gemm_dbg" (per-CTA timestamps).  Unknown keys return
+ * groups), "gemm_dbg" (per-CTA timestamps).  Unknown keys return
  * AVCTC_ERR_BAD_ARG. */
 AVCTC_API int avctc_set_tuning(const char* key, int value);
 
@@ -127,10 +127,6 @@ AVCTC_API int avctc_ctc_scale_grad(void* grad, int dtype, int T, int B, int V, c
  * what the reference does) gives the number of frames to decode per utterance.
  * out_ids[n*T .. ] int32 receives the collapsed token ids, out_len[n] their count.
  * Token lists are bit-exact with the reference on CPU, including torch.topk's tie order.
- * Large batches (N*T >= 2^17 rows) are decoded as a pipeline of frame chunks: the per-frame top-k of chunk c+1 (HBM-bound)
- * runs on `stream` while the beam recurrence of chunk c (a latency-bound chain) runs on an auxiliary stream the library
- * owns; `stream` waits for the last recurrence before the call's work counts as enqueued, so ordering for the caller is
- * unchanged.
  * Optional debug export (may be NULL): final beam scores dbg_scores[n*beam + i] (double) and raw
  * (uncollapsed) best-beam-first paths dbg_paths[(n*beam + i)*T + t] (int32).
  * ---------------------------------------------------------------------------------------------- */

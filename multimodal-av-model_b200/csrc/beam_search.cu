@@ -18,8 +18,6 @@
 // (b+1)(j+1) <= beam candidates can survive the prune (every (b',j') <= (b,j) sorts first), so <= ~beam*ln
 // candidates are ranked by counting, scores in fp64, back-pointers kept per frame.  Rows are staged
 // through a 3-deep cp.async ring so the T-step recurrence never waits on HBM.
-#include <mutex>
-
 #include "common.cuh"
 
 namespace avctc {
@@ -45,13 +43,6 @@ struct BeamParams {
     int prefetch;          // top-k kernel: L2-prefetch the warp's next row (tuning knob "beam_pf")
     float* tk_val;         // [N][T][beam] per-frame top-k values (two-phase path)
     int32_t* tk_idx;       // [N][T][beam] per-frame top-k indices
-    // frame-chunk pipeline (two-phase path at large N*T): this launch covers frames [f0, f1) of every utterance.
-    // top-k kernel: rows are enumerated FRAME-major inside the chunk (row r -> t = f0 + r / N, n = r % N);
-    // recurrence kernel: beam state enters / leaves through st_score / st_nb, back-pointers live in bp_global.
-    int f0, f1, chunked;
-    double* st_score;      // [N][kBeamMax]
-    int* st_nb;            // [N]
-    uint16_t* bp16_global; // [N][T][beam] 16-bit back-pointers of all chunks (copied to shared memory by the last one)
 };
 
 __device__ __forceinline__ bool ranks_before(float x, float y) {  // TopKImpl.h:56-58
@@ -482,8 +473,8 @@ __global__ void __launch_bounds__(kTopkWarps * 32) beam_topk_kernel(const BeamPa
     int* ti = reinterpret_cast<int*>(tv + kBeamMax + 1);
     float* srow = reinterpret_cast<float*>(ti + kBeamMax + 1);
     int* qi = reinterpret_cast<int*>(srow + p.row_floats);
-    const unsigned uT = (unsigned)p.T, uN = (unsigned)p.N;
-    const unsigned rows = p.chunked ? uN * (unsigned)(p.f1 - p.f0) : uN * uT;       // host guarantees N*T < 2^31
+    const unsigned rows = (unsigned)p.N * (unsigned)p.T;       // host guarantees N*T < 2^31
+    const unsigned uT = (unsigned)p.T;
     const bool can_fast = p.fast && (k + 1 <= 32) && (p.V >= k + 1);
     const int full_slots = (MODE == 0) ? NV : (MODE == 1) ? NV - 1 : p.V / 32;
     const bool tail_ok = lane + 32 * (NV - 1) < p.V;           // MODE 1: the one ragged slot
@@ -492,31 +483,23 @@ __global__ void __launch_bounds__(kTopkWarps * 32) beam_topk_kernel(const BeamPa
         if (MODE == 1) return j < NV - 1 || tail_ok;
         return j < full_slots || lane + 32 * j < p.V;
     };
-    for (unsigned rr = blockIdx.x * kTopkWarps + warp; rr < rows; rr += gridDim.x * kTopkWarps) {
-        // r = index of the row in the [N,T] list arrays; chunked launches walk their rows frame-major
-        unsigned n, t, r;
-        if (p.chunked) { t = (unsigned)p.f0 + rr / uN; n = rr - (rr / uN) * uN; r = n * uT + t; }
-        else { r = rr; n = r / uT; t = r - n * uT; }
+    for (unsigned r = blockIdx.x * kTopkWarps + warp; r < rows; r += gridDim.x * kTopkWarps) {
         if (p.lengths) {
+            const unsigned n = r / uT, t = r - n * uT;
             const long long fl = p.lengths[n];
             if ((long long)t >= fl) continue;
         }
         const float* row;
-        const bool dense = !p.chunked && p.stride_n == (int64_t)uT * p.stride_t;
+        const bool dense = p.stride_n == (int64_t)uT * p.stride_t;
         if (dense) row = p.lp + (int64_t)r * p.stride_t + lane;     // dense [N,T,V]
-        else row = p.lp + (int64_t)n * p.stride_n + (int64_t)t * p.stride_t + lane;
+        else { const unsigned n = r / uT, t = r - n * uT; row = p.lp + (int64_t)n * p.stride_n + (int64_t)t * p.stride_t + lane; }
         float x[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) x[j] = valid(j) ? __ldcs(row + 32 * j) : AVCTC_NEG_INF;
-        if (p.prefetch && (dense || p.chunked)) {       // the warp's next row: one 128-byte line per lane into L2
-            const unsigned rn = rr + gridDim.x * kTopkWarps;
-            if (rn < rows && lane * 32 < p.V) {
-                const float* nx;
-                if (p.chunked) { const unsigned tn = (unsigned)p.f0 + rn / uN, nn = rn - (rn / uN) * uN;
-                                 nx = p.lp + (int64_t)nn * p.stride_n + (int64_t)tn * p.stride_t; }
-                else nx = p.lp + (int64_t)rn * p.stride_t;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + lane * 32));
-            }
+        if (p.prefetch && dense) {       // the warp's next row: one 128-byte line per lane into L2
+            const unsigned rn = r + gridDim.x * kTopkWarps;
+            if (rn < rows && lane * 32 < p.V)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.lp + (int64_t)rn * p.stride_t + lane * 32));
         }
         float ml = x[0];
 #pragma unroll
@@ -628,10 +611,6 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
 
     long long fl = p.lengths ? p.lengths[n] : p.T;
     const int frames = (int)(fl < 0 ? 0 : (fl > p.T ? p.T : fl));
-    // chunked launches advance frames [f0, f1) only; the beam state of the utterance lives in st_score / st_nb in between
-    const int t_begin = p.chunked ? min(p.f0, frames) : 0;
-    const int t_end = p.chunked ? min(p.f1, frames) : frames;
-    const bool last_chunk = !p.chunked || p.f1 >= p.T;
     // back-pointers: in shared memory as 16-bit (parent << 10 | token; the two-phase path has V <= 1024, beam <= 32),
     // which doubles the resident warps per SM of this latency-bound kernel; the global spill keeps 32-bit entries
     uint32_t* bp = bp_in_smem ? bp_s : p.bp_global + (size_t)n * p.T * k;
@@ -644,29 +623,22 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
                 if ((b + 1) * (j + 1) <= k) { en_b[m] = (unsigned char)b; en_j[m] = (unsigned char)j; ++m; }
         score[0] = 0.0;
     }
-    int nb = 1, cur = 0;
-    if (p.chunked && p.f0 > 0) {
-        nb = p.st_nb[n];
-        if (lane < nb) score[lane] = p.st_score[(size_t)n * kBeamMax + lane];
-    }
     __syncwarp();
+    int nb = 1, cur = 0;
     const bool fast_enum = p.n_enum <= 32;
     const int my_b = (lane < p.n_enum) ? en_b[lane] : 0, my_j = (lane < p.n_enum) ? en_j[lane] : 0;
     const float* tvp = p.tk_val + (size_t)n * p.T * k;
     const int32_t* tip = p.tk_idx + (size_t)n * p.T * k;
     float tv_n = 0.f; int ti_n = 0;
-    if (t_begin < t_end && lane < k) { tv_n = tvp[(size_t)t_begin * k + lane]; ti_n = tip[(size_t)t_begin * k + lane]; }
-    const float* tv_nx = tvp + (size_t)t_begin * k + lane;     // running pointers: the next frame's list / this frame's back-pointer row
-    const int32_t* ti_nx = tip + (size_t)t_begin * k + lane;
-    uint32_t* bp_t = bp + (size_t)t_begin * k;
-    // chunked: 16-bit entries go to global memory (they must outlive the launch); the last chunk pulls all of them into
-    // shared memory before the back-track, whose 150 dependent reads would otherwise each be an L2 round trip
-    uint16_t* const bp16_g = p.chunked ? p.bp16_global + (size_t)n * p.T * k : nullptr;
-    uint16_t* bp16_t = (p.chunked ? bp16_g : bp16) + (size_t)t_begin * k;
-    for (int t = t_begin; t < t_end; ++t, bp_t += k, bp16_t += k) {
+    if (frames > 0 && lane < k) { tv_n = tvp[lane]; ti_n = tip[lane]; }
+    const float* tv_nx = tvp + lane;           // running pointers: the next frame's list / this frame's back-pointer row
+    const int32_t* ti_nx = tip + lane;
+    uint32_t* bp_t = bp;
+    uint16_t* bp16_t = bp16;
+    for (int t = 0; t < frames; ++t, bp_t += k, bp16_t += k) {
         const float tvv = tv_n; const int tii = ti_n;
         tv_nx += k; ti_nx += k;
-        if (t + 1 < t_end && lane < k) { tv_n = *tv_nx; ti_n = *ti_nx; }
+        if (t + 1 < frames && lane < k) { tv_n = *tv_nx; ti_n = *ti_nx; }
         if (fast_enum) {
             // <= 32 candidates: lane m IS candidate m.  Rank = number of strictly greater scores (16-byte shared loads,
             // NaN padding compares false); equal scores give equal ranks, which match.any detects -> exact route below.
@@ -747,16 +719,6 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
         cur ^= 1;
         nb = keep;
     }
-    if (p.chunked && last_chunk) {
-        __syncwarp();
-        for (int i = lane; i < frames * k; i += 32) bp16[i] = bp16_g[i];
-        __syncwarp();
-    }
-    if (!last_chunk) {       // park the beam state for the next chunk's launch
-        if (lane < nb) p.st_score[(size_t)n * kBeamMax + lane] = score[cur * kBeamMax + lane];
-        if (lane == 0) p.st_nb[n] = nb;
-        return;
-    }
     if (frames > 0) {
         const bool dbg = (p.dbg_paths != nullptr);
         if (lane == 0 || (dbg && lane < nb)) {
@@ -806,8 +768,7 @@ static int enum_count(int k) {
 }
 
 struct BeamPlan { size_t off_bp, off_path, off_status, off_tv, off_ti, total; bool bp_in_smem; size_t smem; int row_floats, n_enum, use_nth;
-                  bool two_phase; size_t smem_topk, smem_recur_per_warp; bool bp_in_smem2;
-                  int chunks; size_t off_sts, off_stn, off_bp16; };
+                  bool two_phase; size_t smem_topk, smem_recur_per_warp; bool bp_in_smem2; };
 
 static bool beam_plan(int N, int T, int V, int beam, BeamPlan* pl) {
     if (beam < 1 || beam > kBeamMax || beam > V) return false;
@@ -830,47 +791,13 @@ static bool beam_plan(int N, int T, int V, int beam, BeamPlan* pl) {
     const size_t recur_fixed = 2 * kBeamMax * 8 + (size_t)(pl->n_enum > 32 ? pl->n_enum : 32) * 8 + 2 * (size_t)pl->n_enum + 16;
     const size_t bp16_bytes = bp_bytes / 2;              // two-phase recurrence: 16-bit entries in shared memory
     pl->bp_in_smem2 = bp16_bytes <= (size_t)kBpSmemBytes / 2;
-    // Frame-chunk pipeline: the recurrence is a chain of T dependent steps per utterance (~1.5 us each) that would start
-    // only after the HBM-bound top-k pass over ALL rows; cut T into chunks, run top-k frame-major per chunk, and let the
-    // recurrence of chunk i run (second stream) under the top-k of chunk i+1.  Worth it when the top-k pass is long
-    // enough to hide a chunk's recurrence: >= 2^17 rows, >= 48 frames.  Knob "beam_chunks": 0 auto, 1 off, n = n chunks.
-    pl->chunks = 1;
-    if (pl->two_phase) {
-        const int knob = avctc_tuning_get("beam_chunks", 0);
-        if (knob > 1) pl->chunks = knob < T ? knob : (T > 0 ? T : 1);
-        else if (knob == 0 && (long long)N * T >= (1 << 17) && T >= 48) pl->chunks = T >= 144 ? 6 : (T >= 96 ? 4 : 2);
-        if (!pl->bp_in_smem2) pl->chunks = 1;               // the last chunk back-tracks from shared memory
-    }
     pl->smem_recur_per_warp = (recur_fixed + (pl->bp_in_smem2 ? bp16_bytes : 0) + 15) / 16 * 16;
     const bool need_bp_global = pl->two_phase ? !pl->bp_in_smem2 : !pl->bp_in_smem;
     pl->off_bp = o; if (need_bp_global) o = (o + (size_t)N * bp_bytes + 255) / 256 * 256;
     pl->off_tv = o; if (pl->two_phase) o = (o + (size_t)N * (T > 0 ? T : 1) * beam * 4 + 255) / 256 * 256;
     pl->off_ti = o; if (pl->two_phase) o = (o + (size_t)N * (T > 0 ? T : 1) * beam * 4 + 255) / 256 * 256;
-    pl->off_sts = o; if (pl->chunks > 1) o = (o + (size_t)N * kBeamMax * 8 + 255) / 256 * 256;
-    pl->off_stn = o; if (pl->chunks > 1) o = (o + (size_t)N * 4 + 255) / 256 * 256;
-    pl->off_bp16 = o; if (pl->chunks > 1) o = (o + (size_t)N * (T > 0 ? T : 1) * beam * 2 + 255) / 256 * 256;
     pl->total = o;
     return true;
-}
-
-// per-device auxiliary stream + events of the frame-chunk pipeline (process lifetime, created on first use)
-struct BeamAux { cudaStream_t stream = nullptr; cudaEvent_t ev[16] = {}; int nev = 0; std::mutex mu; };
-static BeamAux* beam_aux(int dev, int chunks) {
-    static BeamAux aux[64];
-    static std::mutex create_mu;
-    if (dev < 0 || dev >= 64 || chunks + 2 > 16) return nullptr;
-    BeamAux* a = &aux[dev];
-    std::lock_guard<std::mutex> lk(create_mu);
-    if (!a->stream) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);                  // hi = numerically lowest = highest priority
-        if (cudaStreamCreateWithPriority(&a->stream, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
-    }
-    while (a->nev < chunks + 2) {
-        if (cudaEventCreateWithFlags(&a->ev[a->nev], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        ++a->nev;
-    }
-    return a;
 }
 
 }  // namespace avctc
@@ -917,9 +844,12 @@ extern "C" int avctc_beam_search(const float* log_probs, int64_t stride_n, int64
         bp.tk_idx = reinterpret_cast<int32_t*>(w + pl.off_ti);
         bp.bp_global = pl.bp_in_smem2 ? nullptr : reinterpret_cast<uint32_t*>(w + pl.off_bp);
         const int need = (V + 31) / 32;
+        const long long rows = (long long)N * T;
+        long long blocks = (rows + kTopkWarps - 1) / kTopkWarps;
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
 #define AVCTC_TOPK(NV, MODE)                                                                                        \
     do {                                                                                                            \
         static bool cfg = false;                                                                                    \
@@ -936,58 +866,21 @@ extern "C" int avctc_beam_search(const float* log_probs, int64_t stride_n, int64
         else if (V > 32 * (NV - 1)) AVCTC_TOPK(NV, 1);                                                              \
         else AVCTC_TOPK(NV, 2);                                                                                     \
     } while (0)
-        auto launch_topk = [&](long long rows) -> int {
-            long long blocks = (rows + kTopkWarps - 1) / kTopkWarps;
-            if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
-            if (need <= 4) AVCTC_TOPK(4, 2);
-            else if (need <= 8) AVCTC_TOPK(8, 2);
-            else if (need <= 16) AVCTC_TOPK(16, 2);
-            else if (need <= 25) AVCTC_TOPK_M(25);
-            else if (need <= 26) AVCTC_TOPK_M(26);
-            else AVCTC_TOPK_M(32);
-            return (int)cudaGetLastError();
-        };
+        if (need <= 4) AVCTC_TOPK(4, 2);
+        else if (need <= 8) AVCTC_TOPK(8, 2);
+        else if (need <= 16) AVCTC_TOPK(16, 2);
+        else if (need <= 25) AVCTC_TOPK_M(25);
+        else if (need <= 26) AVCTC_TOPK_M(26);
+        else AVCTC_TOPK_M(32);
+#undef AVCTC_TOPK_M
+#undef AVCTC_TOPK
+        AVCTC_CUDA_RETURN(cudaGetLastError());
         const size_t smem2 = pl.smem_recur_per_warp * kRecurWarps;
         static bool cfg2 = false;
         if (!cfg2 && smem2 > 48 * 1024) {
             AVCTC_CUDA_RETURN(cudaFuncSetAttribute(beam_recur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             cfg2 = true;
         }
-        bp.f0 = 0; bp.f1 = T; bp.chunked = 0; bp.st_score = nullptr; bp.st_nb = nullptr; bp.bp16_global = nullptr;
-        if (pl.chunks > 1) {
-            // frame-chunk pipeline: top-k of chunk c on the caller's stream, the recurrence of chunk c on the library's
-            // auxiliary (high-priority) stream of this device, ordered by events; the caller's stream waits for the last
-            // recurrence, so for the caller everything is still "enqueued on `stream`".
-            BeamAux* ax = beam_aux(dev, pl.chunks);
-            if (!ax) return (int)cudaErrorUnknown;
-            std::lock_guard<std::mutex> lk(ax->mu);
-            bp.chunked = 1;
-            bp.st_score = reinterpret_cast<double*>(w + pl.off_sts);
-            bp.st_nb = reinterpret_cast<int*>(w + pl.off_stn);
-            bp.bp16_global = reinterpret_cast<uint16_t*>(w + pl.off_bp16);
-            AVCTC_CUDA_RETURN(cudaEventRecord(ax->ev[0], st));
-            AVCTC_CUDA_RETURN(cudaStreamWaitEvent(ax->stream, ax->ev[0], 0));
-            for (int c = 0; c < pl.chunks; ++c) {
-                bp.f0 = (int)((long long)T * c / pl.chunks);
-                bp.f1 = (int)((long long)T * (c + 1) / pl.chunks);
-                int rc = launch_topk((long long)N * (bp.f1 - bp.f0));
-                if (rc) return rc;
-                AVCTC_CUDA_RETURN(cudaEventRecord(ax->ev[1 + c], st));
-                AVCTC_CUDA_RETURN(cudaStreamWaitEvent(ax->stream, ax->ev[1 + c], 0));
-                beam_recur_kernel<<<(N + kRecurWarps - 1) / kRecurWarps, kRecurWarps * 32, smem2, ax->stream>>>(
-                    bp, (int)pl.smem_recur_per_warp, 1);
-                AVCTC_CUDA_RETURN(cudaGetLastError());
-            }
-            AVCTC_CUDA_RETURN(cudaEventRecord(ax->ev[1 + pl.chunks], ax->stream));
-            AVCTC_CUDA_RETURN(cudaStreamWaitEvent(st, ax->ev[1 + pl.chunks], 0));
-            return AVCTC_OK;
-        }
-        {
-            int rc = launch_topk((long long)N * T);
-            if (rc) return rc;
-        }
-#undef AVCTC_TOPK_M
-#undef AVCTC_TOPK
         beam_recur_kernel<<<(N + kRecurWarps - 1) / kRecurWarps, kRecurWarps * 32, smem2, st>>>(
             bp, (int)pl.smem_recur_per_warp, pl.bp_in_smem2 ? 1 : 0);
         return (int)cudaGetLastError();

@@ -154,36 +154,3 @@ def test_beam_config5_full_size_equals_collapsed_row_maximum():
     # decoding is a pure function of the utterance: any sub-batch, in any order, gives the same lists
     sub = torch.tensor([4095, 17, 2048, 17], device="cuda")
     assert pkg.beam_search_batch(lp[sub], beam_width=k, blank=blank) == [res[4095], res[17], res[2048], res[17]]
-
-
-@pytest.mark.parametrize("chunks", [2, 3, 7])
-def test_beam_frame_chunk_pipeline_is_bit_identical(chunks):
-    """Large batches are decoded as a pipeline of frame chunks (top-k of chunk c+1 on the caller's stream over the
-    recurrence of chunk c on the library's auxiliary stream; the beam state is parked in the workspace between
-    launches, back-pointers live in global memory until the last chunk).  Forced here on a small batch with ties,
-    ragged lengths (shorter than a chunk, zero, ending inside a chunk) and the debug export: every token list, every
-    final beam score and every raw beam path equals the single-launch decode and the oracle."""
-    pkg = _pkg()
-    g = torch.Generator().manual_seed(11)
-    N, T, V, k = 9, 61, 800, 10
-    lp = (3 * torch.randn(N, T, V, generator=g)).log_softmax(-1)
-    lp[::3] = lp[::3].bfloat16().float()
-    lp[4, 20] = -1.5                                    # an all-equal row: pure tie order
-    lens = torch.tensor([61, 61, 7, 0, 61, 30, 31, 60, 1])
-    dev = lp.cuda()
-    pkg._lib.set_tuning("beam_chunks", 1)
-    try:
-        base = pkg.beam_search_batch(dev, beam_width=k, blank=3, return_debug=True)
-        base_len = pkg.beam_search_batch(dev, beam_width=k, blank=3, lengths=lens)
-        pkg._lib.set_tuning("beam_chunks", chunks)
-        for _ in range(2):                              # twice: the auxiliary stream / events are reused across calls
-            got = pkg.beam_search_batch(dev, beam_width=k, blank=3, return_debug=True)
-            got_len = pkg.beam_search_batch(dev, beam_width=k, blank=3, lengths=lens)
-            assert got[0] == base[0]
-            assert torch.equal(got[1], base[1]) and torch.equal(got[2], base[2])
-            assert got_len == base_len
-    finally:
-        pkg._lib.set_tuning("beam_chunks", 0)
-    for i in range(N):
-        assert base_len[i] == oracle.beam_search(lp[i, :int(lens[i])].contiguous().numpy(), k, 3)
-    assert base_len[3] == []
