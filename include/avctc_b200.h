@@ -49,7 +49,8 @@ AVCTC_API const char* avctc_status_string(int status);
  * "ctc_ws" (1 = warp-specialised TMA-fed scan, 0 = single-warp scan), "ctc_k" (log-domain scan, states per lane:
  * 0 = auto, 2/4/8/16), "ctc_pf" (gradient pass: L2 prefetch distance in rows, 0 = off, +4 = also alpha/beta),
  * "ctc_overlap" (1 = a gradient pass launched right behind the scan starts on each sample as soon as that sample's
- * alpha/beta rows are complete, 0 = it waits for the whole scan grid), "ctc_stamp" (1 = the CTC kernels leave
+ * alpha/beta rows are complete, 0 = it waits for the whole scan grid), "ctc_stage" (1 = the fp32 gradient pass stages each log-prob row in
+ * shared memory with cp.async, 0 = register streaming), "ctc_stamp" (1 = the CTC kernels leave
  * globaltimer stamps in the workspace's flag block: debug / tests), "ctc_grad_warps", "beam_fast" (1 = threshold top-k fast path), "beam_two_phase" (1 = top-k for all rows first),
  * "beam_pf" (1 = L2 prefetch of the next row), "pdl" (1 = programmatic dependent launch for the GEMM / softmax / CTC
  * kernel chains), "lstm_tag" (BiLSTM step exchange: 0 counter barrier, 1 sentinel polling in the forward pass when

@@ -706,6 +706,7 @@ struct GradParams {
     int prefetch;     // grad_lin: L2-prefetch the warp's next log-prob row (tuning knob "ctc_pf")
     int row_floats;   // per-warp smem floats for one staged row (>= V + 8, multiple of 4)
     int w_floats;     // per-warp smem floats for state weights (>= 2*Lmax+1, multiple of 4)
+    int stage;        // grad_lin, fp32: the whole log-prob row goes to per-warp shared memory with cp.async first
 };
 
 template <typename T>
@@ -1473,11 +1474,55 @@ __device__ __forceinline__ void grad_stream_row(const TIn* __restrict__ lrow, TI
     }
 }
 
+// Same arithmetic with the log-prob row already in shared memory (row_s[c] = class c): the global loads of the row
+// were issued all at once by cp.async (stage_row) instead of one 16-byte load per lane per loop iteration, so a warp
+// has its whole 3.2 KB row in flight, not 512 bytes of it.
+template <bool POS>
+__device__ __forceinline__ void grad_stream_row_smem(const float* __restrict__ row_s, int o_in, float* __restrict__ grow,
+                                                     int V, const float* __restrict__ delta, int o_out, float scale,
+                                                     float lscale, int lane) {
+    const int nq = (o_out + V + 3) / 4;
+    const bool same = (o_in == o_out);           // then row_s + c0 is 16-byte aligned whenever grow + c0 is
+    for (int q = lane; q < nq; q += 32) {
+        const int c0 = q * 4 - o_out;
+        const bool full = (c0 >= 0) && (c0 + 4 <= V);
+        float x[4];
+        if (full && same) {
+            const float4 v = *reinterpret_cast<const float4*>(row_s + c0);
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = c0 + k;
+                x[k] = (c >= 0 && c < V) ? row_s[c] : 0.f;
+            }
+        }
+        const float4 d = *reinterpret_cast<const float4*>(delta + q * 4);
+        const float dd[4] = {d.x, d.y, d.z, d.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float e = ex2_approx(fmaf(x[k], AVCTC_LOG2E, lscale));   // |scale| * exp(lp)
+            o[k] = POS ? fmaf(dd[k], -scale, e) : -fmaf(dd[k], scale, e);
+        }
+        if (full) {
+            __stcs(reinterpret_cast<float4*>(grow + c0), make_float4(o[0], o[1], o[2], o[3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = c0 + k;
+                if (c >= 0 && c < V) grow[c] = o[k];
+            }
+        }
+    }
+}
+
 constexpr int kZeroChunk = 4;          // early mode: rows beyond the input length are handed out four at a time
 constexpr int kSpreadMaxB = 256;      // batch sizes whose completion order is sorted inside the gradient kernel
 
+// (fp32: the staged row makes shared memory, not registers, the occupancy limit: 3 CTAs per SM, 85 registers)
 template <int K, typename TIn>
-__global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(const GradParams p) {
+__global__ void __launch_bounds__(256, (K <= 8) ? (sizeof(TIn) == 4 ? 3 : 4) : 1) ctc_grad_lin_kernel(const GradParams p) {
     constexpr int KL = K / 2;
     constexpr int kVec = VecTraits<TIn>::kVec;
     extern __shared__ __align__(16) float smem[];
@@ -1579,6 +1624,12 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
     }
     float* delta = smem + (size_t)warp * (p.row_floats + p.w_floats);   // class posteriors; all-zero between rows
     float* wbuf = delta + p.row_floats;                                  // label-state weights of the current row
+    const bool stage = (sizeof(TIn) == 4) && p.stage;
+    if (stage) {         // per-warp layout with a staged row: delta | wbuf | rowbuf
+        delta = smem + (size_t)warp * (2 * p.row_floats + p.w_floats);
+        wbuf = delta + p.row_floats;
+    }
+    float* const rowbuf = wbuf + p.w_floats;                             // [row_floats] the current log-prob row (stage)
     for (int i = lane; i < p.row_floats; i += 32) delta[i] = 0.f;
     __syncwarp();
     const int WS = max(1, Wtot / p.B);                                   // warps per sample (static mapping)
@@ -1692,6 +1743,10 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
             TIn* grow = grad + (size_t)row * p.V;
             const int o_out = (int)((reinterpret_cast<uintptr_t>(grow) / sizeof(TIn)) & (kVec - 1));
             const TIn* lrow = lpbase + (int64_t)t * p.stride_t + (int64_t)b * p.stride_b;
+            int o_in_s = 0;
+            if constexpr (sizeof(TIn) == 4) {
+                if (stage) o_in_s = stage_row(reinterpret_cast<const float*>(lrow), p.V, rowbuf, lane);   // cp.async, one group
+            }
             if (pf_lines > 0 && t + pf_dist * step < t1) {    // a later row of this warp: pull its lines into L2 now
                 if (lane < pf_lines) {
                     const char* nx = reinterpret_cast<const char*>(lrow + (int64_t)pf_dist * step * p.stride_t) + lane * 128;
@@ -1721,10 +1776,19 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
                     cbv[j] = cbp[sm / K];
                 }
             }
-            const float xb = to_float(__ldg(lrow + p.blank)) * AVCTC_LOG2E;
-            float xl[KL];
+            float xb, xl[KL];
+            if (stage) {                 // the row has landed (its latency overlapped the alpha/beta loads above)
+                cp_async_wait<0>();
+                __syncwarp();
+                const float* row_s = rowbuf + o_in_s;
+                xb = row_s[p.blank] * AVCTC_LOG2E;
 #pragma unroll
-            for (int i = 0; i < KL; ++i) xl[i] = to_float(__ldg(lrow + cls[i])) * AVCTC_LOG2E;
+                for (int i = 0; i < KL; ++i) xl[i] = row_s[cls[i]] * AVCTC_LOG2E;
+            } else {
+                xb = to_float(__ldg(lrow + p.blank)) * AVCTC_LOG2E;
+#pragma unroll
+                for (int i = 0; i < KL; ++i) xl[i] = to_float(__ldg(lrow + cls[i])) * AVCTC_LOG2E;
+            }
             float w[K];
 #pragma unroll
             for (int j = 0; j < K; ++j) {
@@ -1762,8 +1826,19 @@ __global__ void __launch_bounds__(256, (K <= 8) ? 4 : 1) ctc_grad_lin_kernel(con
             }
             if (lane == 0) delta[o_out + p.blank] = pbs;
             __syncwarp();
-            if (scale > 0.f) grad_stream_row<TIn, true>(lrow, grow, p.V, delta, o_out, scale, lscale, lane);
-            else grad_stream_row<TIn, false>(lrow, grow, p.V, delta, o_out, scale, lscale, lane);
+            bool streamed = false;
+            if constexpr (sizeof(TIn) == 4) {
+                if (stage) {
+                    float* g32 = reinterpret_cast<float*>(grow);
+                    if (scale > 0.f) grad_stream_row_smem<true>(rowbuf + o_in_s, o_in_s, g32, p.V, delta, o_out, scale, lscale, lane);
+                    else grad_stream_row_smem<false>(rowbuf + o_in_s, o_in_s, g32, p.V, delta, o_out, scale, lscale, lane);
+                    streamed = true;
+                }
+            }
+            if (!streamed) {
+                if (scale > 0.f) grad_stream_row<TIn, true>(lrow, grow, p.V, delta, o_out, scale, lscale, lane);
+                else grad_stream_row<TIn, false>(lrow, grow, p.V, delta, o_out, scale, lscale, lane);
+            }
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < KL; ++i)
@@ -1972,7 +2047,8 @@ static int launch_grad(const GradParams& gp_in, cudaStream_t st) {
 template <int K, typename TIn>
 static int launch_grad_lin(const GradParams& gp, cudaStream_t st) {
     const int warps = 8;
-    const size_t smem = (size_t)(gp.row_floats + gp.w_floats) * sizeof(float) * warps;
+    const bool stage = (sizeof(TIn) == 4) && gp.stage;
+    const size_t smem = (size_t)((stage ? 2 : 1) * gp.row_floats + gp.w_floats) * sizeof(float) * warps;
     if (smem > 200 * 1024) return AVCTC_ERR_UNSUPPORTED;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
@@ -2124,6 +2200,7 @@ extern "C" int avctc_ctc_backward(const void* log_probs, int dtype, int64_t stri
     gp.K = pl.K; gp.W = pl.W; gp.S_pad = pl.S_pad; gp.Lpad = pl.Lpad; gp.linear = pl.linear;
     gp.cw = pl.CW; gp.flag = nullptr; gp.run_if = 0; gp.done = nullptr; gp.stamp = avctc_tuning_get("ctc_stamp", 0);
     gp.prefetch = avctc_tuning_get("ctc_pf", 1);
+    gp.stage = avctc_tuning_get("ctc_stage", 1);
     gp.row_floats = (V + 8 + 3) & ~3;
     gp.w_floats = (2 * max_target_len + 1 + 3) & ~3;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
