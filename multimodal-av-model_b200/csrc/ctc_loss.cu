@@ -1481,39 +1481,33 @@ template <bool POS>
 __device__ __forceinline__ void grad_stream_row_smem(const float* __restrict__ row_s, int o_in, float* __restrict__ grow,
                                                      int V, const float* __restrict__ delta, int o_out, float scale,
                                                      float lscale, int lane) {
-    const int nq = (o_out + V + 3) / 4;
-    const bool same = (o_in == o_out);           // then row_s + c0 is 16-byte aligned whenever grow + c0 is
-    for (int q = lane; q < nq; q += 32) {
-        const int c0 = q * 4 - o_out;
-        const bool full = (c0 >= 0) && (c0 + 4 <= V);
-        float x[4];
-        if (full && same) {
+    // 16-byte chunk q of the OUTPUT row covers classes c0 = 4q - o_out .. c0 + 3.  Chunks [q_lo, q_hi) are complete
+    // (no bounds predicates in the loop); the at most two ragged ones at the ends are left to one lane each.
+    const int q_lo = (o_out + 3) >> 2, q_hi = (o_out + V) >> 2;
+    auto one = [&](float x, float d) -> float {
+        const float e = ex2_approx(fmaf(x, AVCTC_LOG2E, lscale));          // |scale| * exp(lp)
+        return POS ? fmaf(d, -scale, e) : -fmaf(d, scale, e);
+    };
+    if (o_in == o_out) {                         // row_s + c0 is 16-byte aligned whenever grow + c0 is
+        for (int q = q_lo + lane; q < q_hi; q += 32) {
+            const int c0 = q * 4 - o_out;
             const float4 v = *reinterpret_cast<const float4*>(row_s + c0);
-            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int c = c0 + k;
-                x[k] = (c >= 0 && c < V) ? row_s[c] : 0.f;
-            }
+            const float4 d = *reinterpret_cast<const float4*>(delta + q * 4);
+            __stcs(reinterpret_cast<float4*>(grow + c0), make_float4(one(v.x, d.x), one(v.y, d.y), one(v.z, d.z), one(v.w, d.w)));
         }
-        const float4 d = *reinterpret_cast<const float4*>(delta + q * 4);
-        const float dd[4] = {d.x, d.y, d.z, d.w};
-        float o[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float e = ex2_approx(fmaf(x[k], AVCTC_LOG2E, lscale));   // |scale| * exp(lp)
-            o[k] = POS ? fmaf(dd[k], -scale, e) : -fmaf(dd[k], scale, e);
+    } else {
+        for (int q = q_lo + lane; q < q_hi; q += 32) {
+            const int c0 = q * 4 - o_out;
+            const float4 d = *reinterpret_cast<const float4*>(delta + q * 4);
+            __stcs(reinterpret_cast<float4*>(grow + c0),
+                   make_float4(one(row_s[c0], d.x), one(row_s[c0 + 1], d.y), one(row_s[c0 + 2], d.z), one(row_s[c0 + 3], d.w)));
         }
-        if (full) {
-            __stcs(reinterpret_cast<float4*>(grow + c0), make_float4(o[0], o[1], o[2], o[3]));
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int c = c0 + k;
-                if (c >= 0 && c < V) grow[c] = o[k];
-            }
-        }
+    }
+    if (lane == 0 && o_out > 0) {                // ragged head: classes 0 .. 3 - o_out of chunk 0
+        for (int c = 0; c < 4 - o_out && c < V; ++c) grow[c] = one(row_s[c], delta[o_out + c]);
+    }
+    if (lane == 1 && ((o_out + V) & 3) && q_hi >= q_lo) {      // ragged tail: chunk q_hi
+        for (int c = max(q_hi * 4 - o_out, (o_out > 0) ? 4 - o_out : 0); c < V; ++c) grow[c] = one(row_s[c], delta[o_out + c]);
     }
 }
 
