@@ -473,6 +473,7 @@ static bool ldims(int B, int T, int In, int H, LDims* d) {
     if (knob > 0) G = knob;
     else if (B > 8) G = max_groups < 2 ? 1 : (B > 32 && max_groups >= 4 ? 4 : 2);
     if (G > max_groups) G = max_groups;
+    while ((B + G - 1) / G > 32 && G < max_groups) ++G;        // a group holds at most 32 sequences (knob or not)
     if (G > B) G = B;
     const int Bg = (B + G - 1) / G;
     if (Bg > 32) return false;
