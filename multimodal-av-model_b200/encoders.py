@@ -214,6 +214,14 @@ class AudioEncoder(nn.Module):
             _install_feature_cache(fe)
         fe(x)
 
+    def begin_step(self):
+        """Forget the cached feature-extractor output.  The cache exists to serve the SECOND call of a step (the reference
+        runs the audio encoder once per speaker on the same waveform, trainer.py:94-95); a batch tensor that is kept
+        resident and fed again in the next step must be encoded again, as it would be with any fresh batch."""
+        st = getattr(getattr(self.model, "feature_extractor", None), "_avctc_cache_state", None)
+        if st is not None:
+            st["ref"] = None
+
     def _layer_segment(self, layer):
         seg = getattr(layer, "_avctc_graph_seg", None)
         if seg is None:
@@ -321,6 +329,7 @@ def _install_feature_cache(fe):
 
     fe.forward = cached_forward
     fe._avctc_cached = True
+    fe._avctc_cache_state = state
 
 
 def install_frozen_cast_cache(root):
