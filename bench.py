@@ -625,13 +625,16 @@ def bench_infonce(device, peaks, iters=10):
                 loss = loss + 0.3 * (-F.log_softmax(weak @ neg.T / 0.07, dim=-1)).mean()
             loss.backward()
     t, _ = event_time(ours, iters, 3, flush, device)
+    t_q, _ = event_time_queued(ours, iters, 2, flush, device, hold_cycles=1400000)
     t_stock, _ = event_time(stock, iters, 3, flush, device)
     rows = x.shape[0] * x.shape[1]
     alg = rows * 1024 * 2 + 128 * 1024 * 4
-    return dict(rows=rows, fwd_bwd_ms=t, torch_cuda_ms=t_stock, speedup_vs_torch_cuda=t_stock / t, algorithmic_bytes=alg,
-                gbs=alg / t / 1e6, hbm_frac=alg / t / 1e6 / peaks["hbm"],
-                note="eager Python op (projection GEMM + fused normalise/pair kernels, fwd+bwd); 4.6 MB of input is ~1 us of "
-                     "HBM time, so the op is launch-latency bound at the reference's batch size")
+    return dict(rows=rows, fwd_bwd_ms=t, queued_fwd_bwd_ms=t_q, torch_cuda_ms=t_stock, speedup_vs_torch_cuda=t_stock / t,
+                algorithmic_bytes=alg, gbs=alg / t / 1e6, hbm_frac=alg / t / 1e6 / peaks["hbm"],
+                note="fwd_bwd_ms: eager Python op from an idle GPU (projection GEMM + fused normalise/pair kernels, fwd+bwd); "
+                     "queued_fwd_bwd_ms: the same call with the launch queue pre-filled = device time of its kernels; 4.6 MB of "
+                     "input is ~1 us of HBM time, so the op is launch-latency bound at the reference's batch size; in the train "
+                     "step both speakers' losses run on a side stream under the BiLSTM kernels")
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
