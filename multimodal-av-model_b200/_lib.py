@@ -146,6 +146,27 @@ def stream_ptr(device) -> int:
     return torch._C._cuda_getCurrentRawStream(idx)
 
 
+class _NoSwitch:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def device_guard(device):
+    """`with device_guard(dev):` = torch.cuda.device(dev), without the two device switches (and ~8 us of Python) when
+    `dev` already is the current device — the case for every call of a one-process-per-GPU job."""
+    import torch
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_SWITCH
+    return torch.cuda.device(device)
+
+
 def require_cuda(t, name: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor: the AV-CTC hot path has no CPU implementation "

@@ -45,7 +45,7 @@ def beam_search_batch(log_probs, beam_width: int = 5, blank: int = 0, lengths=No
     dbg_p = torch.zeros((N, k, max(T, 1)), dtype=torch.int32, device=dev) if return_debug else None
     if lengths is not None:
         lengths = torch.as_tensor(lengths).to(device=dev, dtype=torch.long).contiguous()
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.check(L.avctc_beam_search(
             lp.data_ptr(), lp.stride(0), lp.stride(1), N, T, V,
             lengths.data_ptr() if lengths is not None else None, k, int(blank),

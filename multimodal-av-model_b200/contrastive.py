@@ -42,7 +42,7 @@ class _InfoNCEFn(torch.autograd.Function):
         ws_bytes = int(L.avctc_infonce_workspace_bytes(N, P))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(L.avctc_infonce_forward(yd.data_ptr(), _lib.dtype_enum(yd), yd.stride(0), mask.data_ptr(), N, P,
                                                float(temperature), float(w_pos), float(w_neg), loss.data_ptr(),
                                                ws.data_ptr(), ws_bytes, _lib.stream_ptr(dev)), "avctc_infonce_forward")
@@ -58,7 +58,7 @@ class _InfoNCEFn(torch.autograd.Function):
         go = gout.detach().float().reshape(1).contiguous()
         out_dtype = ydtype if ydtype in (torch.float32, torch.bfloat16) else torch.float32
         dy = torch.empty((N, P), dtype=out_dtype, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(_lib.lib().avctc_infonce_backward(mask.data_ptr(), N, P, temperature, w_pos, w_neg, go.data_ptr(),
                                                          dy.data_ptr(), _lib.dtype_enum(dy), P, ws.data_ptr(), ws_bytes,
                                                          _lib.stream_ptr(dev)), "avctc_infonce_backward")

@@ -62,7 +62,7 @@ class _CTCLossFn(torch.autograd.Function):
         grad = None
         out = torch.empty(B if red == 0 else 1, dtype=torch.float32, device=dev)
         off_ptr = offsets.data_ptr() if offsets is not None else None
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             if need_grad:
                 # The gradient pass goes out NOW, directly behind the scan, with a unit grad_out: launched there it
                 # starts on each utterance as soon as that utterance's alpha/beta rows are complete, under the scans of
@@ -97,7 +97,7 @@ class _CTCLossFn(torch.autograd.Function):
         dev = grad.device
         go = grad_out.detach().to(torch.float32).contiguous()
         gstride = 0 if go.numel() == 1 else 1
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(_lib.lib().avctc_ctc_scale_grad(grad.data_ptr(), _lib.dtype_enum(grad), T, B, V, go.data_ptr(),
                                                        gstride, _lib.stream_ptr(dev)), "avctc_ctc_scale_grad")
         return grad, None, None, None, None, None, None

@@ -42,7 +42,7 @@ class _CTCHeadFn(torch.autograd.Function):
         L = _lib.lib()
         lp = torch.empty((M, V), dtype=torch.float32, device=dev)
         fused = V <= 1024
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             if fused:
                 _lib.check(L.avctc_ctc_head_forward(xb.data_ptr(), wb.data_ptr(), bf.data_ptr(), M, V, D, lp.data_ptr(),
                                                     int(passes), _lib.stream_ptr(dev)), "avctc_ctc_head_forward")
@@ -72,7 +72,7 @@ class _CTCHeadFn(torch.autograd.Function):
         g_b = torch.empty(V, dtype=torch.float32, device=dev)
         dz = torch.empty((M, Vp), dtype=_BF16, device=dev)
         dxb = torch.empty((M, D), dtype=_BF16, device=dev) if ctx.needs_input_grad[0] else None
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(_lib.lib().avctc_ctc_head_backward(lp.data_ptr(), dy.data_ptr(), xb.data_ptr(), wb.data_ptr(), M, V, D,
                                                           dz.data_ptr(), g_w.data_ptr(), g_b.data_ptr(),
                                                           dxb.data_ptr() if dxb is not None else None,

@@ -78,7 +78,7 @@ def _colsum(x, out=None):
     M, N = x.shape
     if out is None:
         out = torch.empty(N, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _lib.device_guard(x.device):
         _lib.check(_lib.lib().avctc_colsum(x.data_ptr(), _lib.dtype_enum(x), M, N, x.stride(0), out.data_ptr(), 0,
                                            _lib.stream_ptr(x.device)), "avctc_colsum")
     return out
@@ -115,7 +115,7 @@ class _FusionCoreFnPy(torch.autograd.Function):
         input_lengths = torch.empty(B, dtype=torch.long, device=dev)
         rs_bytes = int(L.avctc_resample_workspace_bytes(B, Ta))
         rs_ws = torch.empty(rs_bytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(L.avctc_resample_forward(audio_c.data_ptr(), _lib.dtype_enum(audio_c), mask_c.data_ptr(), B, Ta, Da,
                                                 T, xa.data_ptr(), mask_out.data_ptr(), input_lengths.data_ptr(),
                                                 rs_ws.data_ptr(), rs_bytes, st), "avctc_resample_forward")
@@ -150,7 +150,7 @@ class _FusionCoreFnPy(torch.autograd.Function):
         gemm(operand(q, k_inner=hd, r_outer=T), operand(kv, k_inner=hd, r_outer=T), T, T, hd, S, batch=BH,
              inner_count=H, ldc=Tp, c_outer=H * T * Tp, c_inner=T * Tp, alpha=alpha)
         P = torch.empty((BH, T, Tp), dtype=_BF16, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(L.avctc_softmax_forward(S.data_ptr(), P.data_ptr(), BH * T, T, Tp, st), "avctc_softmax_forward")
         o = torch.empty((M, E), dtype=_BF16, device=dev)
         vv = kv[:, E:]
@@ -188,7 +188,7 @@ class _FusionCoreFnPy(torch.autograd.Function):
         gemm(operand(do, k_inner=hd, r_outer=T), operand(vv, k_inner=hd, r_outer=T), T, T, hd, dP, batch=BH,
              inner_count=H, ldc=Tp, c_outer=H * T * Tp, c_inner=T * Tp)
         dS = torch.empty((BH, T, Tp), dtype=_BF16, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(L.avctc_softmax_backward(P.data_ptr(), dP.data_ptr(), dS.data_ptr(), BH * T, T, Tp, st),
                        "avctc_softmax_backward")
         dq = torch.empty((M, E), dtype=_BF16, device=dev)
@@ -219,7 +219,7 @@ class _FusionCoreFnPy(torch.autograd.Function):
             dxa = _dgrad(da, wb_ap)
             out_dtype = audio_dtype if audio_dtype in (torch.float32, _BF16) else torch.float32
             d_audio = torch.empty((B, Ta, Da), dtype=out_dtype, device=dev)
-            with torch.cuda.device(dev):
+            with _lib.device_guard(dev):
                 _lib.check(L.avctc_resample_backward(dxa.data_ptr(), B, Ta, Da, T, rs_ws.data_ptr(), d_audio.data_ptr(),
                                                      _lib.dtype_enum(d_audio), st), "avctc_resample_backward")
             d_audio = d_audio.to(audio_dtype)
@@ -276,7 +276,7 @@ class _FusionCoreFn(torch.autograd.Function):
         out = torch.empty((B, T, E), dtype=out_dtype, device=dev)
         mask_out = torch.empty((B, T), dtype=torch.long, device=dev)
         input_lengths = torch.empty(B, dtype=torch.long, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(L.avctc_fusion_forward(xv.data_ptr(), audio_c.data_ptr(), _lib.dtype_enum(audio_c), mask_c.data_ptr(),
                                               *[t.data_ptr() for t in ws], B, T, Ta, Dv, Da, E, H, out.data_ptr(),
                                               _lib.dtype_enum(out), mask_out.data_ptr(), input_lengths.data_ptr(),
@@ -316,7 +316,7 @@ class _FusionCoreFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             d_audio = torch.empty((B, Ta, Da), dtype=audio_dtype if audio_dtype in (torch.float32, _BF16) else torch.float32,
                                   device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(L.avctc_fusion_backward(dfc.data_ptr(), _lib.dtype_enum(dfc), xv.data_ptr(), B, T, Ta, Dv, Da, E, H,
                                                *[t.data_ptr() for t in g],
                                                d_visual.data_ptr() if d_visual is not None else None,
@@ -353,7 +353,7 @@ class _BiLSTMFn(torch.autograd.Function):
         scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
         y = torch.empty((B, T, 2 * H), dtype=_BF16, device=dev)
         ptrs = (ctypes.c_void_p * 16)(*[w.data_ptr() for w in ws])
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(L.avctc_bilstm_forward(xb.data_ptr(), B, T, In, H, ptrs, y.data_ptr(), saved.data_ptr(), saved_bytes,
                                               scratch.data_ptr(), scratch_bytes, int(need_grad), _lib.stream_ptr(dev)),
                        "avctc_bilstm_forward")
@@ -373,7 +373,7 @@ class _BiLSTMFn(torch.autograd.Function):
         scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
         dx = torch.empty((B, T, In), dtype=_BF16, device=dev) if ctx.needs_input_grad[0] else None
         ptrs = (ctypes.c_void_p * 16)(*[g.data_ptr() for g in grads])
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(L.avctc_bilstm_backward(dyb.data_ptr(), xb.data_ptr(), B, T, In, H, ptrs,
                                                dx.data_ptr() if dx is not None else None, saved.data_ptr(), saved_bytes,
                                                scratch.data_ptr(), scratch_bytes, _lib.stream_ptr(dev)),

@@ -47,7 +47,7 @@ def gemm(a, b, M, N, K, out: torch.Tensor, *, batch=1, inner_count=1, ldc=None, 
     if bias is not None and bias.dtype != torch.float32:
         raise RuntimeError("bias must be float32")
     dev = out.device
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.check(_lib.lib().avctc_gemm_bf16(
             ctypes.byref(opa), ctypes.byref(opb), int(M), int(N), int(K), int(batch), int(inner_count),
             out.data_ptr(), _lib.dtype_enum(out), int(ldc), int(c_outer), int(c_inner),
@@ -93,7 +93,7 @@ class LinearFn(torch.autograd.Function):
         g_b = None
         if has_b:
             g_b = torch.empty(N, dtype=torch.float32, device=dev)
-            with torch.cuda.device(dev):
+            with _lib.device_guard(dev):
                 _lib.check(_lib.lib().avctc_colsum(d.data_ptr(), _lib.BF16, M, N, N, g_b.data_ptr(), 0,
                                                    _lib.stream_ptr(dev)), "avctc_colsum")
         dx = None

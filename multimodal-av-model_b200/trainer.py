@@ -60,7 +60,7 @@ def _log_softmax_again(lp):
     x = lp.detach().float().contiguous()
     out = torch.empty_like(x)
     V = x.shape[-1]
-    with torch.cuda.device(x.device):
+    with _lib.device_guard(x.device):
         _lib.check(_lib.lib().avctc_log_softmax_forward(x.data_ptr(), _lib.F32, out.data_ptr(), _lib.F32, x.numel() // V, V,
                                                         _lib.stream_ptr(x.device)), "avctc_log_softmax_forward")
     return out
