@@ -121,7 +121,8 @@ class VisualEncoder(nn.Module):
         seg = getattr(self, "_graph_seg", None)
         if seg is None:
             from .graphed import GraphedSegment
-            seg = self._graph_seg = GraphedSegment(self._forward_impl, list(self.parameters()), list(self.buffers()))
+            seg = self._graph_seg = GraphedSegment(self._forward_impl, list(self.parameters()), list(self.buffers()),
+                                                   modules=list(self.modules()))
         if seg.usable(x):
             return seg(x)
         return self._forward_impl(x)
@@ -227,7 +228,7 @@ class AudioEncoder(nn.Module):
         if seg is None:
             from .graphed import GraphedSegment
             seg = GraphedSegment(lambda h, m: layer(h, attention_mask=m, output_attentions=False)[0],
-                                 list(layer.parameters()), max_entries=4)
+                                 list(layer.parameters()), max_entries=4, modules=list(layer.modules()))
             object.__setattr__(layer, "_avctc_graph_seg", seg)
         return seg
 
@@ -309,7 +310,7 @@ def _install_feature_cache(fe):
     from .graphed import GraphedSegment
     inner = fe.forward
     state = {"ref": None, "key": None, "out": None}
-    seg = GraphedSegment(inner, list(fe.parameters()))      # seven conv + norm + GELU layers: one graph launch
+    seg = GraphedSegment(inner, list(fe.parameters()), modules=list(fe.modules()))   # 7 x (conv, norm, GELU): one graph launch
 
     def cached_forward(input_values):
         frozen = not any(p.requires_grad for p in fe.parameters()) and not getattr(fe, "_requires_grad", False)

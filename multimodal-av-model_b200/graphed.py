@@ -26,17 +26,21 @@ def _sig(t):
 
 class GraphedSegment:
     """fn(*tensors) -> tensor, captured per input signature.  `params` are the parameters fn reads (all must be frozen),
-    `buffers` the buffers it updates in place (restored after the capture warm-up so warm-up runs leave no trace)."""
+    `buffers` the buffers it updates in place (restored after the capture warm-up so warm-up runs leave no trace),
+    `modules` the modules whose train/eval mode changes what fn launches."""
 
-    def __init__(self, fn, params, buffers=(), max_entries=6, warmup=2):
+    def __init__(self, fn, params, buffers=(), max_entries=6, warmup=2, modules=()):
         self.fn = fn
         self.params = list(params)
         self.buffers = list(buffers)
+        self.modules = list(modules)           # their train/eval flags are part of the signature (BatchNorm, dropout)
         self.max_entries = max_entries
         self.warmup = warmup
         self.cache = collections.OrderedDict()
+        self.seen = collections.OrderedDict()      # signature -> times met without a graph (bounded)
         self.replays = 0
         self.captures = 0
+        self.eager = 0
 
     def usable(self, *inputs):
         if not _lib.tuning_enabled("enc_graphs"):
@@ -52,11 +56,26 @@ class GraphedSegment:
         dev = next(t for t in inputs if t is not None).device
         key = (tuple(_sig(t) for t in inputs), torch.is_autocast_enabled(),
                torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else None,
-               sum(p._version for p in self.params), tuple(p.data_ptr() for p in self.params[:4]))
+               sum(p._version for p in self.params), tuple(p.data_ptr() for p in self.params[:4]),
+               tuple(m.training for m in self.modules))
         ent = self.cache.get(key)
         if ent is None:
+            # A capture costs `warmup` + 1 extra runs of the segment, so it must pay for itself: a signature is captured
+            # the SECOND time it is met (padded batch shapes of a real data loader vary; a shape seen once may never
+            # return), and capturing stops altogether while past captures were replayed less than four times each.
+            n = self.seen.get(key, 0)
+            thrashing = self.captures >= 8 and self.replays < 4 * self.captures
+            if n < 1 or thrashing:
+                self.seen[key] = n + 1
+                self.seen.move_to_end(key)
+                while len(self.seen) > 64:
+                    self.seen.popitem(last=False)
+                self.eager += 1
+                with torch.no_grad():
+                    return self.fn(*inputs)
             ent = self._capture(inputs, dev)
             self.cache[key] = ent
+            self.seen.pop(key, None)
             while len(self.cache) > self.max_entries:
                 self.cache.popitem(last=False)
         else:
