@@ -222,6 +222,11 @@ class MultimodalTrainer:
         st = getattr(self, "_aux_stream", None)
         if st is None or st.device != ref.device:
             st = self._aux_stream = torch.cuda.Stream(device=ref.device)
+            # the projection layer's gradients are produced on the side stream and accumulated by nodes created on the
+            # main stream: intended (autograd synchronises the two), so the advisory warning about it is switched off
+            quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+            if quiet is not None:
+                quiet(False)
         return st
 
     def _ensure_projection(self, D):
