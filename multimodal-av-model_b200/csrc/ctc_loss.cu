@@ -989,6 +989,7 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(prog + 128);  // [2][NG] rows landed ("full")
     unsigned long long* mbar_empty = mbar + 2 * NG;                                // [2][NG] rows consumed ("empty")
     __shared__ double fin[2];
+    __shared__ int tgt_s[256];            // clamped labels of the sample (the probability-domain plan has 2L+1 <= 512)
 
     long long tbl = p.input_lengths[b];
     long long tll = p.target_lengths[b];
@@ -1195,6 +1196,25 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
 
     if (warp == 3) {
         // ================================================================ writer
+        // Repeated-label chains for the gradient pass (which label positions share a class: deterministic per-class
+        // posterior sums).  They depend on the targets only, so they are built here, while the row pipeline fills and
+        // this warp has nothing to write yet — not by the recurrence warp behind its last frame, where every sample
+        // paid for them (~L^2/32 global loads) on its critical path.
+        if (dir == 0 && p.chain) {
+            for (int j = lane; j < L; j += 32) {
+                const long long c = tgt[j];
+                tgt_s[j] = (int)(c < 0 ? 0 : (c >= p.V ? p.V - 1 : c));
+            }
+            __syncwarp();
+            for (int j = lane; j < L; j += 32) {
+                const int c = tgt_s[j];
+                bool first = true;
+                for (int k = 0; k < j; ++k) if (tgt_s[k] == c) { first = false; break; }
+                int nxt = kChainNone;
+                for (int k = j + 1; k < L; ++k) if (tgt_s[k] == c) { nxt = k; break; }
+                p.chain[(size_t)b * p.Lpad + j] = nxt | (first ? kChainFirst : 0);
+            }
+        }
         if (!do_store || Tb < 2) { signal_done(p.done, b, lane, 1); return; }
         const size_t rowi1 = (size_t)b * p.T + (dir ? Tb - 2 : 1);       // scan frame 1
         float* wsp = (dir ? p.beta : p.alpha) + rowi1 * p.S_pad + (size_t)g * K;
@@ -1367,15 +1387,16 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
         const int tau = base + u;
         if (tau < Tb) frame(tau, (1 + u) & (RD - 1), (u / G) & 1, (u & 1) == 1, 1);
     }
+    if (dir == 0) {      // only the last two lattice states enter the likelihood: the fp64 logarithm runs for them alone
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-        const int st = g * K + j;
-        const double tv = (a[j] > 0.f) ? log2((double)a[j]) + (double)C : -(double)CUDART_INF_F;
-        if (st == S - 1) fin[0] = tv;
-        if (st == S - 2) fin[1] = tv;
-    }
-    __syncwarp();
-    if (dir == 0) {
+        for (int j = 0; j < K; ++j) {
+            const int st = g * K + j;
+            if (st == S - 1 || st == S - 2) {
+                const double tv = (a[j] > 0.f) ? log2((double)a[j]) + (double)C : -(double)CUDART_INF_F;
+                fin[st == S - 1 ? 0 : 1] = tv;
+            }
+        }
+        __syncwarp();
         if (lane == 0) {
             const double x = fin[0], y = fin[1];
             const double m = fmax(x, y), n = fmin(x, y);
@@ -1385,18 +1406,8 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
             p.nll[b] = (float)(-ll2 * AVCTC_LN2_D);
             if (p.nll2) p.nll2[b] = -ll2;
         }
-        if (p.chain) {
-            for (int j = lane; j < L; j += 32) {
-                const long long c = tgt[j];
-                bool first = true;
-                for (int k = 0; k < j; ++k) if (tgt[k] == c) { first = false; break; }
-                int nxt = kChainNone;
-                for (int k = j + 1; k < L; ++k) if (tgt[k] == c) { nxt = k; break; }
-                p.chain[(size_t)b * p.Lpad + j] = nxt | (first ? kChainFirst : 0);
-            }
-        }
     }
-    signal_done(p.done, b, lane, 1);              // frame 0, nll and the repeat chains are in memory
+    signal_done(p.done, b, lane, 1);              // frame 0 and nll are in memory (the writer warp signals rows + chains)
     if (p.stamp && p.flag && lane == 0) stamp_max(p.flag, 1);
 }
 
