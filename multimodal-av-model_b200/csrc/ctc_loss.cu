@@ -135,6 +135,12 @@ __device__ __forceinline__ void stamp_max(int* flag, int slot) {
     unsigned long long* s = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(flag) + 64) + slot;
     atomicMax(s, global_timer_ns());
 }
+// debug: maximum over CTAs of a duration (ns); slots 4..7 and 10..13 of the same block (8, 9 are the gradient pass's
+// control words)
+__device__ __forceinline__ void stamp_dur(int* flag, int slot, unsigned long long ns) {
+    unsigned long long* s = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(flag) + 64) + slot;
+    atomicMax(s, ns);
+}
 __device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -1159,7 +1165,10 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
                         mx = fmaxf(mx, xl[i]);
                         mn = fminf(mn, raw - ninf_l[i]);          // invalid states contribute +inf
                     }
-                    risky |= (mx - mn > kLinSafeRange);            // p of some class would leave fp32's safe range
+                    // p of some class would leave fp32's safe range: raise the guard flag NOW, before this frame is handed to
+                    // the recurrence -- the sample cannot be reported complete (done[b]) with the store still pending, and
+                    // the gradient pass / the guarded twins read the flag long after that
+                    if (mx - mn > kLinSafeRange && !risky) { risky = true; if (p.flag) *p.flag = 1; }
                     const float ms = mx * AVCTC_LOG2E;
                     const float Ef = (ms > -1.0e29f) ? floorf(ms) : 0.f;
                     const float pblank = ex2_approx(fmaf(xb, AVCTC_LOG2E, -Ef));
@@ -1190,7 +1199,6 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
             if (lane == 0) ws_mbar_arrive(ws_smem_u32(&mbar_empty[pw * NG + sl]));   // the DMA warp may refill the slot
             if (++sl == NG) { sl = 0; par ^= 1u; }
         }
-        if (risky && p.flag) *p.flag = 1;     // the host's conditional log-domain launches redo this batch
         return;
     }
 
@@ -1252,6 +1260,7 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
     }
 
     // ==================================================================== recurrence (warp 2)
+    const unsigned long long tm0 = p.stamp ? global_timer_ns() : 0ull;
     float skipf[KL];
 #pragma unroll
     for (int i = 0; i < KL; ++i) {
@@ -1376,6 +1385,7 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
         asm volatile("" ::: "memory");
         st_volatile_shared_s32(&prog[64 + lane], tau + 1);
     };
+    const unsigned long long tm1 = p.stamp ? global_timer_ns() : 0ull;
     int base = 1;
 #pragma unroll 1
     for (; base + 2 * G <= Tb; base += 2 * G) {          // full groups: no bounds checks on the chain
@@ -1387,6 +1397,7 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
         const int tau = base + u;
         if (tau < Tb) frame(tau, (1 + u) & (RD - 1), (u / G) & 1, (u & 1) == 1, 1);
     }
+    const unsigned long long tm2 = p.stamp ? global_timer_ns() : 0ull;
     if (dir == 0) {      // only the last two lattice states enter the likelihood: the fp64 logarithm runs for them alone
 #pragma unroll
         for (int j = 0; j < K; ++j) {
@@ -1408,7 +1419,14 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
         }
     }
     signal_done(p.done, b, lane, 1);              // frame 0 and nll are in memory (the writer warp signals rows + chains)
-    if (p.stamp && p.flag && lane == 0) stamp_max(p.flag, 1);
+    if (p.stamp && p.flag && lane == 0) {
+        stamp_max(p.flag, 1);
+        const unsigned long long tm3 = global_timer_ns();
+        stamp_dur(p.flag, 4, tm1 - tm0);                       // prologue of the recurrence warp
+        stamp_dur(p.flag, 5, tm3 - tm2);                       // epilogue (likelihood, fence, counter)
+        stamp_dur(p.flag, 6, (tm2 - tm1) * 1000ull / (unsigned long long)(Tb > 1 ? Tb - 1 : 1));   // ps per frame
+        stamp_dur(p.flag, 7, tm2 - tm1);                       // longest frame loop
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1533,6 +1551,7 @@ __global__ void __launch_bounds__(256, (K <= 8) ? (sizeof(TIn) == 4 ? 3 : 4) : 1
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     pdl_launch_dependents();
+    const unsigned long long tg0 = p.stamp ? global_timer_ns() : 0ull;
     // Launched with the PDL attribute, this grid can be resident while the scan before it on the stream is still
     // running (backward enqueued right behind forward).  If every sample's completion counter is already full the
     // kernel takes the ordinary route: griddepcontrol.wait, after which everything before it on the stream (scan,
@@ -1547,23 +1566,42 @@ __global__ void __launch_bounds__(256, (K <= 8) ? (sizeof(TIn) == 4 ? 3 : 4) : 1
     // Control words in the flag block (zeroed by avctc_ctc_forward, re-zeroed by the last warp of this grid):
     // int[32] mode (0 undecided, 1 ordinary, 2 early; the first CTA decides for the grid), int[33] next ticket,
     // int[34] CTAs finished, int[35] next ticket of the zero rows.
-    __shared__ int early_s, chunk_s, warps_left_s;
+    __shared__ int early_s, chunk_s, warps_left_s, zdrawn_s;
     __shared__ int tb_s[kSpreadMaxB], order_s[kSpreadMaxB], start_s[kSpreadMaxB + 1], zstart_s[kSpreadMaxB + 1];
     int* const ctrl = p.done ? const_cast<int*>(p.flag) + 32 : nullptr;
+    // A CTA that becomes resident only when the scan CTAs leave starts on a saturated memory system, where every
+    // dependent global round trip costs microseconds of the tail: its independent loads (input lengths, the mode word,
+    // the zero-row ticket counter) are issued together here, and a mode that is already decided is taken as it is.
+    const bool spread_ok = ctrl && p.B <= kSpreadMaxB;
+    int mine = 0;
+    if (spread_ok && (int)threadIdx.x < p.B) {
+        const long long v = p.input_lengths[threadIdx.x];
+        mine = (int)(v < 0 ? 0 : (v > p.T ? p.T : v));
+    }
     if (threadIdx.x < 32) {
         int mode = 1;
-        if (ctrl && p.B <= kSpreadMaxB) {
-            bool all = true;
-            for (int i = lane; i < p.B; i += 32) all = all && (ld_acquire_gpu_s32(p.done + i) >= kDoneTarget);
-            all = __all_sync(kFullMask, all);
-            if (lane == 0) {
-                const int want = all ? 1 : 2;
-                const int old = atomicCAS(ctrl, 0, want);
-                mode = old ? old : want;
+        if (spread_ok) {
+            int seen = 0;
+            if (lane < 2) seen = *reinterpret_cast<const volatile int*>(ctrl + (lane ? 3 : 0));
+            const int decided = __shfl_sync(kFullMask, seen, 0);
+            const int zdrawn = __shfl_sync(kFullMask, seen, 1);
+            if (decided) {
+                mode = decided;
+            } else {
+                bool all = true;
+                for (int i = lane; i < p.B; i += 32) all = all && (ld_acquire_gpu_s32(p.done + i) >= kDoneTarget);
+                all = __all_sync(kFullMask, all);
+                if (lane == 0) {
+                    const int want = all ? 1 : 2;
+                    const int old = atomicCAS(ctrl, 0, want);
+                    mode = old ? old : want;
+                }
             }
+            if (lane == 0) zdrawn_s = zdrawn;
         }
         if (lane == 0) { early_s = (mode == 2) ? 1 : 0; warps_left_s = nwarp; }
     }
+    if (spread_ok && (int)threadIdx.x < p.B) tb_s[threadIdx.x] = mine;
     __syncthreads();
     const bool early = early_s != 0;
     const int gw = blockIdx.x * nwarp + warp, Wtot = gridDim.x * nwarp;
@@ -1586,13 +1624,6 @@ __global__ void __launch_bounds__(256, (K <= 8) ? (sizeof(TIn) == 4 ? 3 : 4) : 1
     };
     if (use_spread) {
         const int tid = threadIdx.x;
-        int mine = 0;
-        if (tid < p.B) {
-            const long long v = p.input_lengths[tid];
-            mine = (int)(v < 0 ? 0 : (v > p.T ? p.T : v));
-            tb_s[tid] = mine;
-        }
-        __syncthreads();
         if (tid < p.B) {
             int R = 0;
             for (int j = 0; j < p.B; ++j) R += tb_s[j];
@@ -1671,7 +1702,7 @@ __global__ void __launch_bounds__(256, (K <= 8) ? (sizeof(TIn) == 4 ? 3 : 4) : 1
     // no sample is complete yet)
     if (early) {
         const int nz = zstart_s[p.B];
-        for (;;) {
+        while (zdrawn_s < nz) {                     // (every zero chunk already drawn when this CTA arrived: nothing to do)
             int z = 0;
             if (lane == 0) z = atomicAdd(ctrl + 3, 1);
             z = __shfl_sync(kFullMask, z, 0);
@@ -1853,6 +1884,12 @@ __global__ void __launch_bounds__(256, (K <= 8) ? (sizeof(TIn) == 4 ? 3 : 4) : 1
         }
     };
 
+    if (p.stamp && p.flag && lane == 0) {       // debug: set-up + zero rows of this warp, when the last warp started on its
+        int* const f = const_cast<int*>(p.flag);                                        // rows, when the last CTA entered
+        stamp_dur(f, 10, global_timer_ns() - tg0);
+        stamp_max(f, 11);
+        atomicMax(reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(f) + 64) + 12, tg0);
+    }
     if (use_spread) {
         const int c = chunk_s, ntasks = start_s[p.B];
         auto draw = [&]() -> int {
@@ -2244,7 +2281,10 @@ extern "C" int avctc_ctc_scale_grad(void* grad, int dtype, int T, int B, int V, 
     return (int)cudaGetLastError();
 }
 
-// forward + reduce + backward(unit or given grad_out) as ONE host call: what the autograd host enqueues at forward time
+// forward + reduce + backward(unit or given grad_out) as ONE host call: what the autograd host enqueues at forward time.
+// (Measured: issuing the gradient pass directly behind the scan, ahead of the guarded log-domain scan and the reduction,
+// lets its late CTAs enter 2-4 us instead of 12-23 us after the last scan CTA, but the guard scan and the reduction then
+// trail the gradient pass one after the other instead of running under it: 189 us either way at T=1000.)
 extern "C" int avctc_ctc_forward_backward(const void* log_probs, int dtype, int64_t stride_t, int64_t stride_b, int T, int B,
                                           int V, const int64_t* targets, int64_t target_stride,
                                           const int64_t* target_offsets, const int64_t* input_lengths,

@@ -32,7 +32,8 @@ for T in (250, 1000):
         t_b, _ = bench.event_time(bwd, 10, 2, flush, dev)
         _lib.set_tuning("ctc_stamp", 1)
         flush(); fwd(); bwd(); torch.cuda.synchronize()
-        blk = ws[wsb - ((256 + 4 * B + 255) // 256) * 256:][64:96].cpu().numpy().view(np.uint64)
+        blkall = ws[wsb - ((256 + 4 * B + 255) // 256) * 256:][64:192].cpu().numpy().view(np.uint64)
+        blk = blkall[:4]; dur = blkall[4:8]
         t0 = np.uint64(~blk[0]); scan_end = (int(blk[1]) - int(t0)) / 1e3; grad_end = (int(blk[2]) - int(t0)) / 1e3
         first = (int(np.uint64(~blk[3])) - int(t0)) / 1e3 if blk[3] else float("nan")
         g = grad.clone()
@@ -40,4 +41,15 @@ for T in (250, 1000):
             ref = g
         dmax = float((g - ref).abs().max() / ref.abs().max())
         print(f"T={T} overlap={ov}: fwd+bwd {t_all*1e3:.1f} us, bwd alone {t_b*1e3:.1f} us | stamps: scan end {scan_end:.1f} us, "
-              f"first early chunk {first:.1f} us, grad end {grad_end:.1f} us | grad vs first config {dmax:.2e}", flush=True)
+              f"first early chunk {first:.1f} us, grad end {grad_end:.1f} us | recurrence warp: prologue {int(dur[0])/1e3:.1f} us, epilogue {int(dur[1])/1e3:.1f} us, "
+              f"slowest {int(dur[2])/1e3:.1f} ns/frame, longest loop {int(dur[3])/1e3:.1f} us | gradient warps: set-up + zero rows {int(blkall[10])/1e3:.1f} us, "
+              f"last warp at its rows {(int(blkall[11]) - int(t0))/1e3:.1f} us, last CTA entry {(int(blkall[12]) - int(t0))/1e3:.1f} us | grad vs first config {dmax:.2e}", flush=True)
+    # the product order: scan, gradient pass, guarded twins, reduction in ONE call
+    def fb():
+        _lib.check(L.avctc_ctc_forward_backward(lp.data_ptr(), 0, lp.stride(0), lp.stride(1), T, B, V, tg.data_ptr(), tg.stride(0), None,
+                                                il.data_ptr(), tl.data_ptr(), Lm, 0, 1, 1, nll.data_ptr(), loss.data_ptr(), go.data_ptr(), 0,
+                                                grad.data_ptr(), ws.data_ptr(), wsb, st), "fwd_bwd")
+    _lib.set_tuning("ctc_overlap", 1); _lib.set_tuning("ctc_stamp", 0)
+    t_fb, _ = bench.event_time(fb, 20, 3, flush, dev)
+    fb(); torch.cuda.synchronize()
+    print(f"T={T} avctc_ctc_forward_backward: {t_fb*1e3:.1f} us | grad vs first config {float((grad - ref).abs().max() / ref.abs().max()):.2e}", flush=True)
