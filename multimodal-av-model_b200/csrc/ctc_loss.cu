@@ -1503,6 +1503,21 @@ __device__ __forceinline__ void grad_stream_row(const TIn* __restrict__ lrow, TI
     }
 }
 
+// Stage one fp32 row for grad_stream_row_smem: the 16-byte chunks that COVER the row are copied whole (cp.async.cg), so
+// the loop is one predicate + one copy per 512 bytes; buf[o + c] = row[c] with o = the row's misalignment in elements.
+// The up to 12 bytes before / after the row that come along lie in the same 16-byte aligned chunk as row bytes, hence in
+// the same page: always readable (they are never used).
+__device__ __forceinline__ int stage_row_chunks(const float* __restrict__ grow, int V, float* __restrict__ buf, int lane) {
+    const int o = (int)((reinterpret_cast<uintptr_t>(grow) >> 2) & 3);
+    const int nq = (o + V + 3) >> 2;
+    const char* g = reinterpret_cast<const char*>(grow - o) + lane * 16;
+    unsigned sa = (unsigned)__cvta_generic_to_shared(buf) + lane * 16;
+    for (int q = lane; q < nq; q += 32, g += 512, sa += 512)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g));
+    cp_async_commit();
+    return o;
+}
+
 // Same arithmetic with the log-prob row already in shared memory (row_s[c] = class c): the global loads of the row
 // were issued all at once by cp.async (stage_row) instead of one 16-byte load per lane per loop iteration, so a warp
 // has its whole 3.2 KB row in flight, not 512 bytes of it.
@@ -1572,7 +1587,7 @@ __global__ void __launch_bounds__(256, (K <= 8) ? (sizeof(TIn) == 4 ? 3 : 4) : 1
     // A CTA that becomes resident only when the scan CTAs leave starts on a saturated memory system, where every
     // dependent global round trip costs microseconds of the tail: its independent loads (input lengths, the mode word,
     // the zero-row ticket counter) are issued together here, and a mode that is already decided is taken as it is.
-    const bool spread_ok = ctrl && p.B <= kSpreadMaxB;
+    const bool spread_ok = ctrl && p.B <= kSpreadMaxB && p.B <= (int)blockDim.x;      // one thread per sample builds the tables
     int mine = 0;
     if (spread_ok && (int)threadIdx.x < p.B) {
         const long long v = p.input_lengths[threadIdx.x];
@@ -1627,7 +1642,7 @@ __global__ void __launch_bounds__(256, (K <= 8) ? (sizeof(TIn) == 4 ? 3 : 4) : 1
         if (tid < p.B) {
             int R = 0;
             for (int j = 0; j < p.B; ++j) R += tb_s[j];
-            int c = R / (Wtot * 4);
+            int c = R / (Wtot * 4);          // (measured: 3-frame chunks at config 2; 6 -> 219 us, 1 -> 208 us, 3 -> 188 us)
             c = c < 1 ? 1 : (c > 16 ? 16 : c);
             order_s[tid] = (mine + c - 1) / c;               // chunks of this sample (order_s is scratch until below)
             if (tid == 0) chunk_s = c;
@@ -1771,47 +1786,61 @@ __global__ void __launch_bounds__(256, (K <= 8) ? (sizeof(TIn) == 4 ? 3 : 4) : 1
             }
         }
         const int s0 = lane * K;
-        const int nval = min(max(S - s0, 0), K);
         const int sm0 = S - 1 - s0;              // beta (mirrored) index of state s0; state s0+j -> sm0 - j
+        // Per-sample set-up of the row loop (an instruction diet: the loop below used to spend ~45 % of its 1 330
+        // instructions per row on predicated loads with 64-bit index arithmetic and a branch per state).  States beyond
+        // S have alpha == 0 in the workspace (the scan multiplies them by a zero emission), so their weight is zero
+        // whatever beta / exponent they are paired with: every load is unconditional, with the beta index clamped
+        // into the row.  The K mirrored states of a lane fall into at most two lanes of the beta scan: two exponent
+        // loads and a per-state select.
+        // (beta index: sm0 - j with NO clamp for a lane that holds at least one state -- at most K - 1 floats before the
+        // row, i.e. the previous row or, for the first row, the tail of the alpha array that precedes beta in the
+        // workspace; a lane without states reads the first K floats of the row)
+        const int sm0u = sm0 >= 0 ? sm0 : K - 1;
+        unsigned lo_mask = 0;
+        const int cb_hi_i = sm0u / K, cb_lo_i = max(sm0u - (K - 1), 0) / K;
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (max(sm0u - j, 0) / K != cb_hi_i) lo_mask |= 1u << j;
+        // running pointers of the rows t0, t0 + step, ...
+        const TIn* lrow = lpbase + (int64_t)t0 * p.stride_t + (int64_t)b * p.stride_b;
+        TIn* grow = grad + ((size_t)t0 * p.B + b) * p.V;
+        const size_t rowi0 = (size_t)b * p.T + t0;
+        const float* ap = p.alpha + rowi0 * p.S_pad + s0;
+        const float* bp = p.beta + rowi0 * p.S_pad + sm0u;                 // state s0 + j  ->  bp[-j]
+        const int* cap = p.coff_a + rowi0 * p.cw + lane;
+        const int* cbp = p.coff_b + rowi0 * p.cw;
+        const int64_t lstep = (int64_t)step * p.stride_t;
+        const size_t gstep = (size_t)step * p.B * p.V;
+        const int abstep = step * p.S_pad, cstep = step * p.cw;
+        const int base_e = nll2_i - 254;
 
-        for (int t = t0; t < t1; t += step) {
-            const long long row = (long long)t * p.B + b;
-            TIn* grow = grad + (size_t)row * p.V;
+        for (int t = t0; t < t1; t += step, lrow += lstep, grow += gstep, ap += abstep, bp += abstep, cap += cstep, cbp += cstep) {
             const int o_out = (int)((reinterpret_cast<uintptr_t>(grow) / sizeof(TIn)) & (kVec - 1));
-            const TIn* lrow = lpbase + (int64_t)t * p.stride_t + (int64_t)b * p.stride_b;
             int o_in_s = 0;
             if constexpr (sizeof(TIn) == 4) {
-                if (stage) o_in_s = stage_row(reinterpret_cast<const float*>(lrow), p.V, rowbuf, lane);   // cp.async, one group
+                if (stage) o_in_s = stage_row_chunks(reinterpret_cast<const float*>(lrow), p.V, rowbuf, lane);   // cp.async, one group
             }
             if (pf_lines > 0 && t + pf_dist * step < t1) {    // a later row of this warp: pull its lines into L2 now
                 if (lane < pf_lines) {
-                    const char* nx = reinterpret_cast<const char*>(lrow + (int64_t)pf_dist * step * p.stride_t) + lane * 128;
+                    const char* nx = reinterpret_cast<const char*>(lrow + (int64_t)pf_dist * lstep) + lane * 128;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
                 }
                 if (pf_ab && lane < 2 * ab_lines) {
-                    const size_t rn = ((size_t)b * p.T + t + (size_t)pf_dist * step) * p.S_pad;
-                    const char* nx = reinterpret_cast<const char*>((lane < ab_lines ? p.alpha : p.beta) + rn) +
+                    const char* nx = reinterpret_cast<const char*>((lane < ab_lines ? ap - s0 : bp - sm0u) + pf_dist * abstep) +
                                      (lane < ab_lines ? lane : lane - ab_lines) * 128;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
                 }
             }
-            const size_t rowi = (size_t)b * p.T + t;
-            const float* arow = p.alpha + rowi * p.S_pad + s0;
-            const float* brow = p.beta + rowi * p.S_pad;
-            const int* cbp = p.coff_b + rowi * p.cw;
-            const int caL = p.coff_a[rowi * p.cw + lane];
             float av[K], bv[K];
-            int cbv[K];
 #pragma unroll
-            for (int j = 0; j < K; ++j) {
-                av[j] = 0.f; bv[j] = 0.f; cbv[j] = 0;
-                if (j < nval) {
-                    const int sm = sm0 - j;
-                    av[j] = arow[j];
-                    bv[j] = brow[sm];
-                    cbv[j] = cbp[sm / K];
-                }
+            for (int j = 0; j < K / 2; ++j) {
+                const float2 v = reinterpret_cast<const float2*>(ap)[j];
+                av[2 * j] = v.x; av[2 * j + 1] = v.y;
             }
+#pragma unroll
+            for (int j = 0; j < K; ++j) bv[j] = bp[-j];
+            const int e_hi = cbp[cb_hi_i] + *cap + base_e, e_lo = cbp[cb_lo_i] + *cap + base_e;
             float xb, xl[KL];
             if (stage) {                 // the row has landed (its latency overlapped the alpha/beta loads above)
                 cp_async_wait<0>();
@@ -1825,18 +1854,18 @@ __global__ void __launch_bounds__(256, (K <= 8) ? (sizeof(TIn) == 4 ? 3 : 4) : 1
 #pragma unroll
                 for (int i = 0; i < KL; ++i) xl[i] = to_float(__ldg(lrow + cls[i])) * AVCTC_LOG2E;
             }
+            const float fb = nll2_f - xb;
             float w[K];
 #pragma unroll
-            for (int j = 0; j < K; ++j) {
-                w[j] = 0.f;
-                if (av[j] >= 1.17549435e-38f && bv[j] >= 1.17549435e-38f) {
-                    const int ia = __float_as_int(av[j]), ib = __float_as_int(bv[j]);
-                    const float mant = __int_as_float((ia & 0x007fffff) | 0x3f800000) *
-                                       __int_as_float((ib & 0x007fffff) | 0x3f800000);
-                    const int ei = (ia >> 23) + (ib >> 23) - 254 + caL + cbv[j] + nll2_i;
-                    const float x = (float)ei + (nll2_f - ((j & 1) ? xl[j >> 1] : xb));
-                    w[j] = mant * ex2_approx(x);
-                }
+            for (int j = 0; j < K; ++j) {      // alpha*beta/(P*p): mantissa product, integer exponents, no branch
+                const int ia = __float_as_int(av[j]), ib = __float_as_int(bv[j]);
+                const bool ok = (av[j] >= 1.17549435e-38f) && (bv[j] >= 1.17549435e-38f);
+                const float mant = __int_as_float((ia & 0x007fffff) | 0x3f800000) *
+                                   __int_as_float((ib & 0x007fffff) | 0x3f800000);
+                const int ei = (ia >> 23) + (ib >> 23) + (((lo_mask >> j) & 1u) ? e_lo : e_hi);
+                const float x = (float)ei + ((j & 1) ? (nll2_f - xl[j >> 1]) : fb);
+                const float v = mant * ex2_approx(x);
+                w[j] = ok ? v : 0.f;
             }
             float pbs = 0.f;
 #pragma unroll
