@@ -1833,14 +1833,20 @@ __global__ void __launch_bounds__(256, (K <= 8) ? (sizeof(TIn) == 4 ? 3 : 4) : 1
                 }
             }
             float av[K], bv[K];
+            int e_hi = 0, e_lo = 0;
 #pragma unroll
-            for (int j = 0; j < K / 2; ++j) {
-                const float2 v = reinterpret_cast<const float2*>(ap)[j];
-                av[2 * j] = v.x; av[2 * j + 1] = v.y;
+            for (int j = 0; j < K; ++j) { av[j] = 0.f; bv[j] = 0.f; }
+            if (s0 < S) {                // lanes beyond the lattice load nothing (on average half of every alpha / beta row)
+#pragma unroll
+                for (int j = 0; j < K / 2; ++j) {
+                    const float2 v = reinterpret_cast<const float2*>(ap)[j];
+                    av[2 * j] = v.x; av[2 * j + 1] = v.y;
+                }
+#pragma unroll
+                for (int j = 0; j < K; ++j) bv[j] = bp[-j];
+                const int ca = *cap;
+                e_hi = cbp[cb_hi_i] + ca + base_e; e_lo = cbp[cb_lo_i] + ca + base_e;
             }
-#pragma unroll
-            for (int j = 0; j < K; ++j) bv[j] = bp[-j];
-            const int e_hi = cbp[cb_hi_i] + *cap + base_e, e_lo = cbp[cb_lo_i] + *cap + base_e;
             float xb, xl[KL];
             if (stage) {                 // the row has landed (its latency overlapped the alpha/beta loads above)
                 cp_async_wait<0>();
