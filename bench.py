@@ -130,7 +130,11 @@ def build_models(device, seed=0, encoders=True):
     return tr
 
 
-def timed_loop(fn, steps, warmup, device, world):
+GC_LOG = {}      # label -> Python garbage collections inside a timed region (count per generation, milliseconds)
+
+
+def timed_loop(fn, steps, warmup, device, world, label=None):
+    import gc
     import torch.distributed as dist
     for _ in range(warmup):
         fn()
@@ -138,12 +142,25 @@ def timed_loop(fn, steps, warmup, device, world):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(device)
+    stat = {"collections": [0, 0, 0], "ms": 0.0, "t0": 0.0}
+
+    def on_gc(phase, info):
+        if phase == "start":
+            stat["t0"] = time.perf_counter()
+        else:
+            stat["collections"][info["generation"]] += 1
+            stat["ms"] += (time.perf_counter() - stat["t0"]) * 1e3
+    if label:
+        gc.callbacks.append(on_gc)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(steps):
         fn()
     b.record()
     torch.cuda.synchronize(device)
+    if label:
+        gc.callbacks.remove(on_gc)
+        GC_LOG[label] = {"collections": stat["collections"], "ms": round(stat["ms"], 2)}
     if world > 1:
         dist.barrier()
     ms = torch.tensor([a.elapsed_time(b)], device=device)
@@ -170,14 +187,14 @@ def bench_train(args, rank, local, world, device, hot_only=False):
 
         c0 = _lib.launch_count
         with ClockSampler(local) as cs:
-            ms = timed_loop(step_resident, args.steps, args.warmup, device, world)
+            ms = timed_loop(step_resident, args.steps, args.warmup, device, world, label="value")
         launches = (_lib.launch_count - c0) // (args.steps + args.warmup)
-        ms_e2e = timed_loop(step_e2e, args.steps, max(1, args.warmup // 2), device, world)
+        ms_e2e = timed_loop(step_e2e, args.steps, max(1, args.warmup // 2), device, world, label="e2e")
         # the same K steps through MultimodalTrainer.train_epoch (main.py:165): batch i+1 staged on a side stream while step i
         # runs, each step's loss sent to the pinned trainer.loss_log without blocking, one host sync at the end of the epoch
         epoch_batches = [host] * args.steps
         tr.train_epoch([host] * max(1, args.warmup // 2))
-        ms_epoch = timed_loop(lambda: tr.train_epoch(epoch_batches), 1, 0, device, world)
+        ms_epoch = timed_loop(lambda: tr.train_epoch(epoch_batches), 1, 0, device, world, label="epoch")
         assert tr.last_epoch_steps == args.steps and tr.loss_log_count == args.steps
         h2d = int(sum(v.numel() * v.element_size() for k, v in host.items() if not k.endswith("_lengths") or k.startswith("text")))
         grad_params = sum(p.numel() for p in tr.parameters if p.requires_grad)
@@ -190,7 +207,7 @@ def bench_train(args, rank, local, world, device, hot_only=False):
                             epoch_value=utt_per_step * args.steps / (ms_epoch / 1e3),
                             epoch_note="the same K steps through MultimodalTrainer.train_epoch: next batch staged on a side stream, "
                                        "per-step loss copied asynchronously into the pinned loss_log, one sync per epoch"),
-                   gpu_launches=int(launches), clocks=cs.summary(), allreduce_bytes_per_step=grad_params * 4 if world > 1 else 0)
+                   gpu_launches=int(launches), clocks=cs.summary(), host_gc=dict(GC_LOG), allreduce_bytes_per_step=grad_params * 4 if world > 1 else 0)
         del dev_batch
     # hot path only (number A): from encoder features on, same trainer
     from multimodal_av_model_b200.synthetic import make_features
