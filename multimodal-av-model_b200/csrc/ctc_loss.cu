@@ -1426,6 +1426,8 @@ __global__ void __launch_bounds__(kWsThreads) ctc_scan_ws_kernel(const ScanParam
         stamp_dur(p.flag, 5, tm3 - tm2);                       // epilogue (likelihood, fence, counter)
         stamp_dur(p.flag, 6, (tm2 - tm1) * 1000ull / (unsigned long long)(Tb > 1 ? Tb - 1 : 1));   // ps per frame
         stamp_dur(p.flag, 7, tm2 - tm1);                       // longest frame loop
+        atomicMax(p.flag + 60, *reinterpret_cast<volatile int*>(p.flag + 33));      // gradient tickets drawn when this scan CTA ended
+        atomicMax(p.flag + 61, *reinterpret_cast<volatile int*>(p.flag + 35));      // zero-row tickets drawn
     }
 }
 
@@ -1567,6 +1569,13 @@ __global__ void __launch_bounds__(256, (K <= 8) ? (sizeof(TIn) == 4 ? 3 : 4) : 1
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     pdl_launch_dependents();
     const unsigned long long tg0 = p.stamp ? global_timer_ns() : 0ull;
+    if (p.stamp && p.flag && threadIdx.x == 0) {      // debug: histogram of CTA entry times, 16 us buckets from the first scan CTA
+        const unsigned long long t0 = ~*reinterpret_cast<const volatile unsigned long long*>(reinterpret_cast<const char*>(p.flag) + 64);
+        const long long d = (long long)(tg0 - t0);
+        int bk = d < 0 ? 0 : (int)(d / 16000);
+        bk = bk > 15 ? 15 : bk;
+        atomicAdd(const_cast<int*>(p.flag) + 44 + bk, 1);
+    }
     // Launched with the PDL attribute, this grid can be resident while the scan before it on the stream is still
     // running (backward enqueued right behind forward).  If every sample's completion counter is already full the
     // kernel takes the ordinary route: griddepcontrol.wait, after which everything before it on the stream (scan,

@@ -36,6 +36,9 @@ for T in (250, 1000):
         blk = blkall[:4]; dur = blkall[4:8]
         t0 = np.uint64(~blk[0]); scan_end = (int(blk[1]) - int(t0)) / 1e3; grad_end = (int(blk[2]) - int(t0)) / 1e3
         first = (int(np.uint64(~blk[3])) - int(t0)) / 1e3 if blk[3] else float("nan")
+        hist = ws[wsb - ((256 + 4 * B + 255) // 256) * 256:][176:240].cpu().numpy().view(np.int32)
+        tick = ws[wsb - ((256 + 4 * B + 255) // 256) * 256:][240:248].cpu().numpy().view(np.int32)
+        real_rows = int(il.sum().item()); chunk = max(1, min(16, real_rows // (444 * 8 * 4)))
         g = grad.clone()
         if ref is None:
             ref = g
@@ -44,6 +47,8 @@ for T in (250, 1000):
               f"first early chunk {first:.1f} us, grad end {grad_end:.1f} us | recurrence warp: prologue {int(dur[0])/1e3:.1f} us, epilogue {int(dur[1])/1e3:.1f} us, "
               f"slowest {int(dur[2])/1e3:.1f} ns/frame, longest loop {int(dur[3])/1e3:.1f} us | gradient warps: set-up + zero rows {int(blkall[10])/1e3:.1f} us, "
               f"last warp at its rows {(int(blkall[11]) - int(t0))/1e3:.1f} us, last CTA entry {(int(blkall[12]) - int(t0))/1e3:.1f} us | grad vs first config {dmax:.2e}", flush=True)
+        print("      gradient CTA entries per 16 us:", " ".join(str(int(v)) for v in hist),
+              f"| tickets drawn when the last scan CTA ended: {int(tick[0])} x {chunk} rows of {real_rows} real rows; zero-row tickets {int(tick[1])}", flush=True)
     # the product order: scan, gradient pass, guarded twins, reduction in ONE call
     def fb():
         _lib.check(L.avctc_ctc_forward_backward(lp.data_ptr(), 0, lp.stride(0), lp.stride(1), T, B, V, tg.data_ptr(), tg.stride(0), None,
