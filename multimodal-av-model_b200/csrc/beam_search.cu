@@ -297,6 +297,108 @@ __device__ bool topk_fast(const float* row, int V, int k, float* cv, int* ci, vo
     return true;
 }
 
+// One frame of the prune when the (b+1)(j+1) <= beam candidates fit one warp: lane m IS candidate m = (my_b, my_j).
+// (tvv, tii) = this frame's top-k list (lane j holds entry j); sc / sn = scores of the current / next beams.
+// Rank = number of strictly greater scores (16-byte shared loads, NaN padding compares false); equal scores give
+// equal ranks, which match.any detects -> stable (insertion-order) ranks.  Returns the number of beams kept.
+__device__ __forceinline__ int recur_step_enum32(const float tvv, const int tii, const int my_b, const int my_j,
+                                                 const int n_enum, const int nb, const int k, const double* sc, double* sn,
+                                                 double* cand_s, uint16_t* bp16_t, uint32_t* bp_t, const int bp_in_smem,
+                                                 const int lane) {
+    const bool in = (lane < n_enum) && (my_b < nb);
+    const unsigned inmask = __ballot_sync(kFullMask, in);
+    const int M = __popc(inmask);                      // candidates are ordered by beam: `in` is a prefix
+    const float lpv = __shfl_sync(kFullMask, tvv, my_j);
+    const int tok = __shfl_sync(kFullMask, tii, my_j);
+    const double s = in ? sc[my_b] + (double)lpv : __longlong_as_double(0x7ff8000000000000ll);
+    cand_s[lane] = s;
+    __syncwarp();
+    const int keep = min(k, M);
+    // every lane wrote its slot (NaN where it holds no candidate), so the 32 slots are compared in two unrolled halves:
+    // eight 16-byte loads in flight, four chains of predicated increments (DSETP + @p IADD per compare), no loop tail
+    int r = 0;
+    const double2* c2 = reinterpret_cast<const double2*>(cand_s);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (h == 0 || M > 16) {
+            int ra = 0, rb = 0, rc = 0, rd = 0;
+            double2 o[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = c2[8 * h + q];
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) {
+                asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(ra) : "d"(o[q].x), "d"(s));
+                asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(rb) : "d"(o[q].y), "d"(s));
+                asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(rc) : "d"(o[q + 1].x), "d"(s));
+                asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(rd) : "d"(o[q + 1].y), "d"(s));
+            }
+            r += (ra + rb) + (rc + rd);
+        }
+    }
+    bool clash = false;
+    if (in) clash = (__popc(__match_any_sync(inmask, r)) > 1) || (s != s);
+    if (__any_sync(kFullMask, clash)) {                // ties (or NaNs): insertion-order tie-break, as the reference's stable sort
+        r = 0;
+        for (int q = 0; q < M; ++q) {
+            const double o = cand_s[q];
+            r += (o > s) || (o == s && q < lane);
+        }
+    }
+    if (in && r < keep) {
+        sn[r] = s;
+        if (bp_in_smem) bp16_t[r] = (uint16_t)((my_b << 10) | tok);
+        else bp_t[r] = ((uint32_t)my_b << 24) | (uint32_t)tok;
+    }
+    __syncwarp();
+    return keep;
+}
+
+// After the last frame: back-track beams[0] (lane i walks beam i for the debug export), CTC-collapse it (`prev` follows
+// every frame, blank included: beam_search.py:33-40) and write the token list.  Back-pointers: 16-bit (parent << 10 |
+// token) in shared memory (bp16) or 32-bit (parent << 24 | token) entries (bp); sc = scores of the surviving beams.
+__device__ __forceinline__ void beam_finish(const BeamParams& p, const int n, const int k, const int frames, const int nb,
+                                            const uint32_t* bp, const uint16_t* bp16, const int bp_is16, const double* sc,
+                                            int32_t* path, const int lane) {
+    if (frames > 0) {
+        const bool dbg = (p.dbg_paths != nullptr);
+        if (lane == 0 || (dbg && lane < nb)) {
+            int32_t* dst = dbg ? p.dbg_paths + ((size_t)n * k + lane) * p.T : path;
+            int idx = lane;
+            for (int t = frames - 1; t >= 0; --t) {
+                if (bp_is16) {
+                    const unsigned e = bp16[(size_t)t * k + idx];
+                    dst[t] = (int32_t)(e & 0x3ffu);
+                    idx = (int)(e >> 10);
+                } else {
+                    const uint32_t e = bp[(size_t)t * k + idx];
+                    dst[t] = (int32_t)(e & 0xffffffu);
+                    idx = (int)(e >> 24);
+                }
+            }
+            if (dbg && lane == 0)
+                for (int t = 0; t < frames; ++t) path[t] = dst[t];
+        }
+        if (p.dbg_scores && lane < nb) p.dbg_scores[(size_t)n * k + lane] = sc[lane];
+    }
+    __syncwarp();
+    __threadfence_block();
+    int count = 0;
+    int32_t* out = p.out_ids + (size_t)n * p.T;
+    for (int t0 = 0; t0 < frames; t0 += 32) {
+        const int t = t0 + lane;
+        bool keepit = false;
+        int c = 0;
+        if (t < frames) {
+            c = path[t];
+            keepit = (c != p.blank) && (t == 0 || path[t - 1] != c);
+        }
+        const unsigned m = __ballot_sync(kFullMask, keepit);
+        if (keepit) out[count + __popc(m & ((1u << lane) - 1))] = c;
+        count += __popc(m);
+    }
+    if (lane == 0) p.out_len[n] = count;
+}
+
 __global__ void __launch_bounds__(32) beam_search_kernel(const BeamParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = blockIdx.x, lane = threadIdx.x;
@@ -394,39 +496,7 @@ __global__ void __launch_bounds__(32) beam_search_kernel(const BeamParams p) {
     }
     cp_async_wait<0>();
 
-    // ---- back-track (lane i walks beam i; only beam 0 is the result) and CTC-collapse
-    if (frames > 0) {
-        const bool dbg = (p.dbg_paths != nullptr);
-        if (lane == 0 || (dbg && lane < nb)) {
-            int32_t* dst = dbg ? p.dbg_paths + ((size_t)n * k + lane) * p.T : path;
-            int idx = lane;
-            for (int t = frames - 1; t >= 0; --t) {
-                const uint32_t e = bp[(size_t)t * k + idx];
-                dst[t] = (int32_t)(e & 0xffffffu);
-                idx = (int)(e >> 24);
-            }
-            if (dbg && lane == 0)
-                for (int t = 0; t < frames; ++t) path[t] = dst[t];
-        }
-        if (p.dbg_scores && lane < nb) p.dbg_scores[(size_t)n * k + lane] = score[cur * kBeamMax + lane];
-    }
-    __syncwarp();
-    __threadfence_block();
-    int count = 0;
-    int32_t* out = p.out_ids + (size_t)n * p.T;
-    for (int t0 = 0; t0 < frames; t0 += 32) {
-        const int t = t0 + lane;
-        bool keepit = false;
-        int c = 0;
-        if (t < frames) {
-            c = path[t];
-            keepit = (c != p.blank) && (t == 0 || path[t - 1] != c);
-        }
-        const unsigned m = __ballot_sync(kFullMask, keepit);
-        if (keepit) out[count + __popc(m & ((1u << lane) - 1))] = c;
-        count += __popc(m);
-    }
-    if (lane == 0) p.out_len[n] = count;
+    beam_finish(p, n, k, frames, nb, bp, nullptr, 0, score + cur * kBeamMax, path, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -459,6 +529,109 @@ __device__ __forceinline__ float fmax_nan(float a, float b) {      // NaN-propag
 // a prefix sum of the lane counts (no per-slot votes or branches); ranks by counting greater candidates with 16-byte
 // shared loads.  Any tie inside the first k+1 ranks, a NaN, or a candidate list outside [k+1, kCandMax] sends the row
 // to the literal libstdc++ order of torch.topk (topk_exact / topk_nth_exact).
+// One row of torch.topk for the warp.  row = first class of the row + lane; pf = this lane's 128-byte line of the warp's
+// NEXT row (L2 prefetch) or nullptr.  On return (tv, ti)[0..k) in the warp's shared scratch hold the result, visible to
+// every lane.
+template <int NV, int MODE>
+__device__ __forceinline__ void topk_row(const BeamParams& p, const float* __restrict__ row, const float* pf,
+                                         const bool can_fast, const int k, const int lane, float* cv, float* tv, int* ti,
+                                         float* srow, int* qi) {
+    const int full_slots = (MODE == 0) ? NV : (MODE == 1) ? NV - 1 : p.V / 32;
+    const bool tail_ok = lane + 32 * (NV - 1) < p.V;           // MODE 1: the one ragged slot
+    auto valid = [&](int j) -> bool {
+        if (MODE == 0) return true;
+        if (MODE == 1) return j < NV - 1 || tail_ok;
+        return j < full_slots || lane + 32 * j < p.V;
+    };
+    float x[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) x[j] = valid(j) ? __ldcs(row + 32 * j) : AVCTC_NEG_INF;
+    if (pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+    float ml = x[0];
+#pragma unroll
+    for (int j = 1; j < NV; ++j) ml = fmax_nan(ml, x[j]);
+    bool ok = can_fast && !__any_sync(kFullMask, ml != ml);
+    if (ok) {
+        unsigned key = f2key(ml), m = 0;
+        for (int i = 0; i <= k; ++i) {
+            m = __reduce_max_sync(kFullMask, key);
+            if (key == m) key = 0u;
+        }
+        const float tau = __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);   // inverse of f2key (m = 0 -> NaN)
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {      // FSET + IADD per slot (a predicate per slot would be spilled through P2R)
+            unsigned ge;
+            asm("set.ge.u32.f32 %0, %1, %2;" : "=r"(ge) : "f"(x[j]), "f"(tau));
+            if (valid(j)) c -= (int)ge;
+        }
+        int inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(kFullMask, inc, d);
+            if (lane >= d) inc += up;
+        }
+        const int count = __shfl_sync(kFullMask, inc, 31);
+        ok = (count <= kCandMax) && (count >= k + 1);
+        if (ok) {
+            float2* cand = reinterpret_cast<float2*>(cv);          // (value, index bits) pairs, dense
+            uint32_t dst = (uint32_t)__cvta_generic_to_shared(cand + (inc - c));
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {      // 4 instructions per slot: setp, index, predicated 8-byte store + bump
+                if (valid(j))
+                    asm volatile("{\n\t.reg .pred p;\n\t"
+                                 "setp.ge.f32 p, %1, %2;\n\t"
+                                 "@p st.shared.v2.b32 [%0], {%4, %3};\n\t"
+                                 "@p add.u32 %0, %0, 8;\n\t}"
+                                 : "+r"(dst) : "f"(x[j]), "f"(tau), "r"(lane + 32 * j), "r"(__float_as_uint(x[j])) : "memory");
+            }
+            if (lane == 0) cand[count] = make_float2(AVCTC_NEG_INF, 0.f);      // pad the last 16-byte group
+            __syncwarp();
+            bool tie = false;
+            if (count <= 32) {
+                // one candidate per lane: rank = number of greater values; equal values collide on the rank
+                const bool have = lane < count;
+                const float2 me = have ? cand[lane] : make_float2(0.f, 0.f);
+                int gt = 0;
+                for (int j = 0; j < count; j += 2) {
+                    const float4 o = *reinterpret_cast<const float4*>(cand + j);
+                    unsigned g0, g1;            // FSET masks (0 / ~0): one IADD3 retires two compares
+                    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(g0) : "f"(o.x), "f"(me.x));
+                    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(g1) : "f"(o.z), "f"(me.x));
+                    gt -= (int)g0 + (int)g1;
+                }
+                const bool top = have && gt <= k;
+                const unsigned tm = __ballot_sync(kFullMask, top);
+                if (top) {
+                    tie = __popc(__match_any_sync(tm, gt)) > 1;
+                    tv[gt] = me.x; ti[gt] = __float_as_int(me.y);
+                }
+            } else {
+                for (int i = lane; i < count; i += 32) {
+                    const float2 me = cand[i];
+                    int gt = 0, eq = 0;
+                    for (int j = 0; j < count; j += 2) {
+                        const float4 o = *reinterpret_cast<const float4*>(cand + j);
+                        gt += (o.x > me.x) + (o.z > me.x);
+                        eq += (o.x == me.x) + (o.z == me.x);
+                    }
+                    if (gt <= k) { tv[gt] = me.x; ti[gt] = __float_as_int(me.y); tie = tie || (eq > 1); }
+                }
+            }
+            ok = !__any_sync(kFullMask, tie);      // the first k+1 ranks hold distinct values: any algorithm agrees
+        }
+    }
+    if (!ok) {     // ties / NaNs: literal libstdc++ order on a staged copy of the row
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { const int c = lane + 32 * j; if (c < p.V) srow[c] = x[j]; }
+        __syncwarp();
+        if (p.use_nth) topk_nth_exact(srow, qi, p.V, k, tv, ti, lane);
+        else topk_exact(srow, p.V, k, tv, ti, lane);
+    }
+    __syncwarp();
+}
+
 template <int NV, int MODE>
 __global__ void __launch_bounds__(kTopkWarps * 32) beam_topk_kernel(const BeamParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -476,13 +649,6 @@ __global__ void __launch_bounds__(kTopkWarps * 32) beam_topk_kernel(const BeamPa
     const unsigned rows = (unsigned)p.N * (unsigned)p.T;       // host guarantees N*T < 2^31
     const unsigned uT = (unsigned)p.T;
     const bool can_fast = p.fast && (k + 1 <= 32) && (p.V >= k + 1);
-    const int full_slots = (MODE == 0) ? NV : (MODE == 1) ? NV - 1 : p.V / 32;
-    const bool tail_ok = lane + 32 * (NV - 1) < p.V;           // MODE 1: the one ragged slot
-    auto valid = [&](int j) -> bool {
-        if (MODE == 0) return true;
-        if (MODE == 1) return j < NV - 1 || tail_ok;
-        return j < full_slots || lane + 32 * j < p.V;
-    };
     for (unsigned r = blockIdx.x * kTopkWarps + warp; r < rows; r += gridDim.x * kTopkWarps) {
         if (p.lengths) {
             const unsigned n = r / uT, t = r - n * uT;
@@ -493,97 +659,12 @@ __global__ void __launch_bounds__(kTopkWarps * 32) beam_topk_kernel(const BeamPa
         const bool dense = p.stride_n == (int64_t)uT * p.stride_t;
         if (dense) row = p.lp + (int64_t)r * p.stride_t + lane;     // dense [N,T,V]
         else { const unsigned n = r / uT, t = r - n * uT; row = p.lp + (int64_t)n * p.stride_n + (int64_t)t * p.stride_t + lane; }
-        float x[NV];
-#pragma unroll
-        for (int j = 0; j < NV; ++j) x[j] = valid(j) ? __ldcs(row + 32 * j) : AVCTC_NEG_INF;
+        const float* pf = nullptr;
         if (p.prefetch && dense) {       // the warp's next row: one 128-byte line per lane into L2
             const unsigned rn = r + gridDim.x * kTopkWarps;
-            if (rn < rows && lane * 32 < p.V)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.lp + (int64_t)rn * p.stride_t + lane * 32));
+            if (rn < rows && lane * 32 < p.V) pf = p.lp + (int64_t)rn * p.stride_t + lane * 32;
         }
-        float ml = x[0];
-#pragma unroll
-        for (int j = 1; j < NV; ++j) ml = fmax_nan(ml, x[j]);
-        bool ok = can_fast && !__any_sync(kFullMask, ml != ml);
-        if (ok) {
-            unsigned key = f2key(ml), m = 0;
-            for (int i = 0; i <= k; ++i) {
-                m = __reduce_max_sync(kFullMask, key);
-                if (key == m) key = 0u;
-            }
-            const float tau = __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);   // inverse of f2key (m = 0 -> NaN)
-            int c = 0;
-#pragma unroll
-            for (int j = 0; j < NV; ++j) {      // FSET + IADD per slot (a predicate per slot would be spilled through P2R)
-                unsigned ge;
-                asm("set.ge.u32.f32 %0, %1, %2;" : "=r"(ge) : "f"(x[j]), "f"(tau));
-                if (valid(j)) c -= (int)ge;
-            }
-            int inc = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int up = __shfl_up_sync(kFullMask, inc, d);
-                if (lane >= d) inc += up;
-            }
-            const int count = __shfl_sync(kFullMask, inc, 31);
-            ok = (count <= kCandMax) && (count >= k + 1);
-            if (ok) {
-                float2* cand = reinterpret_cast<float2*>(cv);          // (value, index bits) pairs, dense
-                uint32_t dst = (uint32_t)__cvta_generic_to_shared(cand + (inc - c));
-#pragma unroll
-                for (int j = 0; j < NV; ++j) {      // 4 instructions per slot: setp, index, predicated 8-byte store + bump
-                    if (valid(j))
-                        asm volatile("{\n\t.reg .pred p;\n\t"
-                                     "setp.ge.f32 p, %1, %2;\n\t"
-                                     "@p st.shared.v2.b32 [%0], {%4, %3};\n\t"
-                                     "@p add.u32 %0, %0, 8;\n\t}"
-                                     : "+r"(dst) : "f"(x[j]), "f"(tau), "r"(lane + 32 * j), "r"(__float_as_uint(x[j])) : "memory");
-                }
-                if (lane == 0) cand[count] = make_float2(AVCTC_NEG_INF, 0.f);      // pad the last 16-byte group
-                __syncwarp();
-                bool tie = false;
-                if (count <= 32) {
-                    // one candidate per lane: rank = number of greater values; equal values collide on the rank
-                    const bool have = lane < count;
-                    const float2 me = have ? cand[lane] : make_float2(0.f, 0.f);
-                    int gt = 0;
-                    for (int j = 0; j < count; j += 2) {
-                        const float4 o = *reinterpret_cast<const float4*>(cand + j);
-                        unsigned g0, g1;            // FSET masks (0 / ~0): one IADD3 retires two compares
-                        asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(g0) : "f"(o.x), "f"(me.x));
-                        asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(g1) : "f"(o.z), "f"(me.x));
-                        gt -= (int)g0 + (int)g1;
-                    }
-                    const bool top = have && gt <= k;
-                    const unsigned tm = __ballot_sync(kFullMask, top);
-                    if (top) {
-                        tie = __popc(__match_any_sync(tm, gt)) > 1;
-                        tv[gt] = me.x; ti[gt] = __float_as_int(me.y);
-                    }
-                } else {
-                    for (int i = lane; i < count; i += 32) {
-                        const float2 me = cand[i];
-                        int gt = 0, eq = 0;
-                        for (int j = 0; j < count; j += 2) {
-                            const float4 o = *reinterpret_cast<const float4*>(cand + j);
-                            gt += (o.x > me.x) + (o.z > me.x);
-                            eq += (o.x == me.x) + (o.z == me.x);
-                        }
-                        if (gt <= k) { tv[gt] = me.x; ti[gt] = __float_as_int(me.y); tie = tie || (eq > 1); }
-                    }
-                }
-                ok = !__any_sync(kFullMask, tie);      // the first k+1 ranks hold distinct values: any algorithm agrees
-            }
-        }
-        if (!ok) {     // ties / NaNs: literal libstdc++ order on a staged copy of the row
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < NV; ++j) { const int c = lane + 32 * j; if (c < p.V) srow[c] = x[j]; }
-            __syncwarp();
-            if (p.use_nth) topk_nth_exact(srow, qi, p.V, k, tv, ti, lane);
-            else topk_exact(srow, p.V, k, tv, ti, lane);
-        }
-        __syncwarp();
+        topk_row<NV, MODE>(p, row, pf, can_fast, k, lane, cv, tv, ti, srow, qi);
         if (lane < k) {
             p.tk_val[(size_t)r * k + lane] = tv[lane];
             p.tk_idx[(size_t)r * k + lane] = ti[lane];
@@ -640,45 +721,9 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
         tv_nx += k; ti_nx += k;
         if (t + 1 < frames && lane < k) { tv_n = *tv_nx; ti_n = *ti_nx; }
         if (fast_enum) {
-            // <= 32 candidates: lane m IS candidate m.  Rank = number of strictly greater scores (16-byte shared loads,
-            // NaN padding compares false); equal scores give equal ranks, which match.any detects -> exact route below.
-            const bool in = (lane < p.n_enum) && (my_b < nb);
-            const unsigned inmask = __ballot_sync(kFullMask, in);
-            const int M = __popc(inmask);                      // candidates are ordered by beam: `in` is a prefix
-            const double* sc = score + cur * kBeamMax;
-            double* sn = score + (cur ^ 1) * kBeamMax;
-            const float lpv = __shfl_sync(kFullMask, tvv, my_j);
-            const int tok = __shfl_sync(kFullMask, tii, my_j);
-            const double s = in ? sc[my_b] + (double)lpv : __longlong_as_double(0x7ff8000000000000ll);
-            cand_s[lane] = s;
-            __syncwarp();
-            const int keep = min(k, M);
-            int r = 0, r1 = 0;                 // two chains of predicated increments (DSETP + @p IADD per compare)
-            const double2* c2 = reinterpret_cast<const double2*>(cand_s);
-#pragma unroll 4
-            for (int q = 0; q < M; q += 2) {
-                const double2 o = c2[q >> 1];
-                asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(r) : "d"(o.x), "d"(s));
-                asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(r1) : "d"(o.y), "d"(s));
-            }
-            r += r1;
-            bool clash = false;
-            if (in) clash = (__popc(__match_any_sync(inmask, r)) > 1) || (s != s);
-            if (__any_sync(kFullMask, clash)) {                // ties (or NaNs): insertion-order tie-break, as the reference's stable sort
-                r = 0;
-                for (int q = 0; q < M; ++q) {
-                    const double o = cand_s[q];
-                    r += (o > s) || (o == s && q < lane);
-                }
-            }
-            if (in && r < keep) {
-                sn[r] = s;
-                if (bp_in_smem) bp16_t[r] = (uint16_t)((my_b << 10) | tok);
-                else bp_t[r] = ((uint32_t)my_b << 24) | (uint32_t)tok;
-            }
-            __syncwarp();
+            nb = recur_step_enum32(tvv, tii, my_b, my_j, p.n_enum, nb, k, score + cur * kBeamMax, score + (cur ^ 1) * kBeamMax,
+                                   cand_s, bp16_t, bp_t, bp_in_smem, lane);
             cur ^= 1;
-            nb = keep;
             continue;
         }
         int M = 0;
@@ -719,44 +764,164 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
         cur ^= 1;
         nb = keep;
     }
-    if (frames > 0) {
-        const bool dbg = (p.dbg_paths != nullptr);
-        if (lane == 0 || (dbg && lane < nb)) {
-            int32_t* dst = dbg ? p.dbg_paths + ((size_t)n * k + lane) * p.T : path;
-            int idx = lane;
-            for (int t = frames - 1; t >= 0; --t) {
-                if (bp_in_smem) {
-                    const unsigned e = bp16[(size_t)t * k + idx];
-                    dst[t] = (int32_t)(e & 0x3ffu);
-                    idx = (int)(e >> 10);
-                } else {
-                    const uint32_t e = bp[(size_t)t * k + idx];
-                    dst[t] = (int32_t)(e & 0xffffffu);
-                    idx = (int)(e >> 24);
+    beam_finish(p, n, k, frames, nb, bp, bp16, bp_in_smem, score + cur * kBeamMax, path, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused decode (large batches of short utterances): a persistent CTA owns WHOLE utterances.  TW top-k warps take the
+// rows of the CTA's current utterance (warp w: frames w, w+TW, ...) and leave the [T,beam] lists in SHARED memory; RW
+// recurrence warps (utterances alternate between them) follow frame by frame, as soon as the leading frames of their
+// utterance are complete, while the top-k warps already read the next utterance.  Against the two-phase path: the
+// lists never travel through HBM (-2 x N*T*beam*8 bytes), and the latency-bound recurrence runs in the issue slots
+// the HBM-bound top-k warps leave idle instead of after them.
+//
+// Hand-off, all in shared memory (no block-wide barrier after start-up):
+//   prog[buf][w]  = (sequence << 12) | rows finished by top-k warp w for the utterance that occupies list buffer buf
+//                   (written by lane 0 after __syncwarp + fence; stale values carry an older sequence number);
+//   rdone[buf]    = number of sequences whose recurrence has read the last list of buffer buf (top-k warps wait for
+//                   sequence i - NBUF before they overwrite it).
+// Utterance i of a CTA (n = blockIdx.x + i*gridDim.x) uses buffer i % NBUF and recurrence warp i % RW.  No wait can
+// deadlock: top-k warps only wait for recurrences of OLDER sequences, a recurrence only for top-k rows of its own.
+__device__ __forceinline__ void fence_acq_rel_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
+__device__ __forceinline__ void fused_wait_ge(const int* word, int need) {
+    int spins = 0;
+    while (ld_volatile_shared_s32(word) < need) {
+        __nanosleep(64);
+        if (++spins > (1 << 24)) __trap();      // never hang the GPU on a protocol bug
+    }
+    fence_acq_rel_cta();
+}
+
+// leading frames of the utterance whose top-k lists are complete (warp-uniform)
+template <int TW>
+__device__ __forceinline__ int fused_frames_ready(const int* prog_buf, const int seq, const int lane) {
+    int c = 0x7fffffff;
+    if (lane < TW) {
+        const int v = ld_volatile_shared_s32(prog_buf + lane);
+        const int cnt = ((v >> 12) == seq) ? (v & 0xfff) : 0;
+        c = lane + cnt * TW;                    // first frame of warp `lane` that is not finished
+    }
+    return __reduce_min_sync(kFullMask, c);
+}
+
+constexpr int kFusedCtrlBytes = 256;            // prog[NBUF][8] + rdone[NBUF] ints
+__host__ __device__ inline size_t fused_list_bytes(int T, int beam) { return ((size_t)T * beam * 6 + 15) / 16 * 16; }
+__host__ __device__ inline size_t fused_recur_bytes(int T, int beam) {
+    return (2 * kBeamMax * 8 + 32 * 8 + (size_t)T * beam * 2 + 15) / 16 * 16;
+}
+
+// CTAs per SM the register file allows at 64 registers per thread (the top-k warps need 63), at most 4
+__host__ __device__ constexpr int fused_ctas_per_sm(int warps) { return 65536 / (warps * 32 * 64) < 4 ? 65536 / (warps * 32 * 64) : 4; }
+
+template <int NV, int MODE, int TW, int RW, int NBUF>
+__global__ void __launch_bounds__((TW + RW) * 32, fused_ctas_per_sm(TW + RW))
+beam_fused_kernel(const BeamParams p) {
+    static_assert(TW <= 8 && NBUF * 9 * 4 <= kFusedCtrlBytes, "control block layout");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = p.beam;
+    int* prog = reinterpret_cast<int*>(smem_raw);
+    int* rdone = prog + NBUF * 8;
+    const size_t per_warp = topk_smem_per_warp(p.row_floats, p.use_nth);
+    const size_t list_bytes = fused_list_bytes(p.T, k);
+    unsigned char* lists = smem_raw + kFusedCtrlBytes + (size_t)TW * per_warp;
+    unsigned char* recur = lists + (size_t)NBUF * list_bytes;
+    if (threadIdx.x < NBUF * 9) prog[threadIdx.x] = 0;
+    __syncthreads();
+    const int n_seq = (p.N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // host: gridDim.x <= N
+
+    if (warp < TW) {
+        // ==================================================================== top-k warps
+        unsigned char* mine = smem_raw + kFusedCtrlBytes + (size_t)warp * per_warp;
+        float* cv = reinterpret_cast<float*>(mine);
+        int* ci = reinterpret_cast<int*>(cv + kCandPad);
+        float* tv = reinterpret_cast<float*>(ci + kCandPad);
+        int* ti = reinterpret_cast<int*>(tv + kBeamMax + 1);
+        float* srow = reinterpret_cast<float*>(ti + kBeamMax + 1);
+        int* qi = reinterpret_cast<int*>(srow + p.row_floats);
+        const bool can_fast = p.fast && (k + 1 <= 32) && (p.V >= k + 1);
+        const bool pf_lane = p.prefetch && (lane * 32 < p.V);
+        for (int i = 0; i < n_seq; ++i) {
+            const int n = (int)blockIdx.x + i * (int)gridDim.x;
+            const int buf = i % NBUF;
+            const long long fl = p.lengths ? p.lengths[n] : p.T;
+            const int frames = (int)(fl < 0 ? 0 : (fl > p.T ? p.T : fl));
+            if (i >= NBUF) fused_wait_ge(&rdone[buf], i - NBUF + 1);
+            float* lv = reinterpret_cast<float*>(lists + (size_t)buf * list_bytes);
+            uint16_t* li = reinterpret_cast<uint16_t*>(lv + (size_t)p.T * k);
+            const float* base = p.lp + (int64_t)n * p.stride_n;
+            int done = 0;
+            for (int t = warp; t < frames; t += TW) {
+                const float* pf = nullptr;      // the warp's next row (same utterance, else its first row of the next one)
+                if (pf_lane) {
+                    if (t + TW < frames) pf = base + (int64_t)(t + TW) * p.stride_t + lane * 32;
+                    else if (i + 1 < n_seq && warp < p.T) pf = base + (int64_t)gridDim.x * p.stride_n + (int64_t)warp * p.stride_t + lane * 32;
+                }
+                topk_row<NV, MODE>(p, base + (int64_t)t * p.stride_t + lane, pf, can_fast, k, lane, cv, tv, ti, srow, qi);
+                if (lane < k) {
+                    lv[t * k + lane] = tv[lane];
+                    li[t * k + lane] = (uint16_t)ti[lane];
+                }
+                __syncwarp();
+                ++done;
+                if (lane == 0) {
+                    fence_acq_rel_cta();
+                    st_volatile_shared_s32(&prog[buf * 8 + warp], (i << 12) | done);
                 }
             }
-            if (dbg && lane == 0)
-                for (int t = 0; t < frames; ++t) path[t] = dst[t];
         }
-        if (p.dbg_scores && lane < nb) p.dbg_scores[(size_t)n * k + lane] = score[cur * kBeamMax + lane];
+        return;
     }
-    __syncwarp();
-    __threadfence_block();
-    int count = 0;
-    int32_t* out = p.out_ids + (size_t)n * p.T;
-    for (int t0 = 0; t0 < frames; t0 += 32) {
-        const int t = t0 + lane;
-        bool keepit = false;
-        int c = 0;
-        if (t < frames) {
-            c = path[t];
-            keepit = (c != p.blank) && (t == 0 || path[t - 1] != c);
+
+    // ======================================================================== recurrence warps
+    const int rw = warp - TW;
+    unsigned char* mine = recur + (size_t)rw * fused_recur_bytes(p.T, k);
+    double* score = reinterpret_cast<double*>(mine);                        // 2 * kBeamMax
+    double* cand_s = score + 2 * kBeamMax;                                  // 32
+    uint16_t* bp16 = reinterpret_cast<uint16_t*>(cand_s + 32);              // T * beam
+    int my_b = 0, my_j = 0;                    // candidate `lane` of the (b+1)(j+1) <= beam enumeration (beam-major)
+    {
+        int m = 0;
+        for (int b = 0; b < k; ++b)
+            for (int j = 0; j < k; ++j)
+                if ((b + 1) * (j + 1) <= k) { if (m == lane) { my_b = b; my_j = j; } ++m; }
+    }
+    for (int i = rw; i < n_seq; i += RW) {
+        const int n = (int)blockIdx.x + i * (int)gridDim.x;
+        const int buf = i % NBUF;
+        const long long fl = p.lengths ? p.lengths[n] : p.T;
+        const int frames = (int)(fl < 0 ? 0 : (fl > p.T ? p.T : fl));
+        const float* lv = reinterpret_cast<const float*>(lists + (size_t)buf * list_bytes);
+        const uint16_t* li = reinterpret_cast<const uint16_t*>(lv + (size_t)p.T * k);
+        int32_t* path = p.path_ws + (size_t)n * p.T;
+        if (lane == 0) score[0] = 0.0;
+        __syncwarp();
+        int nb = 1, cur = 0, ready = 0;
+        uint16_t* bp16_t = bp16;
+        for (int t = 0; t < frames; ++t, bp16_t += k) {
+            if (t >= ready) {
+                int spins = 0;
+                while ((ready = fused_frames_ready<TW>(prog + buf * 8, i, lane)) <= t) {
+                    __nanosleep(32);
+                    if (++spins > (1 << 24)) __trap();
+                }
+                fence_acq_rel_cta();
+            }
+            float tvv = 0.f; int tii = 0;
+            if (lane < k) { tvv = lv[t * k + lane]; tii = li[t * k + lane]; }
+            nb = recur_step_enum32(tvv, tii, my_b, my_j, p.n_enum, nb, k, score + cur * kBeamMax, score + (cur ^ 1) * kBeamMax,
+                                   cand_s, bp16_t, nullptr, 1, lane);
+            cur ^= 1;
         }
-        const unsigned m = __ballot_sync(kFullMask, keepit);
-        if (keepit) out[count + __popc(m & ((1u << lane) - 1))] = c;
-        count += __popc(m);
+        __syncwarp();                          // every lane has read its last list entry
+        if (lane == 0) {
+            fence_acq_rel_cta();
+            st_volatile_shared_s32(&rdone[buf], i + 1);
+        }
+        beam_finish(p, n, k, frames, nb, nullptr, bp16, 1, score + cur * kBeamMax, path, lane);
+        __syncwarp();
     }
-    if (lane == 0) p.out_len[n] = count;
 }
 
 static int enum_count(int k) {
@@ -768,7 +933,12 @@ static int enum_count(int k) {
 }
 
 struct BeamPlan { size_t off_bp, off_path, off_status, off_tv, off_ti, total; bool bp_in_smem; size_t smem; int row_floats, n_enum, use_nth;
-                  bool two_phase; size_t smem_topk, smem_recur_per_warp; bool bp_in_smem2; };
+                  bool two_phase; size_t smem_topk, smem_recur_per_warp; bool bp_in_smem2;
+                  bool fused_ok; int fused_tw, fused_rw, fused_nbuf; size_t smem_fused; };
+
+struct FusedCfg { int tw, rw, nbuf; };
+static const FusedCfg kFusedCfgs[] = {{7, 1, 2}, {6, 2, 2}, {8, 2, 2}, {6, 2, 3}};     // tuning knob "beam_fused_cfg"
+constexpr int kFusedMaxSmem = 75 * 1024;        // at least three CTAs per SM
 
 static bool beam_plan(int N, int T, int V, int beam, BeamPlan* pl) {
     if (beam < 1 || beam > kBeamMax || beam > V) return false;
@@ -797,7 +967,44 @@ static bool beam_plan(int N, int T, int V, int beam, BeamPlan* pl) {
     pl->off_tv = o; if (pl->two_phase) o = (o + (size_t)N * (T > 0 ? T : 1) * beam * 4 + 255) / 256 * 256;
     pl->off_ti = o; if (pl->two_phase) o = (o + (size_t)N * (T > 0 ? T : 1) * beam * 4 + 255) / 256 * 256;
     pl->total = o;
+    // fused path: vocabularies of 17..26 register slots per lane (513..832 classes), one-warp candidate lists, lists of
+    // NBUF utterances + the top-k scratch in shared memory (short utterances)
+    int cfg = avctc_tuning_get("beam_fused_cfg", 0);
+    if (cfg < 0 || cfg >= (int)(sizeof(kFusedCfgs) / sizeof(kFusedCfgs[0]))) cfg = 0;
+    pl->fused_tw = kFusedCfgs[cfg].tw; pl->fused_rw = kFusedCfgs[cfg].rw; pl->fused_nbuf = kFusedCfgs[cfg].nbuf;
+    pl->smem_fused = kFusedCtrlBytes + (size_t)pl->fused_tw * topk_smem_per_warp(pl->row_floats, pl->use_nth) +
+                     (size_t)pl->fused_nbuf * fused_list_bytes(T, beam) + (size_t)pl->fused_rw * fused_recur_bytes(T, beam);
+    const int need = (V + 31) / 32;
+    pl->fused_ok = pl->two_phase && pl->n_enum <= 32 && need >= 17 && need <= 26 && T >= 1 && T <= 4095 &&
+                   pl->smem_fused <= (size_t)kFusedMaxSmem;
     return true;
+}
+
+template <int NV, int MODE, int TW, int RW, int NBUF>
+static int launch_fused(const BeamParams& bp, size_t smem, int sms, cudaStream_t st) {
+    auto kern = beam_fused_kernel<NV, MODE, TW, RW, NBUF>;
+    static size_t configured = 0;
+    if (smem > configured) {
+        AVCTC_CUDA_RETURN(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedMaxSmem));
+        configured = kFusedMaxSmem;
+    }
+    int occ = 0;
+    AVCTC_CUDA_RETURN(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (TW + RW) * 32, smem));
+    if (occ < 1) return AVCTC_ERR_UNSUPPORTED;
+    long long grid = (long long)sms * occ;
+    const int cap = avctc_tuning_get("beam_fused_grid", 0);      // tests: few CTAs, many utterances per CTA
+    if (cap > 0 && cap < grid) grid = cap;
+    if (grid > bp.N) grid = bp.N;
+    kern<<<(unsigned)grid, (TW + RW) * 32, smem, st>>>(bp);
+    return (int)cudaGetLastError();
+}
+
+template <int NV, int MODE>
+static int launch_fused_cfg(const BeamPlan& pl, const BeamParams& bp, int sms, cudaStream_t st) {
+    if (pl.fused_tw == 7 && pl.fused_rw == 1) return launch_fused<NV, MODE, 7, 1, 2>(bp, pl.smem_fused, sms, st);
+    if (pl.fused_tw == 8) return launch_fused<NV, MODE, 8, 2, 2>(bp, pl.smem_fused, sms, st);
+    if (pl.fused_nbuf == 3) return launch_fused<NV, MODE, 6, 2, 3>(bp, pl.smem_fused, sms, st);
+    return launch_fused<NV, MODE, 6, 2, 2>(bp, pl.smem_fused, sms, st);
 }
 
 }  // namespace avctc
@@ -849,6 +1056,21 @@ extern "C" int avctc_beam_search(const float* log_probs, int64_t stride_n, int64
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        // fused kernel: "beam_fused" = 1 whenever eligible, 0 never, -1 (default) when every SM gets several utterances
+        // per resident CTA (below that the row-parallel top-k pass of the two-phase path fills the GPU better)
+        const int fused_knob = avctc_tuning_get("beam_fused", -1);
+        if (pl.fused_ok && (fused_knob > 0 || (fused_knob < 0 && N >= 4 * sms))) {
+            int rc;
+            if (need <= 25) {
+                if (V == 800) rc = launch_fused_cfg<25, 0>(pl, bp, sms, st);
+                else if (V > 768) rc = launch_fused_cfg<25, 1>(pl, bp, sms, st);
+                else rc = launch_fused_cfg<25, 2>(pl, bp, sms, st);
+            } else {
+                if (V == 832) rc = launch_fused_cfg<26, 0>(pl, bp, sms, st);
+                else rc = launch_fused_cfg<26, 1>(pl, bp, sms, st);
+            }
+            return rc;
+        }
         if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
 #define AVCTC_TOPK(NV, MODE)                                                                                        \
     do {                                                                                                            \

@@ -154,3 +154,60 @@ def test_beam_config5_full_size_equals_collapsed_row_maximum():
     # decoding is a pure function of the utterance: any sub-batch, in any order, gives the same lists
     sub = torch.tensor([4095, 17, 2048, 17], device="cuda")
     assert pkg.beam_search_batch(lp[sub], beam_width=k, blank=blank) == [res[4095], res[17], res[2048], res[17]]
+
+
+@pytest.fixture
+def fused_knobs():
+    pkg = _pkg()
+    yield pkg._lib.set_tuning
+    for key, dflt in (("beam_fused", -1), ("beam_fused_cfg", 0), ("beam_fused_grid", 0)):
+        pkg._lib.set_tuning(key, dflt)
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+def test_beam_fused_kernel_all_beams_vs_oracle(cfg, fused_knobs):
+    """Fused decode kernel (top-k warps + recurrence warps in one persistent CTA, lists in shared memory), forced on at a
+    small batch, every warp layout: all beams, scores and paths against the oracle, exact ties included."""
+    pkg = _pkg()
+    fused_knobs("beam_fused", 1); fused_knobs("beam_fused_cfg", cfg)
+    g = torch.Generator().manual_seed(10 + cfg)
+    N, T, V, k = 37, 150, 800, 10
+    lp = (3 * torch.randn(N, T, V, generator=g)).log_softmax(-1)
+    lp[::3] = lp[::3].bfloat16().float()
+    lp[4, 9] = -2.0                                       # a constant row: torch.topk's tie order
+    for grid in (0, 3):                                   # one utterance per CTA / 13 utterances through 2-3 list buffers
+        fused_knobs("beam_fused_grid", grid)
+        res, scores, paths = pkg.beam_search_batch(lp.cuda(), beam_width=k, blank=3, return_debug=True)
+        for i in range(N):
+            ids, sc, pa = oracle.beam_search(lp[i].numpy(), k, 3, debug=True)
+            assert res[i] == ids
+            assert np.array_equal(scores[i].numpy(), sc)
+            assert np.array_equal(paths[i].numpy(), pa)
+
+
+@pytest.mark.parametrize("V,k", [(801, 10), (832, 11), (790, 10), (600, 7), (513, 1)])
+def test_beam_fused_kernel_vocab_modes_lengths_strides(V, k, fused_knobs):
+    """Every template mode of the fused kernel (V = 32*NV, one ragged slot, generic), ragged lengths (0, 1, T), rows with
+    a stride != V, few CTAs so that list buffers are reused many times: identical to the two-phase kernels, and to the
+    oracle on a sample."""
+    pkg = _pkg()
+    g = torch.Generator().manual_seed(V * 7 + k)
+    N, T = 61, 40
+    lp = (2 * torch.randn(N, T, V + 5, generator=g)).log_softmax(-1)[:, :, :V]
+    lp[1::4] = lp[1::4].bfloat16().float()
+    lp[2, 7] = -2.5
+    lp[3, 3, : V // 2] = float("-inf")
+    lens = torch.randint(0, T + 1, (N,), generator=g)
+    lens[0], lens[5], lens[6] = T, 0, 1
+    dev = lp.cuda()
+    fused_knobs("beam_fused", 0)
+    want = pkg.beam_search_batch(dev, beam_width=k, blank=0, lengths=lens)
+    want_full = pkg.beam_search_batch(dev, beam_width=k, blank=0)
+    fused_knobs("beam_fused", 1)
+    for cfg, grid in ((0, 2), (1, 5), (3, 0)):
+        fused_knobs("beam_fused_cfg", cfg); fused_knobs("beam_fused_grid", grid)
+        assert pkg.beam_search_batch(dev, beam_width=k, blank=0, lengths=lens) == want
+        assert pkg.beam_search_batch(dev, beam_width=k, blank=0) == want_full
+    for i in range(0, N, 7):
+        assert want[i] == oracle.beam_search(lp[i, :int(lens[i])].contiguous().numpy(), k, 0)
+    assert want[5] == []
