@@ -52,9 +52,8 @@ AVCTC_API const char* avctc_status_string(int status);
  * alpha/beta rows are complete, 0 = it waits for the whole scan grid), "ctc_stage" (1 = the fp32 gradient pass stages each log-prob row in
  * shared memory with cp.async, 0 = register streaming), "ctc_stamp" (1 = the CTC kernels leave
  * globaltimer stamps in the workspace's flag block: debug / tests), "ctc_grad_warps", "beam_fast" (1 = threshold top-k fast path), "beam_two_phase" (1 = top-k for all rows first),
- * "beam_pf" (1 = L2 prefetch of the next row), "beam_fused" (-1 = auto: one fused top-k + recurrence kernel for large batches of
- * short utterances, 0 = never, 1 = whenever the shape is eligible), "beam_fused_cfg" (warp layout of the fused kernel),
- * "beam_fused_grid" (cap on its CTAs: tests), "pdl" (1 = programmatic dependent launch for the GEMM / softmax / CTC
+ * "beam_pf" (1 = L2 prefetch of the next row), "beam_fused" (-1 = auto: one fused top-k + recurrence kernel for short utterances
+ * up to 16 x SMs of them per call, 0 = never, 1 = whenever the shape is eligible), "beam_fused_grid" (cap on its CTAs: tests), "pdl" (1 = programmatic dependent launch for the GEMM / softmax / CTC
  * kernel chains), "lstm_tag" (BiLSTM step exchange: 0 counter barrier, 1 sentinel polling in the forward pass when
  * B <= 8, 2 forward always, 3 forward and backward), "lstm_groups" (batch groups of the BiLSTM kernels: 0 auto, n = n
  * groups), "gemm_dbg" (per-CTA timestamps).  Unknown keys return

@@ -535,7 +535,7 @@ __device__ __forceinline__ float fmax_nan(float a, float b) {      // NaN-propag
 template <int NV, int MODE>
 __device__ __forceinline__ void topk_row(const BeamParams& p, const float* __restrict__ row, const float* pf,
                                          const bool can_fast, const int k, const int lane, float* cv, float* tv, int* ti,
-                                         float* srow, int* qi) {
+                                         float* srow, int* qi, int* slow_lock = nullptr) {
     const int full_slots = (MODE == 0) ? NV : (MODE == 1) ? NV - 1 : p.V / 32;
     const bool tail_ok = lane + 32 * (NV - 1) < p.V;           // MODE 1: the one ragged slot
     auto valid = [&](int j) -> bool {
@@ -623,11 +623,20 @@ __device__ __forceinline__ void topk_row(const BeamParams& p, const float* __res
     }
     if (!ok) {     // ties / NaNs: literal libstdc++ order on a staged copy of the row
         __syncwarp();
+        if (slow_lock) {        // the staging buffer is shared by the CTA's top-k warps (fused kernel): one row at a time
+            if (lane == 0)
+                while (atomicCAS(slow_lock, 0, 1) != 0) __nanosleep(200);
+            __syncwarp();
+        }
 #pragma unroll
         for (int j = 0; j < NV; ++j) { const int c = lane + 32 * j; if (c < p.V) srow[c] = x[j]; }
         __syncwarp();
         if (p.use_nth) topk_nth_exact(srow, qi, p.V, k, tv, ti, lane);
         else topk_exact(srow, p.V, k, tv, ti, lane);
+        if (slow_lock) {
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); atomicExch(slow_lock, 0); }
+        }
     }
     __syncwarp();
 }
@@ -805,40 +814,42 @@ __device__ __forceinline__ int fused_frames_ready(const int* prog_buf, const int
     return __reduce_min_sync(kFullMask, c);
 }
 
-constexpr int kFusedCtrlBytes = 256;            // prog[NBUF][8] + rdone[NBUF] ints
+constexpr int kFusedCtrlBytes = 256;            // prog[NBUF][8] + rdone[NBUF] ints + the slow-path lock
+constexpr int kFusedScratch = (kCandPad * 8 + (kBeamMax + 1) * 8 + 15) / 16 * 16;   // per top-k warp: candidates + sorted top-(k+1)
 __host__ __device__ inline size_t fused_list_bytes(int T, int beam) { return ((size_t)T * beam * 6 + 15) / 16 * 16; }
+__host__ __device__ inline size_t fused_slow_bytes(int row_floats, int use_nth) {
+    return ((size_t)row_floats * 4 * (use_nth ? 2 : 1) + 15) / 16 * 16;
+}
 __host__ __device__ inline size_t fused_recur_bytes(int T, int beam) {
     return (2 * kBeamMax * 8 + 32 * 8 + (size_t)T * beam * 2 + 15) / 16 * 16;
 }
 
-// CTAs per SM the register file allows at 64 registers per thread (the top-k warps need 63), at most 4
-__host__ __device__ constexpr int fused_ctas_per_sm(int warps) { return 65536 / (warps * 32 * 64) < 4 ? 65536 / (warps * 32 * 64) : 4; }
-
+// 8 warps per CTA, four CTAs per SM: the 64 registers per thread the top-k rows need (63) fill the register file
 template <int NV, int MODE, int TW, int RW, int NBUF>
-__global__ void __launch_bounds__((TW + RW) * 32, fused_ctas_per_sm(TW + RW))
+__global__ void __launch_bounds__((TW + RW) * 32, 2048 / ((TW + RW) * 32) < 4 ? 2048 / ((TW + RW) * 32) : 4)
 beam_fused_kernel(const BeamParams p) {
-    static_assert(TW <= 8 && NBUF * 9 * 4 <= kFusedCtrlBytes, "control block layout");
+    static_assert(TW <= 8 && (NBUF * 9 + 1) * 4 <= kFusedCtrlBytes && RW <= NBUF, "control block layout");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = p.beam;
     int* prog = reinterpret_cast<int*>(smem_raw);
     int* rdone = prog + NBUF * 8;
-    const size_t per_warp = topk_smem_per_warp(p.row_floats, p.use_nth);
+    int* slow_lock = rdone + NBUF;
     const size_t list_bytes = fused_list_bytes(p.T, k);
-    unsigned char* lists = smem_raw + kFusedCtrlBytes + (size_t)TW * per_warp;
+    float* srow = reinterpret_cast<float*>(smem_raw + kFusedCtrlBytes + (size_t)TW * kFusedScratch);   // shared slow-path row (+ queue)
+    unsigned char* lists = reinterpret_cast<unsigned char*>(srow) + fused_slow_bytes(p.row_floats, p.use_nth);
     unsigned char* recur = lists + (size_t)NBUF * list_bytes;
-    if (threadIdx.x < NBUF * 9) prog[threadIdx.x] = 0;
+    if (threadIdx.x < NBUF * 9 + 1) prog[threadIdx.x] = 0;
     __syncthreads();
     const int n_seq = (p.N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // host: gridDim.x <= N
 
     if (warp < TW) {
         // ==================================================================== top-k warps
-        unsigned char* mine = smem_raw + kFusedCtrlBytes + (size_t)warp * per_warp;
+        unsigned char* mine = smem_raw + kFusedCtrlBytes + (size_t)warp * kFusedScratch;
         float* cv = reinterpret_cast<float*>(mine);
         int* ci = reinterpret_cast<int*>(cv + kCandPad);
         float* tv = reinterpret_cast<float*>(ci + kCandPad);
         int* ti = reinterpret_cast<int*>(tv + kBeamMax + 1);
-        float* srow = reinterpret_cast<float*>(ti + kBeamMax + 1);
         int* qi = reinterpret_cast<int*>(srow + p.row_floats);
         const bool can_fast = p.fast && (k + 1 <= 32) && (p.V >= k + 1);
         const bool pf_lane = p.prefetch && (lane * 32 < p.V);
@@ -858,7 +869,7 @@ beam_fused_kernel(const BeamParams p) {
                     if (t + TW < frames) pf = base + (int64_t)(t + TW) * p.stride_t + lane * 32;
                     else if (i + 1 < n_seq && warp < p.T) pf = base + (int64_t)gridDim.x * p.stride_n + (int64_t)warp * p.stride_t + lane * 32;
                 }
-                topk_row<NV, MODE>(p, base + (int64_t)t * p.stride_t + lane, pf, can_fast, k, lane, cv, tv, ti, srow, qi);
+                topk_row<NV, MODE>(p, base + (int64_t)t * p.stride_t + lane, pf, can_fast, k, lane, cv, tv, ti, srow, qi, slow_lock);
                 if (lane < k) {
                     lv[t * k + lane] = tv[lane];
                     li[t * k + lane] = (uint16_t)ti[lane];
@@ -934,10 +945,12 @@ static int enum_count(int k) {
 
 struct BeamPlan { size_t off_bp, off_path, off_status, off_tv, off_ti, total; bool bp_in_smem; size_t smem; int row_floats, n_enum, use_nth;
                   bool two_phase; size_t smem_topk, smem_recur_per_warp; bool bp_in_smem2;
-                  bool fused_ok; int fused_tw, fused_rw, fused_nbuf; size_t smem_fused; };
+                  bool fused_ok; size_t smem_fused; };
 
-struct FusedCfg { int tw, rw, nbuf; };
-static const FusedCfg kFusedCfgs[] = {{7, 1, 2}, {6, 2, 2}, {8, 2, 2}, {6, 2, 3}};     // tuning knob "beam_fused_cfg"
+// Warp layout of the fused kernel, measured on B200 at config 5 and its shards (profiles/r02_beam_fused_ab*.txt): six
+// top-k warps + two recurrence warps, two list buffers.  One recurrence warp per CTA cannot keep up with the top-k warps
+// at large batches; 10- and 12-warp CTAs or 48 registers per thread (more resident warps, a few spills) are slower.
+constexpr int kFusedTW = 6, kFusedRW = 2, kFusedNBuf = 2;
 constexpr int kFusedMaxSmem = 75 * 1024;        // at least three CTAs per SM
 
 static bool beam_plan(int N, int T, int V, int beam, BeamPlan* pl) {
@@ -969,42 +982,32 @@ static bool beam_plan(int N, int T, int V, int beam, BeamPlan* pl) {
     pl->total = o;
     // fused path: vocabularies of 17..26 register slots per lane (513..832 classes), one-warp candidate lists, lists of
     // NBUF utterances + the top-k scratch in shared memory (short utterances)
-    int cfg = avctc_tuning_get("beam_fused_cfg", 0);
-    if (cfg < 0 || cfg >= (int)(sizeof(kFusedCfgs) / sizeof(kFusedCfgs[0]))) cfg = 0;
-    pl->fused_tw = kFusedCfgs[cfg].tw; pl->fused_rw = kFusedCfgs[cfg].rw; pl->fused_nbuf = kFusedCfgs[cfg].nbuf;
-    pl->smem_fused = kFusedCtrlBytes + (size_t)pl->fused_tw * topk_smem_per_warp(pl->row_floats, pl->use_nth) +
-                     (size_t)pl->fused_nbuf * fused_list_bytes(T, beam) + (size_t)pl->fused_rw * fused_recur_bytes(T, beam);
+    pl->smem_fused = kFusedCtrlBytes + (size_t)kFusedTW * kFusedScratch + fused_slow_bytes(pl->row_floats, pl->use_nth) +
+                     (size_t)kFusedNBuf * fused_list_bytes(T, beam) + (size_t)kFusedRW * fused_recur_bytes(T, beam);
     const int need = (V + 31) / 32;
     pl->fused_ok = pl->two_phase && pl->n_enum <= 32 && need >= 17 && need <= 26 && T >= 1 && T <= 4095 &&
                    pl->smem_fused <= (size_t)kFusedMaxSmem;
     return true;
 }
 
-template <int NV, int MODE, int TW, int RW, int NBUF>
+template <int NV, int MODE>
 static int launch_fused(const BeamParams& bp, size_t smem, int sms, cudaStream_t st) {
-    auto kern = beam_fused_kernel<NV, MODE, TW, RW, NBUF>;
+    auto kern = beam_fused_kernel<NV, MODE, kFusedTW, kFusedRW, kFusedNBuf>;
+    constexpr int threads = (kFusedTW + kFusedRW) * 32;
     static size_t configured = 0;
     if (smem > configured) {
         AVCTC_CUDA_RETURN(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedMaxSmem));
         configured = kFusedMaxSmem;
     }
     int occ = 0;
-    AVCTC_CUDA_RETURN(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (TW + RW) * 32, smem));
+    AVCTC_CUDA_RETURN(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     if (occ < 1) return AVCTC_ERR_UNSUPPORTED;
     long long grid = (long long)sms * occ;
     const int cap = avctc_tuning_get("beam_fused_grid", 0);      // tests: few CTAs, many utterances per CTA
     if (cap > 0 && cap < grid) grid = cap;
     if (grid > bp.N) grid = bp.N;
-    kern<<<(unsigned)grid, (TW + RW) * 32, smem, st>>>(bp);
+    kern<<<(unsigned)grid, threads, smem, st>>>(bp);
     return (int)cudaGetLastError();
-}
-
-template <int NV, int MODE>
-static int launch_fused_cfg(const BeamPlan& pl, const BeamParams& bp, int sms, cudaStream_t st) {
-    if (pl.fused_tw == 7 && pl.fused_rw == 1) return launch_fused<NV, MODE, 7, 1, 2>(bp, pl.smem_fused, sms, st);
-    if (pl.fused_tw == 8) return launch_fused<NV, MODE, 8, 2, 2>(bp, pl.smem_fused, sms, st);
-    if (pl.fused_nbuf == 3) return launch_fused<NV, MODE, 6, 2, 3>(bp, pl.smem_fused, sms, st);
-    return launch_fused<NV, MODE, 6, 2, 2>(bp, pl.smem_fused, sms, st);
 }
 
 }  // namespace avctc
@@ -1056,18 +1059,21 @@ extern "C" int avctc_beam_search(const float* log_probs, int64_t stride_n, int64
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        // fused kernel: "beam_fused" = 1 whenever eligible, 0 never, -1 (default) when every SM gets several utterances
-        // per resident CTA (below that the row-parallel top-k pass of the two-phase path fills the GPU better)
+        // fused kernel: "beam_fused" = 1 whenever eligible, 0 never, -1 (default) up to four utterances per resident CTA.
+        // Measured (profiles/r02_beam_fused_ab.txt): both routes are instruction-issue bound, the fused kernel hides the
+        // recurrence's latency and saves a launch and the HBM round trip of the lists (1.05x at 2048 utterances, 1.2x at
+        // 1024, 1.35x at 592), but its hand-off polling costs ~6 % more instructions once every SM is saturated anyway
+        // (0.93x at 4096).
         const int fused_knob = avctc_tuning_get("beam_fused", -1);
-        if (pl.fused_ok && (fused_knob > 0 || (fused_knob < 0 && N >= 4 * sms))) {
+        if (pl.fused_ok && (fused_knob > 0 || (fused_knob < 0 && N <= 16 * sms))) {
             int rc;
             if (need <= 25) {
-                if (V == 800) rc = launch_fused_cfg<25, 0>(pl, bp, sms, st);
-                else if (V > 768) rc = launch_fused_cfg<25, 1>(pl, bp, sms, st);
-                else rc = launch_fused_cfg<25, 2>(pl, bp, sms, st);
+                if (V == 800) rc = launch_fused<25, 0>(bp, pl.smem_fused, sms, st);
+                else if (V > 768) rc = launch_fused<25, 1>(bp, pl.smem_fused, sms, st);
+                else rc = launch_fused<25, 2>(bp, pl.smem_fused, sms, st);
             } else {
-                if (V == 832) rc = launch_fused_cfg<26, 0>(pl, bp, sms, st);
-                else rc = launch_fused_cfg<26, 1>(pl, bp, sms, st);
+                if (V == 832) rc = launch_fused<26, 0>(bp, pl.smem_fused, sms, st);
+                else rc = launch_fused<26, 1>(bp, pl.smem_fused, sms, st);
             }
             return rc;
         }

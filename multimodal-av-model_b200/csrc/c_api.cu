@@ -5,7 +5,7 @@
 
 namespace {
 struct Knob { const char* key; int value; };
-Knob g_knobs[] = {{"ctc_k", 0}, {"ctc_lin", 1}, {"ctc_ws", 1}, {"beam_fast", 1}, {"beam_two_phase", 1}, {"ctc_grad_warps", 0}, {"gemm_dbg", 0}, {"pdl", 1}, {"ctc_pf", 1}, {"beam_pf", 1}, {"lstm_tag", 1}, {"lstm_groups", 0}, {"ctc_stage", 1}, {"ctc_overlap", 1}, {"ctc_stamp", 0}, {"beam_fused", -1}, {"beam_fused_cfg", 0}, {"beam_fused_grid", 0}};
+Knob g_knobs[] = {{"ctc_k", 0}, {"ctc_lin", 1}, {"ctc_ws", 1}, {"beam_fast", 1}, {"beam_two_phase", 1}, {"ctc_grad_warps", 0}, {"gemm_dbg", 0}, {"pdl", 1}, {"ctc_pf", 1}, {"beam_pf", 1}, {"lstm_tag", 1}, {"lstm_groups", 0}, {"ctc_stage", 1}, {"ctc_overlap", 1}, {"ctc_stamp", 0}, {"beam_fused", -1}, {"beam_fused_grid", 0}};
 }  // namespace
 
 int avctc_tuning_get(const char* key, int dflt) {

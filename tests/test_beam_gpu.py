@@ -160,29 +160,28 @@ def test_beam_config5_full_size_equals_collapsed_row_maximum():
 def fused_knobs():
     pkg = _pkg()
     yield pkg._lib.set_tuning
-    for key, dflt in (("beam_fused", -1), ("beam_fused_cfg", 0), ("beam_fused_grid", 0)):
+    for key, dflt in (("beam_fused", -1), ("beam_fused_grid", 0)):
         pkg._lib.set_tuning(key, dflt)
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
-def test_beam_fused_kernel_all_beams_vs_oracle(cfg, fused_knobs):
-    """Fused decode kernel (top-k warps + recurrence warps in one persistent CTA, lists in shared memory), forced on at a
-    small batch, every warp layout: all beams, scores and paths against the oracle, exact ties included."""
+@pytest.mark.parametrize("grid", [0, 3, 1])
+def test_beam_fused_kernel_all_beams_vs_oracle(grid, fused_knobs):
+    """Fused decode kernel (top-k warps + recurrence warps in one persistent CTA, lists in shared memory): all beams,
+    scores and paths against the oracle, exact ties included; one utterance per CTA, and 13 / 37 utterances through the
+    two list buffers of a CTA."""
     pkg = _pkg()
-    fused_knobs("beam_fused", 1); fused_knobs("beam_fused_cfg", cfg)
-    g = torch.Generator().manual_seed(10 + cfg)
+    fused_knobs("beam_fused", 1); fused_knobs("beam_fused_grid", grid)
+    g = torch.Generator().manual_seed(10 + grid)
     N, T, V, k = 37, 150, 800, 10
     lp = (3 * torch.randn(N, T, V, generator=g)).log_softmax(-1)
     lp[::3] = lp[::3].bfloat16().float()
     lp[4, 9] = -2.0                                       # a constant row: torch.topk's tie order
-    for grid in (0, 3):                                   # one utterance per CTA / 13 utterances through 2-3 list buffers
-        fused_knobs("beam_fused_grid", grid)
-        res, scores, paths = pkg.beam_search_batch(lp.cuda(), beam_width=k, blank=3, return_debug=True)
-        for i in range(N):
-            ids, sc, pa = oracle.beam_search(lp[i].numpy(), k, 3, debug=True)
-            assert res[i] == ids
-            assert np.array_equal(scores[i].numpy(), sc)
-            assert np.array_equal(paths[i].numpy(), pa)
+    res, scores, paths = pkg.beam_search_batch(lp.cuda(), beam_width=k, blank=3, return_debug=True)
+    for i in range(N):
+        ids, sc, pa = oracle.beam_search(lp[i].numpy(), k, 3, debug=True)
+        assert res[i] == ids
+        assert np.array_equal(scores[i].numpy(), sc)
+        assert np.array_equal(paths[i].numpy(), pa)
 
 
 @pytest.mark.parametrize("V,k", [(801, 10), (832, 11), (790, 10), (600, 7), (513, 1)])
@@ -204,10 +203,22 @@ def test_beam_fused_kernel_vocab_modes_lengths_strides(V, k, fused_knobs):
     want = pkg.beam_search_batch(dev, beam_width=k, blank=0, lengths=lens)
     want_full = pkg.beam_search_batch(dev, beam_width=k, blank=0)
     fused_knobs("beam_fused", 1)
-    for cfg, grid in ((0, 2), (1, 5), (3, 0)):
-        fused_knobs("beam_fused_cfg", cfg); fused_knobs("beam_fused_grid", grid)
+    for grid in (2, 5, 0):
+        fused_knobs("beam_fused_grid", grid)
         assert pkg.beam_search_batch(dev, beam_width=k, blank=0, lengths=lens) == want
         assert pkg.beam_search_batch(dev, beam_width=k, blank=0) == want_full
     for i in range(0, N, 7):
         assert want[i] == oracle.beam_search(lp[i, :int(lens[i])].contiguous().numpy(), k, 0)
     assert want[5] == []
+
+
+def test_beam_auto_policy_is_value_neutral(fused_knobs):
+    """The default route (fused kernel up to 16 x SMs utterances, two-phase kernels above) returns what either forced
+    route returns."""
+    pkg = _pkg()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    lp = (3 * torch.randn(700, 60, 800, generator=g, device="cuda")).log_softmax(-1)
+    auto = pkg.beam_search_batch(lp, beam_width=10, blank=3)
+    for forced in (0, 1):
+        fused_knobs("beam_fused", forced)
+        assert pkg.beam_search_batch(lp, beam_width=10, blank=3) == auto

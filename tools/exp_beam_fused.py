@@ -1,5 +1,5 @@
-"""A/B of the beam decode kernels on one B200: two-phase (top-k pass, then recurrence) against the fused kernel in every
-warp layout, at config 5 (4096 x [150, 800], beam 10) and at smaller batches (where the auto policy must switch).
+"""A/B of the beam decode kernels on one B200: two-phase (top-k pass, then recurrence) against the fused kernel and
+the default policy, at config 5 (4096 x [150, 800], beam 10) and at smaller batches (where the auto policy must switch).
 Each variant's token lists are compared with the two-phase result before it is timed.
 
     python tools/exp_beam_fused.py [out.txt]
@@ -31,7 +31,7 @@ def main():
     peak = bench.measured_peaks()["hbm"]
     g = torch.Generator(device="cuda").manual_seed(7)
     lp_all = (3 * torch.randn(4096, T, V, generator=g, device=dev)).log_softmax(-1)
-    for N in (4096, 3072, 2048, 592, 16):
+    for N in (4096, 3072, 2048, 1024, 512, 64, 16):
         lp = lp_all[:N]
         wsb = int(L.avctc_beam_workspace_bytes(N, T, V, beam))
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
@@ -41,11 +41,10 @@ def main():
         def run():
             _lib.check(L.avctc_beam_search(lp.data_ptr(), lp.stride(0), lp.stride(1), N, T, V, None, beam, blank,
                                            out.data_ptr(), ol.data_ptr(), None, None, ws.data_ptr(), wsb, st), "beam")
-        variants = [("two-phase", 0, 0)] + [(f"fused cfg {c}", 1, c) for c in range(4)]
+        variants = [("two-phase", 0), ("fused", 1), ("auto", -1)]
         want = None
-        for name, fused, cfg in variants:
+        for name, fused in variants:
             _lib.set_tuning("beam_fused", fused)
-            _lib.set_tuning("beam_fused_cfg", cfg)
             out.zero_(); ol.zero_()
             run()
             torch.cuda.synchronize(dev)
@@ -59,7 +58,6 @@ def main():
             say(f"N={N:5d}  {name:12s}  mean {mean * 1e3:8.1f} us  min {best * 1e3:8.1f} us  {gb / mean * 1e3:7.1f} GB/s  "
                 f"frac {gb / mean * 1e3 / peak:.3f}  identical={same}")
         _lib.set_tuning("beam_fused", -1)
-        _lib.set_tuning("beam_fused_cfg", 0)
     if out_path:
         with open(out_path, "w") as f:
             f.write("\n".join(lines) + "\n")
