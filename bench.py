@@ -429,6 +429,19 @@ def bench_beam(device, rank, world, iters=5, N=4096, T=150, beam=10, comparators
         _lib.check(L.avctc_beam_search(lp.data_ptr(), lp.stride(0), lp.stride(1), n, T, VOCAB, None, beam, BLANK,
                                        out.data_ptr(), ol.data_ptr(), None, None, ws.data_ptr(), wsb, st), "beam")
     t_k, _ = event_time(kernels, iters, 2, flush, device)
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+
+    def route(m):           # beam_search.cu: one fused kernel up to 16 x SMs short utterances per call, two kernels above
+        return "fused top-k + recurrence kernel" if m <= 16 * sms else "two-phase (top-k pass, then recurrence)"
+    sweep = {}
+    if world == 1:          # what one rank decodes when the same 4096 utterances are sharded over 2 / 4 / 8 GPUs
+        for m in (N // 2, N // 4, N // 8):
+            def kernels_m(m=m):
+                _lib.check(L.avctc_beam_search(lp.data_ptr(), lp.stride(0), lp.stride(1), m, T, VOCAB, None, beam, BLANK,
+                                               out.data_ptr(), ol.data_ptr(), None, None, ws.data_ptr(), wsb, st), "beam")
+            t_m, _ = event_time(kernels_m, iters, 2, flush, device)
+            sweep[str(m)] = dict(ms=t_m, utt_per_s=m / t_m * 1e3, hbm_frac=m * T * VOCAB * 4 / t_m / 1e6 / measured_peaks()["hbm"],
+                                 route=route(m))
     for _ in range(1):
         pkg.beam_search_batch(lp_host, beam_width=beam, blank=BLANK)       # host tensor: chunked copy || decode
     torch.cuda.synchronize(device)
@@ -439,7 +452,7 @@ def bench_beam(device, rank, world, iters=5, N=4096, T=150, beam=10, comparators
     out_d = dict(utterances=N, shard=n, beam=beam, ms=t_k, utt_per_s_shard=n / t_k * 1e3, e2e_ms=t_e2e,
                  e2e_utt_per_s_shard=n / t_e2e * 1e3, gbs=n * T * VOCAB * 4 / t_k / 1e6,
                  hbm_frac=n * T * VOCAB * 4 / t_k / 1e6 / measured_peaks()["hbm"],
-                 algorithmic_bytes=n * T * VOCAB * 4,
+                 algorithmic_bytes=n * T * VOCAB * 4, route=route(n), shard_sweep=sweep,
                  note="ms = decode kernels only (log-probs resident in HBM, ids left on the device) = what evaluate() pays, its "
                       "log-probs are device tensors; e2e = beam_search_batch() on pinned host log-probs: chunked H2D overlapped "
                       "with the decode kernels + D2H of ids + Python list construction (PCIe-bound)")

@@ -6,7 +6,7 @@ sys.path.insert(0, root)
 sys.path.insert(0, os.path.join(root, "tests"))
 import pytest
 from multimodal_av_model_b200 import _lib
-DEFAULTS = {"pdl": 1, "ctc_ws": 1, "ctc_lin": 1, "ctc_pf": 1, "ctc_overlap": 1, "ctc_stage": 1, "beam_two_phase": 1, "beam_pf": 1,
+DEFAULTS = {"pdl": 1, "ctc_ws": 1, "ctc_lin": 1, "ctc_pf": 1, "ctc_overlap": 1, "ctc_stage": 1, "beam_two_phase": 1, "beam_pf": 1, "beam_fused": -1,
             "lstm_groups": 0}
 os.environ["AVCTC_KNOB_MATRIX"] = "1"      # tests that assert a launch mode was taken skip that assertion
 CASES = [("pdl", 0, ["tests/test_ctc_gpu.py", "tests/test_fusion_gpu.py", "tests/test_attention_gpu.py", "tests/test_ctc_head_gpu.py"]),
@@ -17,7 +17,8 @@ CASES = [("pdl", 0, ["tests/test_ctc_gpu.py", "tests/test_fusion_gpu.py", "tests
          ("ctc_stage", 0, ["tests/test_ctc_gpu.py"]),
          ("lstm_groups", 1, ["tests/test_lstm_gpu.py", "tests/test_bench_sizes_gpu.py"]),
          ("beam_two_phase", 0, ["tests/test_beam_gpu.py"]),
-         ("beam_pf", 0, ["tests/test_beam_gpu.py"])]
+         ("beam_pf", 0, ["tests/test_beam_gpu.py"]),
+         ("beam_fused", 0, ["tests/test_beam_gpu.py"])]
 bad = 0
 for key, val, files in CASES:
     for k, v in DEFAULTS.items():
