@@ -558,13 +558,15 @@ __device__ __forceinline__ void topk_row(const BeamParams& p, const float* __res
             if (key == m) key = 0u;
         }
         const float tau = __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);   // inverse of f2key (m = 0 -> NaN)
-        int c = 0;
+        int c = 0, c1 = 0;
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {      // FSET + IADD per slot (a predicate per slot would be spilled through P2R)
-            unsigned ge;
-            asm("set.ge.u32.f32 %0, %1, %2;" : "=r"(ge) : "f"(x[j]), "f"(tau));
-            if (valid(j)) c -= (int)ge;
+        for (int j = 0; j < NV; ++j) {      // FSETP + predicated IADD per slot, two chains (set.ge.u32 would be FSETP + SEL + IADD)
+            if (valid(j)) {
+                if (j & 1) asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(c1) : "f"(x[j]), "f"(tau));
+                else asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(c) : "f"(x[j]), "f"(tau));
+            }
         }
+        c += c1;
         int inc = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -585,22 +587,35 @@ __device__ __forceinline__ void topk_row(const BeamParams& p, const float* __res
                                  "@p add.u32 %0, %0, 8;\n\t}"
                                  : "+r"(dst) : "f"(x[j]), "f"(tau), "r"(lane + 32 * j), "r"(__float_as_uint(x[j])) : "memory");
             }
-            if (lane == 0) cand[count] = make_float2(AVCTC_NEG_INF, 0.f);      // pad the last 16-byte group
+            // pad: one candidate per lane when count <= 32 (slots [count, 32) = -inf), else the last 16-byte group
+            if (count <= 32) { if (lane >= count) cand[lane] = make_float2(AVCTC_NEG_INF, 0.f); }
+            else if (lane == 0) cand[count] = make_float2(AVCTC_NEG_INF, 0.f);
             __syncwarp();
             bool tie = false;
             if (count <= 32) {
-                // one candidate per lane: rank = number of greater values; equal values collide on the rank
-                const bool have = lane < count;
-                const float2 me = have ? cand[lane] : make_float2(0.f, 0.f);
+                // one candidate per lane: rank = number of greater values, counted over the 32 slots in two unrolled halves
+                // (eight 16-byte loads in flight, four chains of FSETP + predicated IADD); equal values collide on the rank
+                const float2 me = cand[lane];
+                const float4* c4 = reinterpret_cast<const float4*>(cand);
                 int gt = 0;
-                for (int j = 0; j < count; j += 2) {
-                    const float4 o = *reinterpret_cast<const float4*>(cand + j);
-                    unsigned g0, g1;            // FSET masks (0 / ~0): one IADD3 retires two compares
-                    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(g0) : "f"(o.x), "f"(me.x));
-                    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(g1) : "f"(o.z), "f"(me.x));
-                    gt -= (int)g0 + (int)g1;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h == 0 || count > 16) {
+                        int ga = 0, gb = 0, gc = 0, gd = 0;
+                        float4 o[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) o[q] = c4[8 * h + q];
+#pragma unroll
+                        for (int q = 0; q < 8; q += 2) {
+                            asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(ga) : "f"(o[q].x), "f"(me.x));
+                            asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(gb) : "f"(o[q].z), "f"(me.x));
+                            asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(gc) : "f"(o[q + 1].x), "f"(me.x));
+                            asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(gd) : "f"(o[q + 1].z), "f"(me.x));
+                        }
+                        gt += (ga + gb) + (gc + gd);
+                    }
                 }
-                const bool top = have && gt <= k;
+                const bool top = (lane < count) && gt <= k;
                 const unsigned tm = __ballot_sync(kFullMask, top);
                 if (top) {
                     tie = __popc(__match_any_sync(tm, gt)) > 1;
