@@ -1571,9 +1571,8 @@ __global__ void __launch_bounds__(256, (K <= 8) ? (sizeof(TIn) == 4 ? 3 : 4) : 1
     const unsigned long long tg0 = p.stamp ? global_timer_ns() : 0ull;
     if (p.stamp && p.flag && threadIdx.x == 0) {      // debug: histogram of CTA entry times, 16 us buckets from the first scan CTA
         const unsigned long long t0 = ~*reinterpret_cast<const volatile unsigned long long*>(reinterpret_cast<const char*>(p.flag) + 64);
-        const long long d = (long long)(tg0 - t0);
-        int bk = d < 0 ? 0 : (int)(d / 16000);
-        bk = bk > 15 ? 15 : bk;
+        const long long q = (long long)(tg0 - t0) / 16000;     // no scan stamp (single-warp scan): t0 = ~0, q is huge
+        const int bk = q < 0 ? 0 : (q > 15 ? 15 : (int)q);
         atomicAdd(const_cast<int*>(p.flag) + 44 + bk, 1);
     }
     // Launched with the PDL attribute, this grid can be resident while the scan before it on the stream is still
