@@ -297,34 +297,50 @@ __device__ bool topk_fast(const float* row, int V, int k, float* cv, int* ci, vo
     return true;
 }
 
+// 32-bit shared-window accessors: the recurrence's scratch is addressed without the generic-pointer conversion the
+// compiler would otherwise re-derive (S2UR + ULEA) every frame
+__device__ __forceinline__ uint32_t smem_addr(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ double2 lds_v2f64(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+
 // One frame of the prune when the (b+1)(j+1) <= beam candidates fit one warp: lane m IS candidate m = (my_b, my_j).
-// (tvv, tii) = this frame's top-k list (lane j holds entry j); sc / sn = scores of the current / next beams.
-// Rank = number of strictly greater scores (16-byte shared loads, NaN padding compares false); equal scores give
-// equal ranks, which match.any detects -> stable (insertion-order) ranks.  Returns the number of beams kept.
+// (tvv, tii) = this frame's top-k list (lane j holds entry j).  Shared addresses: sc_a / sn_a = scores of the current /
+// next beams (kBeamMax doubles each), cand_a = 32 candidate scores, bp16_a = this frame's 16-bit back-pointer row (0:
+// 32-bit entries through bp_t).  Rank = number of strictly greater scores; equal scores give equal ranks: two survivors
+// that share a rank store to the same slot, which each detects by reading back the lane tag it left beside its score
+// (the tags live in the current-score row, dead once the candidates are built) -> stable (insertion-order) ranks and a
+// second store.  (A match.any on the ranks costs several hundred cycles of latency per frame: ncu, round 2.)
+// Returns the number of beams kept.
 __device__ __forceinline__ int recur_step_enum32(const float tvv, const int tii, const int my_b, const int my_j,
-                                                 const int n_enum, const int nb, const int k, const double* sc, double* sn,
-                                                 double* cand_s, uint16_t* bp16_t, uint32_t* bp_t, const int bp_in_smem,
-                                                 const int lane) {
+                                                 const int n_enum, const int nb, const int k, const uint32_t sc_a,
+                                                 const uint32_t sn_a, const uint32_t cand_a, const uint32_t bp16_a,
+                                                 uint32_t* bp_t, const int lane) {
     const bool in = (lane < n_enum) && (my_b < nb);
-    const unsigned inmask = __ballot_sync(kFullMask, in);
-    const int M = __popc(inmask);                      // candidates are ordered by beam: `in` is a prefix
+    const int M = __popc(__ballot_sync(kFullMask, in));        // candidates are ordered by beam: `in` is a prefix
     const float lpv = __shfl_sync(kFullMask, tvv, my_j);
     const int tok = __shfl_sync(kFullMask, tii, my_j);
-    const double s = in ? sc[my_b] + (double)lpv : __longlong_as_double(0x7ff8000000000000ll);
-    cand_s[lane] = s;
+    const double s = in ? lds_f64(sc_a + my_b * 8) + (double)lpv : __longlong_as_double(0x7ff8000000000000ll);
+    sts_f64(cand_a + lane * 8, s);
     __syncwarp();
     const int keep = min(k, M);
     // every lane wrote its slot (NaN where it holds no candidate), so the 32 slots are compared in two unrolled halves:
     // eight 16-byte loads in flight, four chains of predicated increments (DSETP + @p IADD per compare), no loop tail
     int r = 0;
-    const double2* c2 = reinterpret_cast<const double2*>(cand_s);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         if (h == 0 || M > 16) {
             int ra = 0, rb = 0, rc = 0, rd = 0;
             double2 o[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) o[q] = c2[8 * h + q];
+            for (int q = 0; q < 8; ++q) o[q] = lds_v2f64(cand_a + (8 * h + q) * 16);
 #pragma unroll
             for (int q = 0; q < 8; q += 2) {
                 asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(ra) : "d"(o[q].x), "d"(s));
@@ -335,21 +351,30 @@ __device__ __forceinline__ int recur_step_enum32(const float tvv, const int tii,
             r += (ra + rb) + (rc + rd);
         }
     }
-    bool clash = false;
-    if (in) clash = (__popc(__match_any_sync(inmask, r)) > 1) || (s != s);
+    const unsigned bpe16 = (unsigned)((my_b << 10) | tok);
+    const uint32_t bpe32 = ((uint32_t)my_b << 24) | (uint32_t)tok;
+    const bool wr = in && r < keep;
+    if (wr) {
+        sts_f64(sn_a + r * 8, s);
+        sts_s32(sc_a + r * 4, lane);
+        if (bp16_a) sts_u16(bp16_a + r * 2, bpe16);
+        else bp_t[r] = bpe32;
+    }
+    __syncwarp();
+    const bool clash = (wr && lds_s32(sc_a + r * 4) != lane) || (in && s != s);
     if (__any_sync(kFullMask, clash)) {                // ties (or NaNs): insertion-order tie-break, as the reference's stable sort
         r = 0;
         for (int q = 0; q < M; ++q) {
-            const double o = cand_s[q];
+            const double o = lds_f64(cand_a + q * 8);
             r += (o > s) || (o == s && q < lane);
         }
+        if (in && r < keep) {
+            sts_f64(sn_a + r * 8, s);
+            if (bp16_a) sts_u16(bp16_a + r * 2, bpe16);
+            else bp_t[r] = bpe32;
+        }
+        __syncwarp();
     }
-    if (in && r < keep) {
-        sn[r] = s;
-        if (bp_in_smem) bp16_t[r] = (uint16_t)((my_b << 10) | tok);
-        else bp_t[r] = ((uint32_t)my_b << 24) | (uint32_t)tok;
-    }
-    __syncwarp();
     return keep;
 }
 
@@ -740,13 +765,14 @@ __global__ void __launch_bounds__(kRecurWarps * 32) beam_recur_kernel(const Beam
     const int32_t* ti_nx = tip + lane;
     uint32_t* bp_t = bp;
     uint16_t* bp16_t = bp16;
+    const uint32_t score_a = smem_addr(score), cand_a = smem_addr(cand_s), bp16_a = smem_addr(bp16);
     for (int t = 0; t < frames; ++t, bp_t += k, bp16_t += k) {
         const float tvv = tv_n; const int tii = ti_n;
         tv_nx += k; ti_nx += k;
         if (t + 1 < frames && lane < k) { tv_n = *tv_nx; ti_n = *ti_nx; }
         if (fast_enum) {
-            nb = recur_step_enum32(tvv, tii, my_b, my_j, p.n_enum, nb, k, score + cur * kBeamMax, score + (cur ^ 1) * kBeamMax,
-                                   cand_s, bp16_t, bp_t, bp_in_smem, lane);
+            nb = recur_step_enum32(tvv, tii, my_b, my_j, p.n_enum, nb, k, score_a + cur * (kBeamMax * 8),
+                                   score_a + (cur ^ 1) * (kBeamMax * 8), cand_a, bp_in_smem ? bp16_a + t * k * 2 : 0u, bp_t, lane);
             cur ^= 1;
             continue;
         }
@@ -906,6 +932,7 @@ beam_fused_kernel(const BeamParams p) {
     double* score = reinterpret_cast<double*>(mine);                        // 2 * kBeamMax
     double* cand_s = score + 2 * kBeamMax;                                  // 32
     uint16_t* bp16 = reinterpret_cast<uint16_t*>(cand_s + 32);              // T * beam
+    const uint32_t score_a = smem_addr(score), cand_a = smem_addr(cand_s), bp16_a = smem_addr(bp16);
     int my_b = 0, my_j = 0;                    // candidate `lane` of the (b+1)(j+1) <= beam enumeration (beam-major)
     {
         int m = 0;
@@ -924,8 +951,7 @@ beam_fused_kernel(const BeamParams p) {
         if (lane == 0) score[0] = 0.0;
         __syncwarp();
         int nb = 1, cur = 0, ready = 0;
-        uint16_t* bp16_t = bp16;
-        for (int t = 0; t < frames; ++t, bp16_t += k) {
+        for (int t = 0; t < frames; ++t) {
             if (t >= ready) {
                 int spins = 0;
                 while ((ready = fused_frames_ready<TW>(prog + buf * 8, i, lane)) <= t) {
@@ -936,8 +962,8 @@ beam_fused_kernel(const BeamParams p) {
             }
             float tvv = 0.f; int tii = 0;
             if (lane < k) { tvv = lv[t * k + lane]; tii = li[t * k + lane]; }
-            nb = recur_step_enum32(tvv, tii, my_b, my_j, p.n_enum, nb, k, score + cur * kBeamMax, score + (cur ^ 1) * kBeamMax,
-                                   cand_s, bp16_t, nullptr, 1, lane);
+            nb = recur_step_enum32(tvv, tii, my_b, my_j, p.n_enum, nb, k, score_a + cur * (kBeamMax * 8),
+                                   score_a + (cur ^ 1) * (kBeamMax * 8), cand_a, bp16_a + t * k * 2, nullptr, lane);
             cur ^= 1;
         }
         __syncwarp();                          // every lane has read its last list entry
