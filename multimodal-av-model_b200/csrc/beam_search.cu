@@ -640,12 +640,12 @@ __device__ __forceinline__ void topk_row(const BeamParams& p, const float* __res
                         gt += (ga + gb) + (gc + gd);
                     }
                 }
+                // equal values collide on the rank: both store to slot gt, and the one whose (unique) class index did not
+                // survive sees it (a match.any on the ranks is several hundred cycles of latency)
                 const bool top = (lane < count) && gt <= k;
-                const unsigned tm = __ballot_sync(kFullMask, top);
-                if (top) {
-                    tie = __popc(__match_any_sync(tm, gt)) > 1;
-                    tv[gt] = me.x; ti[gt] = __float_as_int(me.y);
-                }
+                if (top) { tv[gt] = me.x; ti[gt] = __float_as_int(me.y); }
+                __syncwarp();
+                tie = top && ti[gt] != __float_as_int(me.y);
             } else {
                 for (int i = lane; i < count; i += 32) {
                     const float2 me = cand[i];
