@@ -361,7 +361,8 @@ __device__ __forceinline__ int recur_step_enum32(const float tvv, const int tii,
         else bp_t[r] = bpe32;
     }
     __syncwarp();
-    const bool clash = (wr && lds_s32(sc_a + r * 4) != lane) || (in && s != s);
+    const int tag = lds_s32(sc_a + r * 4);             // r <= 32: inside the row for every lane, no branch around the load
+    const bool clash = (wr & (tag != lane)) | (in & (s != s));
     if (__any_sync(kFullMask, clash)) {                // ties (or NaNs): insertion-order tie-break, as the reference's stable sort
         r = 0;
         for (int q = 0; q < M; ++q) {
