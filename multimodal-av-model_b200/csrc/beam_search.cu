@@ -956,7 +956,7 @@ beam_fused_kernel(const BeamParams p) {
             if (t >= ready) {
                 int spins = 0;
                 while ((ready = fused_frames_ready<TW>(prog + buf * 8, i, lane)) <= t) {
-                    __nanosleep(32);
+                    __nanosleep(160);
                     if (++spins > (1 << 24)) __trap();
                 }
                 fence_acq_rel_cta();
