@@ -5,8 +5,10 @@
     beam_search_batch(log_probs[N,T,V], ...) -> list[list[int]]              new: one launch for a whole batch
 
 The reference decodes one utterance at a time from Python (model/trainer.py:229-242); the batched entry
-runs the per-frame top-k of all N*T rows at HBM speed, then one warp per utterance, and syncs once, only because a Python list is returned.  Token lists are
-bit-exact with the reference on CPU, including torch.topk's tie order.
+decodes a whole batch with one C call (csrc/beam_search.cu: one fused persistent kernel whose top-k warps feed
+recurrence warps through shared memory for up to 16 x SMs short utterances, a top-k pass over all N*T rows + one warp
+per utterance above that) and syncs once, only because a Python list is returned.  Token lists are bit-exact with the
+reference on CPU, including torch.topk's tie order.
 """
 from __future__ import annotations
 

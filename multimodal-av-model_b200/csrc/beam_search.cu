@@ -1,4 +1,4 @@
-// beam_search.cu — batched beam-search decode for sm_100a, one CTA (one warp) per utterance.
+// beam_search.cu — batched beam-search decode for sm_100a.
 //
 // Replaces simple_beam_search(log_probs[T,V], beam_width, blank) (/root/reference/beam_search.py:2-42),
 // which the reference calls once per utterance from a Python loop (model/trainer.py:229-242) at a cost
@@ -11,13 +11,18 @@
 //   * prune = stable sort by score descending (ties keep insertion order: beam-major, k-minor)
 //   * result = CTC collapse of beams[0] where `prev` is updated on every frame, blank included
 //
-// Per frame the warp (1) finds the top-(k+1) with a threshold pass (lane maxima -> (k+1)-th largest ->
-// compaction -> rank); when those k+1 values are pairwise distinct and NaN-free the top-k is unique and
-// any algorithm agrees with torch.  Otherwise (2) it runs the literal libstdc++ heap-select/sort-heap on
-// the shared-memory row (one lane owns the heap, the warp scans ahead with ballots).  (3) Only the
-// (b+1)(j+1) <= beam candidates can survive the prune (every (b',j') <= (b,j) sorts first), so <= ~beam*ln
-// candidates are ranked by counting, scores in fp64, back-pointers kept per frame.  Rows are staged
-// through a 3-deep cp.async ring so the T-step recurrence never waits on HBM.
+// Three routes over the same building blocks:
+//   * beam_fused_kernel   V in 513..832, <= 32 candidates, short utterances, up to 16 x SMs of them per call: persistent
+//                         CTAs, top-k warps feed recurrence warps through shared memory
+//   * beam_topk_kernel + beam_recur_kernel   V <= 1024: top-k of all N*T rows (one warp per row, row in registers), then
+//                         one warp per utterance over the [T,beam] lists
+//   * beam_search_kernel  any V: one warp per utterance does both, rows staged through a 3-deep cp.async ring
+// Per row the warp (1) finds the top-(k+1) with a threshold pass (lane maxima -> (k+1)-th largest -> compaction ->
+// rank); when those k+1 values are pairwise distinct and NaN-free the top-k is unique and any algorithm agrees with
+// torch.  Otherwise (2) it runs the literal libstdc++ heap-select/sort-heap (or nth_element + sort) on the
+// shared-memory row (one lane owns the heap, the warp scans ahead with ballots).  (3) Only the (b+1)(j+1) <= beam
+// candidates can survive the prune (every (b',j') <= (b,j) sorts first), so <= ~beam*ln(beam) candidates are ranked by
+// counting, scores in fp64, back-pointers kept per frame.
 #include "common.cuh"
 
 namespace avctc {
