@@ -429,10 +429,11 @@ def bench_beam(device, rank, world, iters=5, N=4096, T=150, beam=10, comparators
         _lib.check(L.avctc_beam_search(lp.data_ptr(), lp.stride(0), lp.stride(1), n, T, VOCAB, None, beam, BLANK,
                                        out.data_ptr(), ol.data_ptr(), None, None, ws.data_ptr(), wsb, st), "beam")
     t_k, _ = event_time(kernels, iters, 2, flush, device)
-    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    ROUTES = {0: "unsupported", 1: "single kernel (one warp per utterance)", 2: "two-phase (top-k pass, then recurrence)",
+              3: "fused top-k + recurrence kernel"}
 
-    def route(m):           # beam_search.cu: one fused kernel up to 16 x SMs short utterances per call, two kernels above
-        return "fused top-k + recurrence kernel" if m <= 16 * sms else "two-phase (top-k pass, then recurrence)"
+    def route(m):           # asked from the library (avctc_beam_route): the rule lives in csrc/beam_search.cu
+        return ROUTES[int(L.avctc_beam_route(m, T, VOCAB, beam))]
     sweep = {}
     if world == 1:          # what one rank decodes when the same 4096 utterances are sharded over 2 / 4 / 8 GPUs
         for m in (N // 2, N // 4, N // 8):

@@ -133,6 +133,13 @@ AVCTC_API int avctc_ctc_scale_grad(void* grad, int dtype, int T, int B, int V, c
  * (uncollapsed) best-beam-first paths dbg_paths[(n*beam + i)*T + t] (int32).
  * ---------------------------------------------------------------------------------------------- */
 AVCTC_API size_t avctc_beam_workspace_bytes(int N, int T, int V, int beam);
+/* Which kernels avctc_beam_search will launch for this shape on the current device (148 SMs assumed without one) and
+ * the current "beam_fused" / "beam_two_phase" knobs: host-side query, launches nothing. */
+#define AVCTC_BEAM_ROUTE_NONE 0       /* shape not supported */
+#define AVCTC_BEAM_ROUTE_SINGLE 1     /* one kernel, one warp per utterance does top-k and recurrence (V > 1024) */
+#define AVCTC_BEAM_ROUTE_TWO_PHASE 2  /* top-k kernel over all N*T rows, then the recurrence kernel */
+#define AVCTC_BEAM_ROUTE_FUSED 3      /* one persistent kernel: top-k warps feed recurrence warps through shared memory */
+AVCTC_API int avctc_beam_route(int N, int T, int V, int beam);
 AVCTC_API int avctc_beam_search(const float* log_probs, int64_t stride_n, int64_t stride_t, int N, int T, int V,
                       const int64_t* lengths, int beam, int blank,
                       int32_t* out_ids, int32_t* out_len, double* dbg_scores, int32_t* dbg_paths,

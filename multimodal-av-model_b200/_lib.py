@@ -33,6 +33,7 @@ SIGNATURES = {
                                         _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "avctc_ctc_scale_grad": (_i, [_vp, _i, _i, _i, _i, _vp, _i64, _vp]),
     "avctc_beam_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "avctc_beam_route": (_i, [_i, _i, _i, _i]),
     "avctc_beam_search": (_i, [_vp, _i64, _i64, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "avctc_gemm_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, ctypes.c_longlong, ctypes.c_longlong,
                              ctypes.c_longlong, _vp, _i, ctypes.c_float, _i, _vp]),
@@ -78,9 +79,7 @@ KERNELS = {"avctc_ctc_forward": 2, "avctc_ctc_reduce": 1, "avctc_ctc_backward": 
            "avctc_gemm_bf16": 1, "avctc_resample_forward": 2, "avctc_resample_backward": 1, "avctc_softmax_forward": 1,
            "avctc_softmax_backward": 1, "avctc_colsum": 1, "avctc_log_softmax_forward": 1,
            "avctc_log_softmax_backward": 1, "avctc_infonce_forward": 4, "avctc_infonce_backward": 2,
-           "avctc_ctc_head_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
-    "avctc_ctc_head_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "avctc_ctc_head_forward": 1, "avctc_ctc_head_backward": 3, "avctc_attention_forward": 1, "avctc_attention_backward": 1, "avctc_fusion_forward": 7, "avctc_fusion_backward": 8,
+           "avctc_ctc_head_forward": 1, "avctc_ctc_head_backward": 3, "avctc_attention_forward": 1, "avctc_attention_backward": 1, "avctc_fusion_forward": 7, "avctc_fusion_backward": 8,
            "avctc_bilstm_forward": 7, "avctc_bilstm_backward": 20}
 launch_count = 0
 
@@ -97,10 +96,18 @@ class _Counted:
         if n == 0:
             return fn
 
-        def call(*a):
-            global launch_count
-            launch_count += n
-            return fn(*a)
+        if name == "avctc_beam_search":         # 1 kernel on the fused / single-kernel routes, 2 on the two-phase route
+            route = self._cdll.avctc_beam_route
+
+            def call(*a):
+                global launch_count
+                launch_count += 2 if route(a[3], a[4], a[5], a[7]) == 2 else 1
+                return fn(*a)
+        else:
+            def call(*a):
+                global launch_count
+                launch_count += n
+                return fn(*a)
         object.__setattr__(self, name, call)
         return call
 

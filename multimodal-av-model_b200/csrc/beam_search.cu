@@ -1057,9 +1057,35 @@ static int launch_fused(const BeamParams& bp, size_t smem, int sms, cudaStream_t
     return (int)cudaGetLastError();
 }
 
+// "beam_fused" = 1 whenever eligible, 0 never, -1 (default) up to four utterances per resident CTA.  Measured
+// (profiles/r02_beam_fused_ab.txt): both routes are instruction-issue bound; the fused kernel hides the recurrence's
+// latency and saves a launch and the HBM round trip of the lists (1.2x at 1024 utterances, 1.25x at 512), but its
+// hand-off polling costs 13 % more instructions once every SM is saturated anyway (0.88x at 4096).
+static bool beam_use_fused(const BeamPlan& pl, int N, int sms) {
+    const int knob = avctc_tuning_get("beam_fused", -1);
+    return pl.fused_ok && (knob > 0 || (knob < 0 && N <= 16 * sms));
+}
+
+static int beam_sm_count() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        (void)cudaGetLastError();       // no device (host-side planning, tests): plan for a B200
+        sms = 148;
+    }
+    return sms;
+}
+
 }  // namespace avctc
 
 using namespace avctc;
+
+extern "C" int avctc_beam_route(int N, int T, int V, int beam) {
+    BeamPlan pl;
+    if (N <= 0 || T <= 0 || V <= 0 || beam < 1 || beam > V || !beam_plan(N, T, V, beam, &pl)) return AVCTC_BEAM_ROUTE_NONE;
+    if (!pl.two_phase) return AVCTC_BEAM_ROUTE_SINGLE;
+    if ((long long)N * T >= (1ll << 31)) return AVCTC_BEAM_ROUTE_NONE;
+    return beam_use_fused(pl, N, beam_sm_count()) ? AVCTC_BEAM_ROUTE_FUSED : AVCTC_BEAM_ROUTE_TWO_PHASE;
+}
 
 extern "C" size_t avctc_beam_workspace_bytes(int N, int T, int V, int beam) {
     BeamPlan pl;
@@ -1106,13 +1132,7 @@ extern "C" int avctc_beam_search(const float* log_probs, int64_t stride_n, int64
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        // fused kernel: "beam_fused" = 1 whenever eligible, 0 never, -1 (default) up to four utterances per resident CTA.
-        // Measured (profiles/r02_beam_fused_ab.txt): both routes are instruction-issue bound, the fused kernel hides the
-        // recurrence's latency and saves a launch and the HBM round trip of the lists (1.05x at 2048 utterances, 1.2x at
-        // 1024, 1.35x at 592), but its hand-off polling costs ~6 % more instructions once every SM is saturated anyway
-        // (0.93x at 4096).
-        const int fused_knob = avctc_tuning_get("beam_fused", -1);
-        if (pl.fused_ok && (fused_knob > 0 || (fused_knob < 0 && N <= 16 * sms))) {
+        if (beam_use_fused(pl, N, sms)) {
             int rc;
             if (need <= 25) {
                 if (V == 800) rc = launch_fused<25, 0>(bp, pl.smem_fused, sms, st);

@@ -56,8 +56,35 @@ def test_ctc_workspace_plan_and_tuning_knobs():
         assert lib.avctc_set_tuning(k.encode(), 1 if k not in ("ctc_k", "ctc_grad_warps", "gemm_dbg", "ctc_stamp") else 0) == 0, k
     assert lib.avctc_set_tuning(b"no_such_knob", 1) != 0
     for k, v in (("ctc_overlap", 1), ("ctc_ws", 1), ("ctc_lin", 1), ("pdl", 1), ("ctc_pf", 1), ("beam_fast", 1),
-                 ("beam_two_phase", 1), ("beam_pf", 1), ("lstm_tag", 1)):
+                 ("beam_two_phase", 1), ("beam_pf", 1), ("lstm_tag", 1), ("beam_fused", -1), ("beam_fused_grid", 0),
+                 ("lstm_groups", 0), ("ctc_stage", 1)):
         pkg._lib.set_tuning(k, v)                               # leave the defaults behind
+
+
+def test_beam_route_query():
+    """avctc_beam_route: the host-side rule that picks the decode kernels (no device needed: 148 SMs assumed)."""
+    import multimodal_av_model_b200 as pkg
+    lib = pkg._lib.lib()
+    NONE, SINGLE, TWO, FUSED = 0, 1, 2, 3
+    assert lib.avctc_beam_route(4096, 150, 800, 10) == TWO       # config 5 on one GPU: more than 16 x SMs utterances
+    assert lib.avctc_beam_route(2048, 150, 800, 10) == FUSED     # its shard at 2 GPUs
+    assert lib.avctc_beam_route(16, 150, 801, 10) == FUSED       # evaluate() of 8 pairs
+    assert lib.avctc_beam_route(16, 700, 801, 10) == TWO         # lists of 700 frames do not fit shared memory
+    assert lib.avctc_beam_route(16, 150, 1000, 10) == TWO        # 32 register slots per lane: top-k kernel only
+    assert lib.avctc_beam_route(16, 150, 500, 10) == TWO
+    assert lib.avctc_beam_route(16, 150, 800, 12) == TWO         # 35 candidates > one warp
+    assert lib.avctc_beam_route(16, 150, 2000, 10) == SINGLE     # rows too wide for registers
+    assert lib.avctc_beam_route(16, 150, 800, 33) == NONE and lib.avctc_beam_route(0, 150, 800, 10) == NONE
+    try:
+        pkg._lib.set_tuning("beam_fused", 0)
+        assert lib.avctc_beam_route(16, 150, 800, 10) == TWO
+        pkg._lib.set_tuning("beam_fused", 1)
+        assert lib.avctc_beam_route(4096, 150, 800, 10) == FUSED
+        pkg._lib.set_tuning("beam_two_phase", 0)
+        assert lib.avctc_beam_route(16, 150, 800, 10) == SINGLE
+    finally:
+        pkg._lib.set_tuning("beam_fused", -1)
+        pkg._lib.set_tuning("beam_two_phase", 1)
 
 
 def test_product_fails_loudly_without_gpu_tensor():

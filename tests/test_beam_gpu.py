@@ -218,6 +218,7 @@ def test_beam_auto_policy_is_value_neutral(fused_knobs):
     pkg = _pkg()
     g = torch.Generator(device="cuda").manual_seed(11)
     lp = (3 * torch.randn(700, 60, 800, generator=g, device="cuda")).log_softmax(-1)
+    assert pkg._lib.lib().avctc_beam_route(700, 60, 800, 10) == 3 and pkg._lib.lib().avctc_beam_route(4096, 150, 800, 10) == 2
     auto = pkg.beam_search_batch(lp, beam_width=10, blank=3)
     for forced in (0, 1):
         fused_knobs("beam_fused", forced)
